@@ -1,0 +1,121 @@
+/* zkfl.h -- C ABI of libzkfl.so, the B200 (sm_100a) Groth16/BN254 proving backend.
+ *
+ * Drop-in boundary: the reference (/root/reference) has no FFI of its own; its tests reach the
+ * prover by spawning the snarkjs / circom tool-chain (`runCommand`, tests/full_system_simulation.mjs:108-115).
+ * Each entry point below names the tool invocation (reference call site) it replaces.  A Node N-API
+ * addon, the Python host package and the CLI shim all bind exactly these symbols.
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success and a negative
+ * code on failure (message: zkfl_last_error()); no exception crosses the ABI; the caller owns all
+ * buffers; handles are opaque and released by the matching *_free.  A zkfl_ctx is bound to one CUDA
+ * device and is NOT thread-safe (one ctx per GPU per host thread).  There is no CPU fallback: without
+ * a usable CUDA device zkfl_ctx_create fails.
+ *
+ * Encodings: field elements are 32-byte little-endian canonical integers (the `.wtns` encoding);
+ * a proof is 256 bytes: pi_a (x,y) | pi_b (x.c0,x.c1,y.c0,y.c1) | pi_c (x,y), affine canonical
+ * little-endian -- the numbers snarkjs prints in proof.json.  `.zkey` / `.r1cs` are the iden3 binary
+ * formats snarkjs 0.7 reads and writes; `.zkwp` is this library's compiled witness program (the
+ * replacement for the circom-generated `<name>_js/<name>.wasm`).
+ */
+#ifndef ZKFL_H
+#define ZKFL_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct zkfl_ctx zkfl_ctx;
+typedef struct zkfl_circuit zkfl_circuit; /* compiled witness program (.zkwp)  ~ circom .wasm */
+typedef struct zkfl_zkey zkfl_zkey;       /* proving key resident in HBM       ~ snarkjs .zkey */
+typedef struct zkfl_r1cs zkfl_r1cs;       /* constraint system resident in HBM ~ circom .r1cs */
+
+#define ZKFL_OK 0
+#define ZKFL_ERR_ARG (-1)
+#define ZKFL_ERR_FORMAT (-2)
+#define ZKFL_ERR_CUDA (-3)
+#define ZKFL_ERR_NOMEM (-4)
+#define ZKFL_ERR_ASSERT (-5) /* a circuit `===` failed: circom's "Assert Failed" */
+
+const char* zkfl_last_error(void);
+const char* zkfl_version(void);
+
+/* ---- context ------------------------------------------------------------------------------- */
+int zkfl_ctx_create(int device, zkfl_ctx** out);
+void zkfl_ctx_free(zkfl_ctx* ctx);
+
+/* ---- artefacts ----------------------------------------------------------------------------- */
+/* replaces loading `<name>.wasm` in generate_witness.cjs (tests/full_system_simulation.mjs:760-762) */
+int zkfl_circuit_load(zkfl_ctx* ctx, const uint8_t* zkwp, size_t len, zkfl_circuit** out);
+void zkfl_circuit_free(zkfl_circuit* c);
+/* info[0..3] = n_wires, n_public, n_inputs, n_ops */
+int zkfl_circuit_info(const zkfl_circuit* c, uint32_t info[4]);
+
+/* replaces snarkjs reading `<name>_final.zkey` in `groth16 prove` (tests/full_system_simulation.mjs:773-775);
+ * parses the snarkjs layout and uploads coefficients and bases once */
+int zkfl_zkey_load(zkfl_ctx* ctx, const uint8_t* zkey, size_t len, zkfl_zkey** out);
+void zkfl_zkey_free(zkfl_zkey* z);
+/* info[0..2] = n_vars, n_public, domain_size */
+int zkfl_zkey_info(const zkfl_zkey* z, uint32_t info[3]);
+
+/* `.r1cs` for the constraint check the circom witness calculator performs at every `===` */
+int zkfl_r1cs_load(zkfl_ctx* ctx, const uint8_t* r1cs, size_t len, zkfl_r1cs** out);
+void zkfl_r1cs_free(zkfl_r1cs* r);
+
+/* ---- witness: `node generate_witness.cjs wasm input.json out.wtns`, `snarkjs wtns calculate`
+ *      (tests/full_system_simulation.mjs:760-762, tests/test_secureagg.cjs:108-118), batched ------- */
+/* inputs: B x n_inputs field elements in the circuit's input-declaration order (the flattened
+ * input.json); wtns_out: B x n_wires field elements (section 2 of B `.wtns` files).
+ * If r1cs != NULL every constraint is checked on the GPU and first_bad[b] (B entries, may be NULL)
+ * receives the first violated constraint index or 0xFFFFFFFF; any violation -> ZKFL_ERR_ASSERT. */
+int zkfl_wtns_calculate_batch(zkfl_ctx* ctx, const zkfl_circuit* c, const zkfl_r1cs* r1cs, const uint8_t* inputs,
+                              int B, uint8_t* wtns_out, uint32_t* first_bad);
+int zkfl_r1cs_check_batch(zkfl_ctx* ctx, const zkfl_r1cs* r1cs, const uint8_t* wtns, int B, uint32_t* first_bad);
+
+/* ---- prove: `snarkjs groth16 prove zkey wtns proof.json public.json`
+ *      (tests/full_system_simulation.mjs:773-775 and five more call sites), batched ---- */
+/* wtns: B x n_vars; rs: B x 64 bytes (r then s, canonical, < r) or NULL for OS randomness
+ * (snarkjs draws r,s from a CSPRNG); proofs_out: B x 256; publics_out: B x n_public x 32 (may be NULL) */
+int zkfl_groth16_prove_batch(zkfl_ctx* ctx, const zkfl_zkey* z, const uint8_t* wtns, const uint8_t* rs, int B,
+                             uint8_t* proofs_out, uint8_t* publics_out);
+/* `snarkjs.groth16.fullProve(input, wasm, zkey)` batched: witness stays in HBM between the two steps */
+int zkfl_groth16_full_prove_batch(zkfl_ctx* ctx, const zkfl_circuit* c, const zkfl_zkey* z, const uint8_t* inputs,
+                                  const uint8_t* rs, int B, uint8_t* proofs_out, uint8_t* publics_out);
+/* device-resident variant for steady-state measurement: stage() copies inputs and rs to HBM once,
+ * run() proves from HBM leaving proofs in HBM, fetch() copies B x 256 proof bytes back. */
+int zkfl_full_prove_stage(zkfl_ctx* ctx, const zkfl_circuit* c, const zkfl_zkey* z, const uint8_t* inputs,
+                          const uint8_t* rs, int B);
+int zkfl_full_prove_run(zkfl_ctx* ctx, const zkfl_circuit* c, const zkfl_zkey* z, int B);
+int zkfl_full_prove_fetch(zkfl_ctx* ctx, int B, uint8_t* proofs_out);
+
+/* ---- standalone multi-scalar multiplication (BASELINE.json: "G1 MSM pts/s at 2^20") ----------- */
+/* bases: n affine points, Montgomery little-endian (zkey point layout, 64 B G1 / 128 B G2);
+ * scalars: n x 32 B canonical; out: affine canonical (64 / 128 B). */
+int zkfl_g1_msm(zkfl_ctx* ctx, const uint8_t* bases, const uint8_t* scalars, size_t n, uint8_t out[64]);
+int zkfl_g2_msm(zkfl_ctx* ctx, const uint8_t* bases, const uint8_t* scalars, size_t n, uint8_t out[128]);
+/* resident variant: bases uploaded once (they are per-circuit constants), then repeated MSMs */
+int zkfl_msm_bases_load(zkfl_ctx* ctx, const uint8_t* bases, size_t n, int group /*1|2*/, void** handle);
+void zkfl_msm_bases_free(void* handle);
+int zkfl_msm_run(zkfl_ctx* ctx, void* handle, const uint8_t* scalars /* host, or NULL = reuse staged */, size_t n,
+                 uint8_t* out);
+
+/* ---- setup support: `snarkjs groth16 setup` (tests/full_system_simulation.mjs:714-717) needs
+ *      k_i * G for every key scalar; out = affine Montgomery (zkey point layout) ------------------ */
+int zkfl_g1_mul_generator(zkfl_ctx* ctx, const uint8_t* scalars, size_t n, uint8_t* out /* n x 64 */);
+int zkfl_g2_mul_generator(zkfl_ctx* ctx, const uint8_t* scalars, size_t n, uint8_t* out /* n x 128 */);
+
+/* ---- measurement --------------------------------------------------------------------------- */
+/* number of CUDA kernels this library has launched in this process */
+uint64_t zkfl_launch_count(void);
+/* per-stage device timing (CUDA events on the context's stream). enable, run, then read a text
+ * table "stage ms launches\n..." into buf. */
+int zkfl_prof_enable(zkfl_ctx* ctx, int on);
+int zkfl_prof_read(zkfl_ctx* ctx, char* buf, size_t cap);
+/* integer-pipe microbenchmark: n threads x iters x 2 dependent Montgomery products; returns ms */
+int zkfl_bench_modmul(zkfl_ctx* ctx, size_t n_threads, uint32_t iters, float* ms_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZKFL_H */

@@ -1,0 +1,208 @@
+"""Host-side driver of libzkfl.so: one Prover per GPU (one process per GPU when sharding).
+
+Batch-first: the GPU path proves B client instances of one circuit in lock-step (shared bases,
+batch-minor witness layout); `B = 1` is the snarkjs single-proof case.
+"""
+from __future__ import annotations
+
+import ctypes
+import json
+import os
+
+from . import _lib
+from .circuits import CompiledCircuit, build_circuit
+from .formats import FR
+
+
+def _fe_bytes(vals) -> bytes:
+    return b"".join(int(v).to_bytes(32, "little") for v in vals)
+
+
+class Circuit:
+    """A compiled circuit resident on the GPU (witness program + optional R1CS for `===` checks)."""
+
+    def __init__(self, prover: "Prover", zkwp: bytes, r1cs: bytes | None = None, compiled: CompiledCircuit | None = None):
+        self.prover = prover
+        lib = prover.lib
+        self.handle = ctypes.c_void_p()
+        self._zkwp = zkwp
+        _lib.check(lib.zkfl_circuit_load(prover.ctx, _lib.as_ptr(zkwp), len(zkwp), ctypes.byref(self.handle)))
+        info = (ctypes.c_uint32 * 4)()
+        _lib.check(lib.zkfl_circuit_info(self.handle, info))
+        self.n_wires, self.n_public, self.n_inputs, self.n_ops = info[0], info[1], info[2], info[3]
+        self.r1cs_handle = ctypes.c_void_p()
+        if r1cs is not None:
+            _lib.check(lib.zkfl_r1cs_load(prover.ctx, _lib.as_ptr(r1cs), len(r1cs), ctypes.byref(self.r1cs_handle)))
+        self.compiled = compiled
+        if compiled is not None:
+            self.meta = compiled.input_map()
+        else:
+            from .formats import read_container
+            self.meta = json.loads(read_container(zkwp, b"zkwp")[8].decode())
+
+    def flatten_input(self, obj: dict) -> list[int]:
+        """input.json object -> flat signal list (circom semantics: decimal strings, negatives wrap mod r)."""
+        out = []
+        for spec in self.meta["inputs"]:
+            name, shape = spec["name"], spec["shape"]
+            if name not in obj:
+                raise KeyError(f"Signal not found: {name}")
+            flat = []
+
+            def walk(v, dims):
+                if not dims:
+                    if isinstance(v, (list, tuple)):
+                        raise ValueError(f"Too many values for input signal {name}")
+                    flat.append(int(v) % FR)
+                    return
+                if not isinstance(v, (list, tuple)) or len(v) != dims[0]:
+                    raise ValueError(f"Wrong dimensions for input signal {name}")
+                for x in v:
+                    walk(x, dims[1:])
+
+            walk(obj[name], shape)
+            out.extend(flat)
+        return out
+
+    def pack_inputs(self, objs) -> bytes:
+        return b"".join(_fe_bytes(self.flatten_input(o)) for o in objs)
+
+    def close(self):
+        if self.handle:
+            self.prover.lib.zkfl_circuit_free(self.handle)
+            self.handle = ctypes.c_void_p()
+        if self.r1cs_handle:
+            self.prover.lib.zkfl_r1cs_free(self.r1cs_handle)
+            self.r1cs_handle = ctypes.c_void_p()
+
+
+class Zkey:
+    def __init__(self, prover: "Prover", data: bytes):
+        self.prover = prover
+        self.handle = ctypes.c_void_p()
+        _lib.check(prover.lib.zkfl_zkey_load(prover.ctx, _lib.as_ptr(data), len(data), ctypes.byref(self.handle)))
+        info = (ctypes.c_uint32 * 3)()
+        _lib.check(prover.lib.zkfl_zkey_info(self.handle, info))
+        self.n_vars, self.n_public, self.domain = info[0], info[1], info[2]
+
+    def close(self):
+        if self.handle:
+            self.prover.lib.zkfl_zkey_free(self.handle)
+            self.handle = ctypes.c_void_p()
+
+
+class Prover:
+    def __init__(self, device: int = 0):
+        self.lib = _lib.load()
+        self.ctx = ctypes.c_void_p()
+        _lib.check(self.lib.zkfl_ctx_create(device, ctypes.byref(self.ctx)))
+        self.device = device
+
+    def close(self):
+        if self.ctx:
+            self.lib.zkfl_ctx_free(self.ctx)
+            self.ctx = ctypes.c_void_p()
+
+    # ---------------------------------------------------------------- artefacts
+    def load_circuit(self, name_or_compiled, check_constraints: bool = True) -> Circuit:
+        cc = build_circuit(name_or_compiled) if isinstance(name_or_compiled, str) else name_or_compiled
+        return Circuit(self, cc.program_bytes(), cc.r1cs_bytes() if check_constraints else None, cc)
+
+    def load_circuit_files(self, zkwp_path: str, r1cs_path: str | None = None) -> Circuit:
+        zkwp = open(zkwp_path, "rb").read()
+        r1cs = open(r1cs_path, "rb").read() if r1cs_path and os.path.exists(r1cs_path) else None
+        return Circuit(self, zkwp, r1cs)
+
+    def load_zkey(self, data: bytes) -> Zkey:
+        return Zkey(self, data)
+
+    def new_zkey(self, r1cs_bytes: bytes, seed: bytes) -> bytes:
+        from .zkey_setup import new_zkey
+        return new_zkey(self, r1cs_bytes, seed)
+
+    # ---------------------------------------------------------------- witness
+    def calculate_witness(self, circuit: Circuit, inputs, check: bool = True) -> list[bytes]:
+        """inputs: list of input.json objects (or packed bytes). Returns one canonical witness (n_wires*32 B) per client."""
+        packed = inputs if isinstance(inputs, (bytes, bytearray)) else circuit.pack_inputs(inputs)
+        B = len(packed) // (32 * circuit.n_inputs)
+        out = ctypes.create_string_buffer(32 * circuit.n_wires * B)
+        bad = (ctypes.c_uint32 * B)()
+        r1 = circuit.r1cs_handle if (check and circuit.r1cs_handle) else None
+        _lib.check(self.lib.zkfl_wtns_calculate_batch(self.ctx, circuit.handle, r1, _lib.as_ptr(packed), B, out, bad))
+        sz = 32 * circuit.n_wires
+        return [out.raw[b * sz:(b + 1) * sz] for b in range(B)]
+
+    def check_witness(self, circuit: Circuit, wtns: list[bytes]):
+        B = len(wtns)
+        bad = (ctypes.c_uint32 * B)()
+        rc = self.lib.zkfl_r1cs_check_batch(self.ctx, circuit.r1cs_handle, _lib.as_ptr(b"".join(wtns)), B, bad)
+        return rc, list(bad)
+
+    # ---------------------------------------------------------------- prove
+    @staticmethod
+    def _pack_rs(rs, B):
+        if rs is None:
+            return None
+        assert len(rs) == B
+        return b"".join(int(r).to_bytes(32, "little") + int(s).to_bytes(32, "little") for r, s in rs)
+
+    def prove(self, zkey: Zkey, wtns: list[bytes], rs=None):
+        """-> (list of 256-byte proofs, list of public-signal byte strings)"""
+        B = len(wtns)
+        proofs = ctypes.create_string_buffer(256 * B)
+        pubs = ctypes.create_string_buffer(max(32 * zkey.n_public * B, 1))
+        _lib.check(self.lib.zkfl_groth16_prove_batch(self.ctx, zkey.handle, _lib.as_ptr(b"".join(wtns)),
+                                                     _lib.as_ptr(self._pack_rs(rs, B)), B, proofs, pubs))
+        psz = 32 * zkey.n_public
+        return ([proofs.raw[256 * b:256 * (b + 1)] for b in range(B)], [pubs.raw[psz * b:psz * (b + 1)] for b in range(B)])
+
+    def full_prove(self, circuit: Circuit, zkey: Zkey, inputs, rs=None):
+        packed = inputs if isinstance(inputs, (bytes, bytearray)) else circuit.pack_inputs(inputs)
+        B = len(packed) // (32 * circuit.n_inputs)
+        proofs = ctypes.create_string_buffer(256 * B)
+        pubs = ctypes.create_string_buffer(max(32 * zkey.n_public * B, 1))
+        _lib.check(self.lib.zkfl_groth16_full_prove_batch(self.ctx, circuit.handle, zkey.handle, _lib.as_ptr(packed),
+                                                          _lib.as_ptr(self._pack_rs(rs, B)), B, proofs, pubs))
+        psz = 32 * zkey.n_public
+        return ([proofs.raw[256 * b:256 * (b + 1)] for b in range(B)], [pubs.raw[psz * b:psz * (b + 1)] for b in range(B)])
+
+    # ---------------------------------------------------------------- MSM / setup support
+    def g1_msm(self, bases: bytes, scalars: bytes) -> bytes:
+        out = ctypes.create_string_buffer(64)
+        _lib.check(self.lib.zkfl_g1_msm(self.ctx, _lib.as_ptr(bases), _lib.as_ptr(scalars), len(scalars) // 32, out))
+        return out.raw
+
+    def g2_msm(self, bases: bytes, scalars: bytes) -> bytes:
+        out = ctypes.create_string_buffer(128)
+        _lib.check(self.lib.zkfl_g2_msm(self.ctx, _lib.as_ptr(bases), _lib.as_ptr(scalars), len(scalars) // 32, out))
+        return out.raw
+
+    def g1_mul_generator(self, scalars) -> bytes:
+        sc = scalars if isinstance(scalars, (bytes, bytearray)) else _fe_bytes(scalars)
+        n = len(sc) // 32
+        out = ctypes.create_string_buffer(64 * n)
+        _lib.check(self.lib.zkfl_g1_mul_generator(self.ctx, _lib.as_ptr(sc), n, out))
+        return out.raw
+
+    def g2_mul_generator(self, scalars) -> bytes:
+        sc = scalars if isinstance(scalars, (bytes, bytearray)) else _fe_bytes(scalars)
+        n = len(sc) // 32
+        out = ctypes.create_string_buffer(128 * n)
+        _lib.check(self.lib.zkfl_g2_mul_generator(self.ctx, _lib.as_ptr(sc), n, out))
+        return out.raw
+
+    # ---------------------------------------------------------------- measurement
+    def prof_enable(self, on: bool = True):
+        _lib.check(self.lib.zkfl_prof_enable(self.ctx, 1 if on else 0))
+
+    def prof_read(self) -> dict:
+        buf = ctypes.create_string_buffer(1 << 16)
+        _lib.check(self.lib.zkfl_prof_read(self.ctx, buf, len(buf)))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, ms, launches, calls = line.split()
+            out[name] = {"ms": float(ms), "launches": int(launches), "calls": int(calls)}
+        return out
+
+    def launch_count(self) -> int:
+        return int(self.lib.zkfl_launch_count())

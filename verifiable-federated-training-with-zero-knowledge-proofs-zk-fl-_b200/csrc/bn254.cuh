@@ -1,0 +1,229 @@
+// BN254 arithmetic for the sm_100a kernels: Fq / Fr in 8 x 32-bit-limb Montgomery form
+// (R = 2^256, the representation the snarkjs `.zkey` stores its points in -- SURVEY A.5),
+// Fq2 = Fq[u]/(u^2+1), and the short-Weierstrass group law in XYZZ coordinates
+// (x = X/ZZ, y = Y/ZZZ, ZZ^3 = ZZZ^2; infinity <=> ZZ = 0) templated over the coordinate field.
+// The integer pipe (IMAD) is the bound for everything in here; no tensor-core shape exists.
+#pragma once
+#include "zkfl_rt.h"
+
+namespace zk {
+
+// ------------------------------------------------------------------------------ parameters
+struct FqP {
+  static ZK_HD uint32_t mod(int i) {
+    constexpr uint32_t m[8] = {0xd87cfd47u, 0x3c208c16u, 0x6871ca8du, 0x97816a91u, 0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
+    return m[i];
+  }
+  static ZK_HD uint32_t r2(int i) {
+    constexpr uint32_t m[8] = {0x538afa89u, 0xf32cfc5bu, 0xd44501fbu, 0xb5e71911u, 0x0a417ff6u, 0x47ab1effu, 0xcab8351fu, 0x06d89f71u};
+    return m[i];
+  }
+  static ZK_HD uint32_t one(int i) {  // R mod q
+    constexpr uint32_t m[8] = {0xc58f0d9du, 0xd35d438du, 0xf5c70b3du, 0x0a78eb28u, 0x7879462cu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u};
+    return m[i];
+  }
+  static ZK_HD uint32_t inv() { return 0xe4866389u; }  // -q^-1 mod 2^32
+};
+struct FrP {
+  static ZK_HD uint32_t mod(int i) {
+    constexpr uint32_t m[8] = {0xf0000001u, 0x43e1f593u, 0x79b97091u, 0x2833e848u, 0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
+    return m[i];
+  }
+  static ZK_HD uint32_t r2(int i) {
+    constexpr uint32_t m[8] = {0xae216da7u, 0x1bb8e645u, 0xe35c59e3u, 0x53fe3ab1u, 0x53bb8085u, 0x8c49833du, 0x7f4e44a5u, 0x0216d0b1u};
+    return m[i];
+  }
+  static ZK_HD uint32_t one(int i) {  // R mod r
+    constexpr uint32_t m[8] = {0x4ffffffbu, 0xac96341cu, 0x9f60cd29u, 0x36fc7695u, 0x7879462eu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u};
+    return m[i];
+  }
+  static ZK_HD uint32_t inv() { return 0xefffffffu; }
+};
+
+// ------------------------------------------------------------------------------ prime field
+template <class P>
+struct alignas(16) Fp {
+  uint32_t v[8];
+
+  static ZK_HD Fp zero() { Fp r; ZK_UNROLL for (int i = 0; i < 8; i++) r.v[i] = 0; return r; }
+  static ZK_HD Fp one() { Fp r; ZK_UNROLL for (int i = 0; i < 8; i++) r.v[i] = P::one(i); return r; }
+  static ZK_HD Fp r2() { Fp r; ZK_UNROLL for (int i = 0; i < 8; i++) r.v[i] = P::r2(i); return r; }
+  ZK_HD bool is_zero() const { uint32_t o = 0; ZK_UNROLL for (int i = 0; i < 8; i++) o |= v[i]; return o == 0; }
+  ZK_HD bool operator==(const Fp& b) const { uint32_t o = 0; ZK_UNROLL for (int i = 0; i < 8; i++) o |= v[i] ^ b.v[i]; return o == 0; }
+
+  // r = t - mod if t >= mod else t   (t < 2*mod)
+  static ZK_HD Fp reduce_once(const uint32_t* t) {
+    uint32_t s[8]; uint64_t bw = 0;
+    ZK_UNROLL for (int i = 0; i < 8; i++) { uint64_t d = (uint64_t)t[i] - P::mod(i) - bw; s[i] = (uint32_t)d; bw = (d >> 32) & 1; }
+    Fp r; uint32_t keep = (uint32_t)0 - (uint32_t)bw;  // all ones when t < mod
+    ZK_UNROLL for (int i = 0; i < 8; i++) r.v[i] = (t[i] & keep) | (s[i] & ~keep);
+    return r;
+  }
+  friend ZK_HD Fp operator+(const Fp& a, const Fp& b) {
+    uint32_t t[8]; uint64_t c = 0;
+    ZK_UNROLL for (int i = 0; i < 8; i++) { c += (uint64_t)a.v[i] + b.v[i]; t[i] = (uint32_t)c; c >>= 32; }
+    return reduce_once(t);  // a + b < 2^255: no carry out
+  }
+  friend ZK_HD Fp operator-(const Fp& a, const Fp& b) {
+    uint32_t t[8]; uint64_t bw = 0;
+    ZK_UNROLL for (int i = 0; i < 8; i++) { uint64_t d = (uint64_t)a.v[i] - b.v[i] - bw; t[i] = (uint32_t)d; bw = (d >> 32) & 1; }
+    uint32_t msk = (uint32_t)0 - (uint32_t)bw; uint64_t c = 0; Fp r;
+    ZK_UNROLL for (int i = 0; i < 8; i++) { c += (uint64_t)t[i] + (P::mod(i) & msk); r.v[i] = (uint32_t)c; c >>= 32; }
+    return r;
+  }
+  ZK_HD Fp neg() const { return zero() - *this; }
+  ZK_HD Fp dbl() const { return *this + *this; }
+
+  // Montgomery product a*b/R, CIOS; p < 2^254 keeps the running value in 9 words.
+  friend ZK_HD Fp operator*(const Fp& a, const Fp& b) {
+    uint32_t t[9];
+    ZK_UNROLL for (int i = 0; i < 9; i++) t[i] = 0;
+    ZK_UNROLL for (int i = 0; i < 8; i++) {
+      uint64_t c = 0;
+      const uint32_t bi = b.v[i];
+      ZK_UNROLL for (int j = 0; j < 8; j++) { c += (uint64_t)a.v[j] * bi + t[j]; t[j] = (uint32_t)c; c >>= 32; }
+      c += t[8]; t[8] = (uint32_t)c;
+      const uint32_t m = t[0] * P::inv();
+      c = (uint64_t)m * P::mod(0) + t[0]; c >>= 32;
+      ZK_UNROLL for (int j = 1; j < 8; j++) { c += (uint64_t)m * P::mod(j) + t[j]; t[j - 1] = (uint32_t)c; c >>= 32; }
+      c += t[8]; t[7] = (uint32_t)c; t[8] = (uint32_t)(c >> 32);
+    }
+    return reduce_once(t);
+  }
+  ZK_HD Fp sqr() const { return *this * *this; }
+  ZK_HD Fp to_mont() const { return *this * r2(); }
+  ZK_HD Fp from_mont() const { Fp o = zero(); o.v[0] = 1; return *this * o; }
+
+  ZK_HD Fp inv() const {  // Fermat, exponent p - 2 (setup / affine conversion only)
+    Fp r = one();
+    ZK_NOUNROLL for (int i = 253; i >= 0; i--) {
+      r = r.sqr();
+      uint32_t w = P::mod(i >> 5);
+      if ((i >> 5) == 0) w -= 2;  // mod(0) is odd and >= 3: no borrow
+      if ((w >> (i & 31)) & 1) r = r * *this;
+    }
+    return r;
+  }
+};
+typedef Fp<FqP> Fq;
+typedef Fp<FrP> Fr;
+
+// ------------------------------------------------------------------------------ Fq2
+struct alignas(16) Fq2 {
+  Fq a, b;  // a + b*u
+  static ZK_HD Fq2 zero() { Fq2 r; r.a = Fq::zero(); r.b = Fq::zero(); return r; }
+  static ZK_HD Fq2 one() { Fq2 r; r.a = Fq::one(); r.b = Fq::zero(); return r; }
+  ZK_HD bool is_zero() const { return a.is_zero() && b.is_zero(); }
+  ZK_HD bool operator==(const Fq2& o) const { return a == o.a && b == o.b; }
+  friend ZK_HD Fq2 operator+(const Fq2& x, const Fq2& y) { Fq2 r; r.a = x.a + y.a; r.b = x.b + y.b; return r; }
+  friend ZK_HD Fq2 operator-(const Fq2& x, const Fq2& y) { Fq2 r; r.a = x.a - y.a; r.b = x.b - y.b; return r; }
+  ZK_HD Fq2 neg() const { Fq2 r; r.a = a.neg(); r.b = b.neg(); return r; }
+  ZK_HD Fq2 dbl() const { Fq2 r; r.a = a.dbl(); r.b = b.dbl(); return r; }
+  friend ZK_HD Fq2 operator*(const Fq2& x, const Fq2& y) {
+    Fq aa = x.a * y.a, bb = x.b * y.b, s = (x.a + x.b) * (y.a + y.b);
+    Fq2 r; r.a = aa - bb; r.b = s - aa - bb; return r;
+  }
+  ZK_HD Fq2 sqr() const { Fq t = a * b; Fq2 r; r.a = (a + b) * (a - b); r.b = t.dbl(); return r; }
+  ZK_HD Fq2 inv() const { Fq d = (a.sqr() + b.sqr()).inv(); Fq2 r; r.a = a * d; r.b = (b * d).neg(); return r; }
+  ZK_HD Fq2 from_mont() const { Fq2 r; r.a = a.from_mont(); r.b = b.from_mont(); return r; }
+};
+
+// ------------------------------------------------------------------------------ curve points
+template <class F> struct alignas(16) Affine {
+  F x, y;  // Montgomery coordinates; (0,0) encodes infinity (zkey convention)
+  ZK_HD bool is_inf() const { return x.is_zero() && y.is_zero(); }
+};
+template <class F> struct alignas(16) Xyzz {
+  F X, Y, ZZ, ZZZ;
+  static ZK_HD Xyzz infinity() { Xyzz r; r.X = F::zero(); r.Y = F::zero(); r.ZZ = F::zero(); r.ZZZ = F::zero(); return r; }
+  ZK_HD bool is_inf() const { return ZZ.is_zero(); }
+  static ZK_HD Xyzz from_affine(const Affine<F>& p) {
+    if (p.is_inf()) return infinity();
+    Xyzz r; r.X = p.x; r.Y = p.y; r.ZZ = F::one(); r.ZZZ = F::one(); return r;
+  }
+};
+
+template <class F> ZK_HD Xyzz<F> xyzz_dbl(const Xyzz<F>& p) {  // dbl-2008-s-1, a = 0
+  if (p.is_inf()) return p;
+  F U = p.Y.dbl(), V = U.sqr(), W = U * V, S = p.X * V;
+  F M = p.X.sqr(); M = M.dbl() + M;
+  Xyzz<F> r;
+  r.X = M.sqr() - S.dbl();
+  r.Y = M * (S - r.X) - W * p.Y;
+  r.ZZ = V * p.ZZ;
+  r.ZZZ = W * p.ZZZ;
+  return r;
+}
+template <class F> ZK_HD Xyzz<F> xyzz_dbl_affine(const Affine<F>& p) {  // mdbl-2008-s-1
+  F U = p.y.dbl(), V = U.sqr(), W = U * V, S = p.x * V;
+  F M = p.x.sqr(); M = M.dbl() + M;
+  Xyzz<F> r;
+  r.X = M.sqr() - S.dbl();
+  r.Y = M * (S - r.X) - W * p.y;
+  r.ZZ = V;
+  r.ZZZ = W;
+  return r;
+}
+// acc += q (affine, not infinity unless flagged); `negate` flips q first
+template <class F> ZK_HD void xyzz_madd(Xyzz<F>& acc, const Affine<F>& q0, bool negate) {  // madd-2008-s
+  if (q0.is_inf()) return;
+  Affine<F> q = q0;
+  if (negate) q.y = q.y.neg();
+  if (acc.is_inf()) { acc = Xyzz<F>::from_affine(q); return; }
+  F U2 = q.x * acc.ZZ, S2 = q.y * acc.ZZZ;
+  F Pp = U2 - acc.X, Rr = S2 - acc.Y;
+  if (Pp.is_zero()) {
+    if (Rr.is_zero()) acc = xyzz_dbl_affine(q); else acc = Xyzz<F>::infinity();
+    return;
+  }
+  F PP = Pp.sqr(), PPP = Pp * PP, Qq = acc.X * PP;
+  F X3 = Rr.sqr() - PPP - Qq.dbl();
+  acc.Y = Rr * (Qq - X3) - acc.Y * PPP;
+  acc.X = X3;
+  acc.ZZ = acc.ZZ * PP;
+  acc.ZZZ = acc.ZZZ * PPP;
+}
+template <class F> ZK_HD void xyzz_add(Xyzz<F>& acc, const Xyzz<F>& q) {  // add-2008-s
+  if (q.is_inf()) return;
+  if (acc.is_inf()) { acc = q; return; }
+  F U1 = acc.X * q.ZZ, U2 = q.X * acc.ZZ, S1 = acc.Y * q.ZZZ, S2 = q.Y * acc.ZZZ;
+  F Pp = U2 - U1, Rr = S2 - S1;
+  if (Pp.is_zero()) {
+    if (Rr.is_zero()) acc = xyzz_dbl(acc); else acc = Xyzz<F>::infinity();
+    return;
+  }
+  F PP = Pp.sqr(), PPP = Pp * PP, Qq = U1 * PP;
+  F X3 = Rr.sqr() - PPP - Qq.dbl();
+  acc.Y = Rr * (Qq - X3) - S1 * PPP;
+  acc.X = X3;
+  acc.ZZ = acc.ZZ * q.ZZ * PP;
+  acc.ZZZ = acc.ZZZ * q.ZZZ * PPP;
+}
+template <class F> ZK_HD Xyzz<F> xyzz_neg(const Xyzz<F>& p) { Xyzz<F> r = p; r.Y = p.Y.neg(); return r; }
+
+// Montgomery-form affine; infinity -> (0,0)
+template <class F> ZK_HD Affine<F> xyzz_to_affine(const Xyzz<F>& p) {
+  Affine<F> r;
+  if (p.is_inf()) { r.x = F::zero(); r.y = F::zero(); return r; }
+  F i3 = p.ZZZ.inv();
+  F i2 = p.ZZ.sqr() * i3.sqr();  // 1/ZZ = ZZ^2 / ZZZ^2
+  r.x = p.X * i2;
+  r.y = p.Y * i3;
+  return r;
+}
+// k * p, k = 8 canonical little-endian words (< 2^254)
+template <class F> ZK_HD Xyzz<F> xyzz_scalar_mul(const Xyzz<F>& p, const uint32_t* k) {
+  Xyzz<F> r = Xyzz<F>::infinity();
+  ZK_NOUNROLL for (int i = 253; i >= 0; i--) {
+    r = xyzz_dbl(r);
+    if ((k[i >> 5] >> (i & 31)) & 1) xyzz_add(r, p);
+  }
+  return r;
+}
+
+typedef Affine<Fq> G1Affine;
+typedef Affine<Fq2> G2Affine;
+typedef Xyzz<Fq> G1Xyzz;
+typedef Xyzz<Fq2> G2Xyzz;
+
+}  // namespace zk

@@ -1,0 +1,444 @@
+// sm_100a kernels of the Groth16 proving path.
+//
+// Data layout in HBM: everything that has one value per client proof is stored batch-minor,
+// `x[element][b]` with b < B the proof index ("SoA across proofs").  A warp therefore touches
+// 32 consecutive 32-byte field elements (1 KiB, fully coalesced) for ANY element stride, which
+// makes every NTT stage, the sparse A.w/B.w products and the witness program coalesced without
+// shared-memory staging; per-element constants (twiddles, matrix coefficients, round constants)
+// are warp-uniform broadcast loads.  Bases (zkey points) are shared by all proofs of a batch and
+// stay L2-resident (a few MB per circuit).
+//
+// All kernels are sync-free one-thread-per-item kernels: the bound is the integer pipe (IMAD) for
+// the group law / Montgomery products and HBM for the NTT passes; tensor cores do not apply
+// (no dense contraction anywhere on the path).
+#pragma once
+#include "bn254.cuh"
+
+namespace zk {
+
+#ifndef ZKFL_EMUL
+#define ZK_ATOMIC_MIN(p, v) atomicMin((p), (v))
+#else
+static inline void zk_atomic_min_u32(uint32_t* p, uint32_t v) {
+  uint32_t cur = __atomic_load_n(p, __ATOMIC_RELAXED);
+  while (v < cur && !__atomic_compare_exchange_n(p, &cur, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+}
+#define ZK_ATOMIC_MIN(p, v) zk_atomic_min_u32((p), (v))
+#endif
+
+// ================================================================================ layout helpers
+// host layout [b][e] (what .wtns / the C ABI use)  ->  device layout [e][b]
+ZK_GLOBAL void k_aos_to_soa(const Fr* __restrict__ src, Fr* __restrict__ dst, uint32_t n_elem, uint32_t B,
+                            uint32_t dst_elem_off) {
+  size_t tid = ZK_TID;
+  if (tid >= (size_t)n_elem * B) return;
+  uint32_t e = (uint32_t)(tid / B), b = (uint32_t)(tid % B);
+  dst[(size_t)(e + dst_elem_off) * B + b] = src[(size_t)b * n_elem + e];
+}
+ZK_GLOBAL void k_soa_to_aos(const Fr* __restrict__ src, Fr* __restrict__ dst, uint32_t n_elem, uint32_t B) {
+  size_t tid = ZK_TID;
+  if (tid >= (size_t)n_elem * B) return;
+  uint32_t e = (uint32_t)(tid / B), b = (uint32_t)(tid % B);
+  dst[(size_t)b * n_elem + e] = src[(size_t)e * B + b];
+}
+
+// ================================================================================ W1: batched witness evaluator
+struct PoseidonDev {
+  uint32_t rounds, rp;
+  const Fr* C;  // rounds*t round constants, Montgomery
+  const Fr* M;  // t*t MDS, row-major, Montgomery
+};
+struct ProgramDev {
+  uint32_t n_wires, n_inputs, n_ops;
+  const uint32_t* ops;       // 5 words per op
+  const uint32_t* lc_off;
+  const uint32_t* lc_wire;
+  const Fr* lc_coef;         // coef * R^2: coef (*) canonical witness = Montgomery(coef * w)
+  const uint32_t* pos_in;
+  PoseidonDev pk[18];
+};
+
+ZK_D Fr lc_eval(const ProgramDev& p, uint32_t k, const Fr* __restrict__ w, uint32_t B, uint32_t b) {
+  Fr acc = Fr::zero();
+  uint32_t e = ZK_LDG(p.lc_off + k + 1);
+  for (uint32_t i = ZK_LDG(p.lc_off + k); i < e; i++)
+    acc = acc + p.lc_coef[i] * w[(size_t)ZK_LDG(p.lc_wire + i) * B + b];
+  return acc;
+}
+
+// one thread = one client instance; all threads run the same op stream (no divergence).
+// w: canonical witness [n_wires][B]; rows 1..n_inputs already hold the inputs.
+ZK_GLOBAL void k_witness(ProgramDev p, Fr* __restrict__ w, uint32_t B) {
+  uint32_t b = (uint32_t)ZK_TID;
+  if (b >= B) return;
+  Fr one_c = Fr::zero(); one_c.v[0] = 1;
+  w[b] = one_c;
+  for (uint32_t o = 0; o < p.n_ops; o++) {
+    const uint32_t* op = p.ops + 5 * (size_t)o;
+    const uint32_t code = ZK_LDG(op), dst = ZK_LDG(op + 1), a = ZK_LDG(op + 2), bb = ZK_LDG(op + 3), c = ZK_LDG(op + 4);
+    if (code == 1) {
+      w[(size_t)dst * B + b] = lc_eval(p, a, w, B, b).from_mont();
+    } else if (code == 2) {
+      Fr v = lc_eval(p, a, w, B, b) * lc_eval(p, bb, w, B, b);
+      if (c != 0xFFFFFFFFu) v = v + lc_eval(p, c, w, B, b);
+      w[(size_t)dst * B + b] = v.from_mont();
+    } else if (code == 3) {
+      Fr v = lc_eval(p, a, w, B, b).from_mont();
+      for (uint32_t i = 0; i < bb; i++) {
+        Fr bit = Fr::zero();
+        bit.v[0] = (v.v[i >> 5] >> (i & 31)) & 1u;
+        w[(size_t)(dst + i) * B + b] = bit;
+      }
+    } else if (code == 4) {
+      const uint32_t t = a;
+      const PoseidonDev K = p.pk[t];
+      Fr st[17], nx[17];
+      st[0] = Fr::zero();
+      for (uint32_t i = 1; i < t; i++) st[i] = w[(size_t)ZK_LDG(p.pos_in + bb + i - 1) * B + b].to_mont();
+      size_t k = dst;
+      for (uint32_t r = 0; r < K.rounds; r++) {
+        for (uint32_t i = 0; i < t; i++) st[i] = st[i] + K.C[r * t + i];
+        const uint32_t lanes = (r < 4 || r >= 4 + K.rp) ? t : 1;
+        for (uint32_t i = 0; i < lanes; i++) {
+          Fr x2 = st[i].sqr(), x4 = x2.sqr(), x5 = x4 * st[i];
+          w[k * B + b] = x2.from_mont();
+          w[(k + 1) * B + b] = x4.from_mont();
+          w[(k + 2) * B + b] = x5.from_mont();
+          k += 3;
+          st[i] = x5;
+        }
+        for (uint32_t i = 0; i < t; i++) {
+          Fr acc = Fr::zero();
+          for (uint32_t j = 0; j < t; j++) acc = acc + K.M[i * t + j] * st[j];
+          nx[i] = acc;
+        }
+        for (uint32_t i = 0; i < t; i++) st[i] = nx[i];
+      }
+      w[k * B + b] = st[0].from_mont();
+    }
+  }
+}
+
+// ================================================================================ K1: sparse A.w, B.w, C = A o B
+struct CsrDev {
+  const uint32_t* row_off;  // n_rows + 1
+  const uint32_t* wire;
+  const Fr* coef;           // coef * R^2 (the bytes zkey section 4 stores)
+};
+ZK_D Fr csr_row(const CsrDev& m, uint32_t row, const Fr* __restrict__ w, uint32_t B, uint32_t b) {
+  Fr acc = Fr::zero();
+  uint32_t e = ZK_LDG(m.row_off + row + 1);
+  for (uint32_t i = ZK_LDG(m.row_off + row); i < e; i++)
+    acc = acc + m.coef[i] * w[(size_t)ZK_LDG(m.wire + i) * B + b];
+  return acc;
+}
+// abc: [3][n][B] Montgomery (A evals, B evals, C = A*B) over the constraint domain
+ZK_GLOBAL void k_build_abc(CsrDev A, CsrDev Bm, const Fr* __restrict__ w, Fr* __restrict__ abc, uint32_t n, uint32_t B) {
+  size_t tid = ZK_TID;
+  if (tid >= (size_t)n * B) return;
+  uint32_t row = (uint32_t)(tid / B), b = (uint32_t)(tid % B);
+  Fr a = csr_row(A, row, w, B, b), bv = csr_row(Bm, row, w, B, b);
+  abc[tid] = a;
+  abc[(size_t)n * B + tid] = bv;
+  abc[2 * (size_t)n * B + tid] = a * bv;
+}
+// constraint check (what a failing `===` is for circom): first violated row per client, or 0xFFFFFFFF
+ZK_GLOBAL void k_r1cs_check(CsrDev A, CsrDev Bm, CsrDev C, const Fr* __restrict__ w, uint32_t n_rows, uint32_t B,
+                            uint32_t* __restrict__ first_bad) {
+  size_t tid = ZK_TID;
+  if (tid >= (size_t)n_rows * B) return;
+  uint32_t row = (uint32_t)(tid / B), b = (uint32_t)(tid % B);
+  Fr a = csr_row(A, row, w, B, b), bv = csr_row(Bm, row, w, B, b), c = csr_row(C, row, w, B, b);
+  // a, bv, c are Montgomery(value): a*bv = Mont(product), compare in Montgomery form
+  if (!((a * bv) == c)) ZK_ATOMIC_MIN(first_bad + b, row);
+}
+
+// ================================================================================ K2-K5: H polynomial
+// data: [n_poly][n][B]; one radix-2 stage. dif=1: Gentleman-Sande (natural in -> bit-reversed out after
+// all stages, used for the inverse transform), dif=0: Cooley-Tukey (bit-reversed in -> natural out).
+// tw: n/2 powers of the (inverse) root, Montgomery.
+ZK_GLOBAL void k_ntt_stage(Fr* __restrict__ data, const Fr* __restrict__ tw, uint32_t n, uint32_t B, uint32_t n_poly,
+                           uint32_t half, int dif) {
+  size_t tid = ZK_TID;
+  size_t per_poly = (size_t)(n / 2) * B;
+  if (tid >= per_poly * n_poly) return;
+  uint32_t poly = (uint32_t)(tid / per_poly);
+  size_t rem = tid % per_poly;
+  uint32_t pr = (uint32_t)(rem / B), b = (uint32_t)(rem % B);
+  uint32_t blk = pr / half, k = pr % half;
+  size_t i0 = (size_t)blk * 2 * half + k, i1 = i0 + half;
+  Fr* base = data + (size_t)poly * n * B;
+  Fr u = base[i0 * B + b], v = base[i1 * B + b];
+  Fr wv = tw[(size_t)k * (n / 2 / half)];
+  if (dif) {
+    base[i0 * B + b] = u + v;
+    base[i1 * B + b] = (u - v) * wv;
+  } else {
+    v = v * wv;
+    base[i0 * B + b] = u + v;
+    base[i1 * B + b] = u - v;
+  }
+}
+// after the DIF inverse transform position p holds coefficient bitrev(p): multiply by
+// tab[p] = n^-1 * inc^bitrev(p)  (inc = w_{2n}: the odd-coset shift snarkjs applies with batchApplyKey)
+ZK_GLOBAL void k_scale_rows(Fr* __restrict__ data, const Fr* __restrict__ tab, uint32_t n, uint32_t B, uint32_t n_poly) {
+  size_t tid = ZK_TID;
+  size_t per_poly = (size_t)n * B;
+  if (tid >= per_poly * n_poly) return;
+  uint32_t p = (uint32_t)((tid % per_poly) / B);
+  data[tid] = data[tid] * tab[p];
+}
+// joinABC: P = A'*B' - C', Montgomery -> canonical (the H-MSM scalars), out [n][B]
+ZK_GLOBAL void k_join_abc(const Fr* __restrict__ abc, Fr* __restrict__ out, uint32_t n, uint32_t B) {
+  size_t tid = ZK_TID;
+  size_t per_poly = (size_t)n * B;
+  if (tid >= per_poly) return;
+  Fr a = abc[tid], b = abc[per_poly + tid], c = abc[2 * per_poly + tid];
+  out[tid] = (a * b - c).from_mont();
+}
+
+// ================================================================================ K6/K7: Pippenger MSM
+// Batched over B proofs that share the bases. Signed c-bit digits: W = 254/c + 1 windows,
+// nb = 2^(c-1) buckets per window, row = b*W + j identifies one (proof, window) bucket set.
+struct MsmShape {
+  uint32_t m;    // points
+  uint32_t B;    // proofs
+  uint32_t c, W, nb;
+  uint32_t cap;  // entries reserved per row in the sorted index list (= m)
+};
+ZK_HD uint32_t scalar_bits(const uint32_t* k, uint32_t pos, uint32_t c) {
+  uint32_t word = pos >> 5, off = pos & 31;
+  if (word >= 8) return 0;
+  uint32_t v = k[word] >> off;
+  if (off + c > 32 && word < 7) v |= k[word + 1] << (32 - off);
+  return v & ((1u << c) - 1);
+}
+// digit j of the signed recoding; carry is threaded by the caller across j = 0..W-1
+ZK_HD int32_t signed_digit(const uint32_t* k, uint32_t j, uint32_t c, uint32_t& carry) {
+  uint32_t d = scalar_bits(k, j * c, c) + carry;
+  if (d > (1u << (c - 1))) { carry = 1; return (int32_t)d - (int32_t)(1u << c); }
+  carry = 0;
+  return (int32_t)d;
+}
+
+// pass 1: bucket histogram. scalars: canonical [m][B]. counts: [B*W][nb]
+ZK_GLOBAL void k_msm_count(const Fr* __restrict__ scalars, MsmShape s, uint32_t* __restrict__ counts) {
+  size_t tid = ZK_TID;
+  if (tid >= (size_t)s.m * s.B) return;
+  uint32_t b = (uint32_t)(tid % s.B);
+  Fr k = scalars[tid];
+  if (k.is_zero()) return;
+  uint32_t carry = 0;
+  for (uint32_t j = 0; j < s.W; j++) {
+    int32_t d = signed_digit(k.v, j, s.c, carry);
+    if (d == 0) continue;
+    uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
+    ZK_ATOMIC_ADD(counts + ((size_t)b * s.W + j) * s.nb + (mag - 1), 1u);
+  }
+}
+// pass 2a: per-row chunk sums (chunk = SCAN_CHUNK buckets)
+#define ZK_SCAN_CHUNK 128u
+ZK_GLOBAL void k_msm_scan_chunks(const uint32_t* __restrict__ counts, MsmShape s, uint32_t* __restrict__ chunk_sums) {
+  size_t tid = ZK_TID;
+  uint32_t nchunk = (s.nb + ZK_SCAN_CHUNK - 1) / ZK_SCAN_CHUNK;
+  if (tid >= (size_t)s.B * s.W * nchunk) return;
+  size_t row = tid / nchunk;
+  uint32_t ch = (uint32_t)(tid % nchunk);
+  uint32_t lo = ch * ZK_SCAN_CHUNK, hi = lo + ZK_SCAN_CHUNK < s.nb ? lo + ZK_SCAN_CHUNK : s.nb;
+  uint32_t acc = 0;
+  for (uint32_t k = lo; k < hi; k++) acc += counts[row * s.nb + k];
+  chunk_sums[tid] = acc;
+}
+// pass 2b: exclusive offsets inside the row's region of the sorted list; cursors = copy used by the scatter
+ZK_GLOBAL void k_msm_scan_write(const uint32_t* __restrict__ counts, const uint32_t* __restrict__ chunk_sums, MsmShape s,
+                                uint32_t* __restrict__ offsets, uint32_t* __restrict__ cursors) {
+  size_t tid = ZK_TID;
+  uint32_t nchunk = (s.nb + ZK_SCAN_CHUNK - 1) / ZK_SCAN_CHUNK;
+  if (tid >= (size_t)s.B * s.W * nchunk) return;
+  size_t row = tid / nchunk;
+  uint32_t ch = (uint32_t)(tid % nchunk);
+  uint32_t acc = 0;
+  for (uint32_t q = 0; q < ch; q++) acc += chunk_sums[row * nchunk + q];
+  uint32_t lo = ch * ZK_SCAN_CHUNK, hi = lo + ZK_SCAN_CHUNK < s.nb ? lo + ZK_SCAN_CHUNK : s.nb;
+  for (uint32_t k = lo; k < hi; k++) {
+    offsets[row * s.nb + k] = acc;
+    cursors[row * s.nb + k] = acc;
+    acc += counts[row * s.nb + k];
+  }
+}
+// pass 3: scatter point references into bucket order. sorted: [B*W][cap], entry = point | sign << 31
+ZK_GLOBAL void k_msm_scatter(const Fr* __restrict__ scalars, MsmShape s, uint32_t* __restrict__ cursors,
+                             uint32_t* __restrict__ sorted) {
+  size_t tid = ZK_TID;
+  if (tid >= (size_t)s.m * s.B) return;
+  uint32_t i = (uint32_t)(tid / s.B), b = (uint32_t)(tid % s.B);
+  Fr k = scalars[tid];
+  if (k.is_zero()) return;
+  uint32_t carry = 0;
+  for (uint32_t j = 0; j < s.W; j++) {
+    int32_t d = signed_digit(k.v, j, s.c, carry);
+    if (d == 0) continue;
+    uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
+    size_t row = (size_t)b * s.W + j;
+    uint32_t pos = ZK_ATOMIC_ADD(cursors + row * s.nb + (mag - 1), 1u);
+    sorted[row * s.cap + pos] = i | (d < 0 ? 0x80000000u : 0u);
+  }
+}
+// pass 4: bucket accumulation, one thread per (row, bucket): mixed adds of gathered affine bases.
+template <class F>
+ZK_GLOBAL void k_msm_accumulate(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ sorted,
+                                const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ counts, MsmShape s,
+                                Xyzz<F>* __restrict__ buckets) {
+  size_t tid = ZK_TID;
+  if (tid >= (size_t)s.B * s.W * s.nb) return;
+  size_t row = tid / s.nb;
+  uint32_t start = offsets[tid], cnt = counts[tid];
+  const uint32_t* list = sorted + row * s.cap + start;
+  Xyzz<F> acc = Xyzz<F>::infinity();
+  for (uint32_t q = 0; q < cnt; q++) {
+    uint32_t e = list[q];
+    Affine<F> p = bases[e & 0x7FFFFFFFu];
+    xyzz_madd(acc, p, (e >> 31) != 0);
+  }
+  buckets[tid] = acc;
+}
+// pass 5a: running sums over chunks of L buckets: R = sum B_k, T = sum (k - k0) * B_k  (k0 = chunk*L, k from 1)
+template <class F>
+ZK_GLOBAL void k_msm_reduce_chunks(const Xyzz<F>* __restrict__ buckets, MsmShape s, uint32_t L, Xyzz<F>* __restrict__ Rs,
+                                   Xyzz<F>* __restrict__ Ts) {
+  size_t tid = ZK_TID;
+  uint32_t nchunk = s.nb / L;
+  if (tid >= (size_t)s.B * s.W * nchunk) return;
+  size_t row = tid / nchunk;
+  uint32_t ch = (uint32_t)(tid % nchunk);
+  const Xyzz<F>* bk = buckets + row * s.nb + (size_t)ch * L;
+  Xyzz<F> run = Xyzz<F>::infinity(), acc = Xyzz<F>::infinity();
+  for (int k = (int)L - 1; k >= 0; k--) {
+    xyzz_add(run, bk[k]);
+    xyzz_add(acc, run);
+  }
+  Rs[tid] = run;
+  Ts[tid] = acc;
+}
+// pass 5b: window sum S = sum_t T_t + L * sum_t t * R_t, one thread per row
+template <class F>
+ZK_GLOBAL void k_msm_reduce_rows(const Xyzz<F>* __restrict__ Rs, const Xyzz<F>* __restrict__ Ts, MsmShape s, uint32_t L,
+                                 Xyzz<F>* __restrict__ win) {
+  size_t row = ZK_TID;
+  if (row >= (size_t)s.B * s.W) return;
+  uint32_t nchunk = s.nb / L;
+  const Xyzz<F>* R = Rs + row * nchunk;
+  const Xyzz<F>* T = Ts + row * nchunk;
+  Xyzz<F> run = Xyzz<F>::infinity(), acc = Xyzz<F>::infinity(), tsum = Xyzz<F>::infinity();
+  for (int t = (int)nchunk - 1; t >= 1; t--) {
+    xyzz_add(run, R[t]);
+    xyzz_add(acc, run);
+  }
+  for (uint32_t l = L; l > 1; l >>= 1) acc = xyzz_dbl(acc);
+  for (uint32_t t = 0; t < nchunk; t++) xyzz_add(tsum, T[t]);
+  xyzz_add(acc, tsum);
+  win[row] = acc;
+}
+// pass 6: Horner over the windows, one thread per proof: out[b] = sum_j 2^(c*j) * win[b][j]
+template <class F>
+ZK_GLOBAL void k_msm_combine(const Xyzz<F>* __restrict__ win, MsmShape s, Xyzz<F>* __restrict__ out) {
+  size_t b = ZK_TID;
+  if (b >= s.B) return;
+  Xyzz<F> acc = win[b * s.W + (s.W - 1)];
+  for (int j = (int)s.W - 2; j >= 0; j--) {
+    for (uint32_t q = 0; q < s.c; q++) acc = xyzz_dbl(acc);
+    xyzz_add(acc, win[b * s.W + j]);
+  }
+  out[b] = acc;
+}
+
+// ================================================================================ K8: blinding / finalisation
+struct VkDev {
+  G1Affine alpha1, beta1, delta1;
+  G2Affine beta2, delta2;
+};
+// phase 1: fixed-base terms. thread (b, k): k=0 r*delta1, 1 s*delta1, 2 -(r*s)*delta1 (G1) ; k=3 s*delta2 (G2)
+// rs: canonical [B][2] (host order: r then s). t_g1: [B][3], t_g2: [B]
+ZK_GLOBAL void k_fin_fixed(VkDev vk, const Fr* __restrict__ rs, uint32_t B, G1Xyzz* __restrict__ t_g1, G2Xyzz* __restrict__ t_g2) {
+  size_t tid = ZK_TID;
+  if (tid >= (size_t)B * 4) return;
+  uint32_t b = (uint32_t)(tid / 4), k = (uint32_t)(tid % 4);
+  Fr r = rs[2 * (size_t)b], sv = rs[2 * (size_t)b + 1];
+  if (k == 0) t_g1[3 * (size_t)b] = xyzz_scalar_mul(G1Xyzz::from_affine(vk.delta1), r.v);
+  else if (k == 1) t_g1[3 * (size_t)b + 1] = xyzz_scalar_mul(G1Xyzz::from_affine(vk.delta1), sv.v);
+  else if (k == 2) {
+    Fr nrs = (r.to_mont() * sv.to_mont()).neg().from_mont();
+    t_g1[3 * (size_t)b + 2] = xyzz_scalar_mul(G1Xyzz::from_affine(vk.delta1), nrs.v);
+  } else t_g2[b] = xyzz_scalar_mul(G2Xyzz::from_affine(vk.delta2), sv.v);
+}
+// phase 2: thread (b, k): k=0: pi_a = A + alpha + r*delta1, then s*pi_a ; k=1: pi_b1 = B1 + beta1 + s*delta1, then r*pi_b1
+// msm_g1: [4][B] = A, B1, C, H results. outputs pis[B][2] (pi_a, pi_b1) and var[B][2] (s*pi_a, r*pi_b1)
+ZK_GLOBAL void k_fin_var(VkDev vk, const Fr* __restrict__ rs, uint32_t B, const G1Xyzz* __restrict__ msm_g1,
+                         const G1Xyzz* __restrict__ t_g1, G1Xyzz* __restrict__ pis, G1Xyzz* __restrict__ var) {
+  size_t tid = ZK_TID;
+  if (tid >= (size_t)B * 2) return;
+  uint32_t b = (uint32_t)(tid / 2), k = (uint32_t)(tid % 2);
+  Fr r = rs[2 * (size_t)b], sv = rs[2 * (size_t)b + 1];
+  G1Xyzz p = msm_g1[(size_t)k * B + b];
+  xyzz_madd(p, k == 0 ? vk.alpha1 : vk.beta1, false);
+  xyzz_add(p, t_g1[3 * (size_t)b + k]);
+  pis[tid] = p;
+  var[tid] = xyzz_scalar_mul(p, k == 0 ? sv.v : r.v);
+}
+// phase 3: assemble, normalise, write the 256-byte proof (A | B | C, affine canonical LE)
+ZK_GLOBAL void k_fin_write(VkDev vk, uint32_t B, const G1Xyzz* __restrict__ msm_g1, const G2Xyzz* __restrict__ msm_g2,
+                           const G1Xyzz* __restrict__ t_g1, const G2Xyzz* __restrict__ t_g2, const G1Xyzz* __restrict__ pis,
+                           const G1Xyzz* __restrict__ var, Fq* __restrict__ proofs /* [B][8] */) {
+  size_t tid = ZK_TID;
+  if (tid >= (size_t)B * 3) return;
+  uint32_t b = (uint32_t)(tid / 3), k = (uint32_t)(tid % 3);
+  Fq* out = proofs + 8 * (size_t)b;
+  if (k == 0) {
+    G1Affine a = xyzz_to_affine(pis[2 * (size_t)b]);
+    out[0] = a.x.from_mont(); out[1] = a.y.from_mont();
+  } else if (k == 1) {
+    G2Xyzz p = msm_g2[b];
+    xyzz_madd(p, vk.beta2, false);
+    xyzz_add(p, t_g2[b]);
+    G2Affine a = xyzz_to_affine(p);
+    out[2] = a.x.a.from_mont(); out[3] = a.x.b.from_mont(); out[4] = a.y.a.from_mont(); out[5] = a.y.b.from_mont();
+  } else {
+    G1Xyzz p = msm_g1[2 * (size_t)B + b];
+    xyzz_add(p, msm_g1[3 * (size_t)B + b]);
+    xyzz_add(p, var[2 * (size_t)b]);
+    xyzz_add(p, var[2 * (size_t)b + 1]);
+    xyzz_add(p, t_g1[3 * (size_t)b + 2]);
+    G1Affine a = xyzz_to_affine(p);
+    out[6] = a.x.from_mont(); out[7] = a.y.from_mont();
+  }
+}
+
+// ================================================================================ misc
+// out[i] = k_i * G as Montgomery affine (zkey point layout): `groth16 setup`'s scalar multiplications
+template <class F>
+ZK_GLOBAL void k_gen_mul(Affine<F> gen, const Fr* __restrict__ scalars, size_t n, Affine<F>* __restrict__ out) {
+  size_t i = ZK_TID;
+  if (i >= n) return;
+  Fr k = scalars[i];
+  out[i] = xyzz_to_affine(xyzz_scalar_mul(Xyzz<F>::from_affine(gen), k.v));
+}
+// a single XYZZ result -> affine canonical bytes (standalone MSM API)
+template <class F>
+ZK_GLOBAL void k_to_affine_canonical(const Xyzz<F>* __restrict__ in, size_t n, Affine<F>* __restrict__ out) {
+  size_t i = ZK_TID;
+  if (i >= n) return;
+  Affine<F> a = xyzz_to_affine(in[i]);
+  a.x = a.x.from_mont();
+  a.y = a.y.from_mont();
+  out[i] = a;
+}
+// integer-pipe microbenchmark: `iters` dependent Montgomery products per thread (roofline denominator)
+ZK_GLOBAL void k_bench_modmul(Fq* __restrict__ data, size_t n, uint32_t iters) {
+  size_t i = ZK_TID;
+  if (i >= n) return;
+  Fq x = data[i], y = x;
+  ZK_NOUNROLL for (uint32_t k = 0; k < iters; k++) { x = x * y; y = y * x; }
+  data[i] = x + y;
+}
+
+}  // namespace zk

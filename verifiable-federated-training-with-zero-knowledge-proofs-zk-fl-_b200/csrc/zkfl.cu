@@ -1,0 +1,792 @@
+// libzkfl.so host side: artefact parsing (.zkey / .r1cs / .zkwp), HBM residency, kernel orchestration
+// on one CUDA stream per context, and the C ABI declared in include/zkfl.h.
+#include "kernels.cuh"
+
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/zkfl.h"
+
+#ifdef ZKFL_EMUL
+thread_local zk_emul_idx zk_emul_cur;
+#endif
+
+using namespace zk;
+
+// ------------------------------------------------------------------------------------ errors / counters
+static thread_local std::string g_err;
+static std::atomic<uint64_t> g_launches(0);
+namespace zkrt {
+void note_launch(const char*) { g_launches.fetch_add(1, std::memory_order_relaxed); }
+}  // namespace zkrt
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+#define CU(expr)                                                                                     \
+  do {                                                                                               \
+    cudaError_t _e = (expr);                                                                         \
+    if (_e != cudaSuccess) return fail(ZKFL_ERR_CUDA, std::string(#expr) + ": " + zkrt::err_str(_e)); \
+  } while (0)
+#define TRY(expr)            \
+  do {                       \
+    int _r = (expr);         \
+    if (_r != 0) return _r;  \
+  } while (0)
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes) {
+    if (bytes <= cap) return 0;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    // grow with headroom so alternating batch sizes do not thrash
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) { p = nullptr; return fail(ZKFL_ERR_NOMEM, "cudaMalloc(" + std::to_string(bytes) + ") failed"); }
+    cap = bytes;
+    return 0;
+  }
+  template <class T> T* as() const { return (T*)p; }
+  ~DevBuf() { if (p) cudaFree(p); }
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+};
+
+struct ProfRec { std::string name; cudaEvent_t e0, e1; uint64_t launches; };
+struct ProfAgg { double ms = 0; uint64_t launches = 0; uint64_t calls = 0; };
+
+struct zkfl_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool prof = false;
+  std::vector<ProfRec> pending;
+  std::map<std::string, ProfAgg> agg;
+  std::vector<std::string> order;
+  // workspace (grow-only)
+  DevBuf w, abc, hsc, stage_in, stage_rs, aos;
+  DevBuf counts, offsets, cursors, chunk_sums, sorted, buckets, Rs, Ts, win;
+  DevBuf res_g1, res_g2, t_g1, t_g2, pis, var, proofs, pubs, bad;
+  DevBuf msm_sc, msm_out;
+};
+
+struct Stage {
+  zkfl_ctx* c; size_t idx = (size_t)-1; uint64_t l0;
+  Stage(zkfl_ctx* c_, const char* name) : c(c_) {
+    if (!c->prof) return;
+    ProfRec r; r.name = name; r.launches = 0;
+    cudaEventCreate(&r.e0); cudaEventCreate(&r.e1);
+    cudaEventRecord(r.e0, c->stream);
+    l0 = g_launches.load();
+    c->pending.push_back(r); idx = c->pending.size() - 1;
+  }
+  ~Stage() {
+    if (idx == (size_t)-1) return;
+    cudaEventRecord(c->pending[idx].e1, c->stream);
+    c->pending[idx].launches = g_launches.load() - l0;
+  }
+};
+
+// ------------------------------------------------------------------------------------ host field helpers
+static Fr fr_from_bytes_canonical(const uint8_t* p) { Fr r; memcpy(r.v, p, 32); return r; }
+static Fr fr_pow(Fr base, const uint32_t* e, int nwords) {
+  Fr r = Fr::one();
+  for (int i = nwords * 32 - 1; i >= 0; i--) { r = r.sqr(); if ((e[i >> 5] >> (i & 31)) & 1) r = r * base; }
+  return r;
+}
+static Fr fr_root_of_unity(int power) {  // ffjavascript: nqr = 5, w[28] = 5^((r-1)/2^28), w[k] = w[k+1]^2
+  uint32_t e[8];
+  for (int i = 0; i < 8; i++) e[i] = FrP::mod(i);
+  e[0] -= 1;
+  for (int i = 0; i < 8; i++) e[i] = (e[i] >> 28) | (i < 7 ? e[i + 1] << 4 : 0);
+  Fr five = Fr::zero(); five.v[0] = 5;
+  Fr w = fr_pow(five.to_mont(), e, 8);
+  for (int i = 28; i > power; i--) w = w.sqr();
+  return w;
+}
+static bool fr_bytes_lt_mod(const uint8_t* p) {
+  uint32_t v[8]; memcpy(v, p, 32);
+  for (int i = 7; i >= 0; i--) { if (v[i] < FrP::mod(i)) return true; if (v[i] > FrP::mod(i)) return false; }
+  return false;
+}
+
+// ------------------------------------------------------------------------------------ iden3 binfile
+struct Sec { const uint8_t* p; uint64_t len; };
+static int parse_sections(const uint8_t* d, size_t len, const char* magic, std::map<uint32_t, Sec>& out) {
+  if (!d || len < 12 || memcmp(d, magic, 4)) return fail(ZKFL_ERR_FORMAT, std::string("bad magic, expected ") + magic);
+  uint32_t n; memcpy(&n, d + 8, 4);
+  size_t p = 12;
+  for (uint32_t i = 0; i < n; i++) {
+    if (p + 12 > len) return fail(ZKFL_ERR_FORMAT, "truncated section table");
+    uint32_t id; uint64_t l; memcpy(&id, d + p, 4); memcpy(&l, d + p + 4, 8); p += 12;
+    if (l > len - p) return fail(ZKFL_ERR_FORMAT, "truncated section");
+    if (!out.count(id)) out[id] = Sec{d + p, l};
+    p += l;
+  }
+  return 0;
+}
+
+template <class T>
+static int upload(zkfl_ctx* c, DevBuf& buf, const T* host, size_t count) {
+  TRY(buf.reserve(count ? count * sizeof(T) : 16));
+  if (count) CU(cudaMemcpyAsync(buf.p, host, count * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+struct CsrHost {
+  std::vector<uint32_t> row_off, wire;
+  std::vector<Fr> coef;
+};
+struct CsrBufs {
+  DevBuf row_off, wire, coef;
+  CsrDev dev() const { CsrDev d; d.row_off = row_off.as<uint32_t>(); d.wire = wire.as<uint32_t>(); d.coef = coef.as<Fr>(); return d; }
+};
+static int upload_csr(zkfl_ctx* c, const CsrHost& h, CsrBufs& b) {
+  TRY(upload(c, b.row_off, h.row_off.data(), h.row_off.size()));
+  TRY(upload(c, b.wire, h.wire.data(), h.wire.size()));
+  TRY(upload(c, b.coef, h.coef.data(), h.coef.size()));
+  return 0;
+}
+// builds CSR from COO triples (row, wire, coef) with counting sort by row
+static void coo_to_csr(uint32_t n_rows, const std::vector<uint32_t>& rows, const std::vector<uint32_t>& wires,
+                       const std::vector<Fr>& coefs, CsrHost& out) {
+  out.row_off.assign(n_rows + 1, 0);
+  for (uint32_t r : rows) out.row_off[r + 1]++;
+  for (uint32_t i = 0; i < n_rows; i++) out.row_off[i + 1] += out.row_off[i];
+  out.wire.resize(rows.size()); out.coef.resize(rows.size());
+  std::vector<uint32_t> cur(out.row_off.begin(), out.row_off.end() - 1);
+  for (size_t i = 0; i < rows.size(); i++) { uint32_t p = cur[rows[i]]++; out.wire[p] = wires[i]; out.coef[p] = coefs[i]; }
+}
+
+// ------------------------------------------------------------------------------------ handles
+struct zkfl_circuit {
+  zkfl_ctx* ctx;
+  uint32_t n_wires, n_public, n_inputs, n_ops;
+  DevBuf ops, lc_off, lc_wire, lc_coef, pos_in, pconst;
+  ProgramDev dev;
+};
+struct zkfl_r1cs {
+  zkfl_ctx* ctx;
+  uint32_t n_wires, n_constraints;
+  CsrBufs A, B, C;
+};
+struct zkfl_zkey {
+  zkfl_ctx* ctx;
+  uint32_t n_vars, n_public, domain, log_n;
+  CsrBufs A, B;
+  DevBuf pA, pB1, pB2, pC, pH, tw_fwd, tw_inv, coset;
+  VkDev vk;
+};
+struct MsmBases {
+  zkfl_ctx* ctx; int group; size_t n; DevBuf pts;
+};
+
+// ------------------------------------------------------------------------------------ MSM pipeline
+static uint32_t env_u32(const char* name, uint32_t dflt) {
+  const char* v = getenv(name);
+  return v && *v ? (uint32_t)strtoul(v, nullptr, 10) : dflt;
+}
+static MsmShape msm_shape(uint32_t m, uint32_t B) {
+  uint32_t best_c = 4; double best = 1e300;
+  for (uint32_t c = 4; c <= 16; c++) {
+    double W = 254 / c + 1, nb = (double)(1u << (c - 1));
+    double cost = W * ((double)m + 2.6 * nb);
+    if (cost < best) { best = cost; best_c = c; }
+  }
+  uint32_t c = env_u32("ZKFL_MSM_C", best_c);
+  if (c < 2) c = 2;
+  if (c > 16) c = 16;
+  MsmShape s; s.m = m; s.B = B; s.c = c; s.W = 254 / c + 1; s.nb = 1u << (c - 1); s.cap = m;
+  return s;
+}
+static uint32_t reduce_chunk(const MsmShape& s) {
+  uint32_t L = 1;
+  while (L * L < s.nb) L <<= 1;  // ~sqrt(nb)
+  if (L > s.nb) L = s.nb;
+  return L;
+}
+
+static int msm_sort(zkfl_ctx* c, const Fr* scalars, const MsmShape& s) {
+  size_t rows = (size_t)s.B * s.W;
+  uint32_t nchunk = (s.nb + ZK_SCAN_CHUNK - 1) / ZK_SCAN_CHUNK;
+  TRY(c->counts.reserve(rows * s.nb * 4));
+  TRY(c->offsets.reserve(rows * s.nb * 4));
+  TRY(c->cursors.reserve(rows * s.nb * 4));
+  TRY(c->chunk_sums.reserve(rows * nchunk * 4));
+  TRY(c->sorted.reserve(rows * s.cap * 4));
+  CU(cudaMemsetAsync(c->counts.p, 0, rows * s.nb * 4, c->stream));
+  ZK_LAUNCH(k_msm_count, (size_t)s.m * s.B, 256, c->stream, scalars, s, c->counts.as<uint32_t>());
+  ZK_LAUNCH(k_msm_scan_chunks, rows * nchunk, 128, c->stream, c->counts.as<uint32_t>(), s, c->chunk_sums.as<uint32_t>());
+  ZK_LAUNCH(k_msm_scan_write, rows * nchunk, 128, c->stream, c->counts.as<uint32_t>(), c->chunk_sums.as<uint32_t>(), s,
+            c->offsets.as<uint32_t>(), c->cursors.as<uint32_t>());
+  ZK_LAUNCH(k_msm_scatter, (size_t)s.m * s.B, 256, c->stream, scalars, s, c->cursors.as<uint32_t>(), c->sorted.as<uint32_t>());
+  CU(cudaGetLastError());
+  return 0;
+}
+// buckets -> per-proof sums out[B]; uses the lists left by msm_sort
+template <class F>
+static int msm_run(zkfl_ctx* c, const Affine<F>* bases, const MsmShape& s, Xyzz<F>* out) {
+  size_t rows = (size_t)s.B * s.W;
+  uint32_t L = reduce_chunk(s), nchunk = s.nb / L;
+  TRY(c->buckets.reserve(rows * s.nb * sizeof(Xyzz<F>)));
+  TRY(c->Rs.reserve(rows * nchunk * sizeof(Xyzz<F>)));
+  TRY(c->Ts.reserve(rows * nchunk * sizeof(Xyzz<F>)));
+  TRY(c->win.reserve(rows * sizeof(Xyzz<F>)));
+  ZK_LAUNCH(k_msm_accumulate<F>, rows * s.nb, 128, c->stream, bases, c->sorted.as<uint32_t>(), c->offsets.as<uint32_t>(),
+            c->counts.as<uint32_t>(), s, c->buckets.as<Xyzz<F>>());
+  ZK_LAUNCH(k_msm_reduce_chunks<F>, rows * nchunk, 128, c->stream, c->buckets.as<Xyzz<F>>(), s, L, c->Rs.as<Xyzz<F>>(),
+            c->Ts.as<Xyzz<F>>());
+  ZK_LAUNCH(k_msm_reduce_rows<F>, rows, 64, c->stream, c->Rs.as<Xyzz<F>>(), c->Ts.as<Xyzz<F>>(), s, L, c->win.as<Xyzz<F>>());
+  ZK_LAUNCH(k_msm_combine<F>, s.B, 32, c->stream, c->win.as<Xyzz<F>>(), s, out);
+  CU(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------ prove pipeline (witness in c->w)
+static int prove_from_device_witness(zkfl_ctx* c, const zkfl_zkey* z, const Fr* rs_dev, uint32_t B) {
+  const uint32_t n = z->domain, m = z->n_vars;
+  Fr* w = c->w.as<Fr>();
+  TRY(c->abc.reserve(3 * (size_t)n * B * sizeof(Fr)));
+  TRY(c->hsc.reserve((size_t)n * B * sizeof(Fr)));
+  TRY(c->res_g1.reserve(4 * (size_t)B * sizeof(G1Xyzz)));
+  TRY(c->res_g2.reserve((size_t)B * sizeof(G2Xyzz)));
+  Fr* abc = c->abc.as<Fr>();
+  {
+    Stage st(c, "build_abc");
+    ZK_LAUNCH(k_build_abc, (size_t)n * B, 128, c->stream, z->A.dev(), z->B.dev(), w, abc, n, B);
+  }
+  {
+    Stage st(c, "ntt");
+    for (uint32_t h = n / 2; h >= 1; h >>= 1)
+      ZK_LAUNCH(k_ntt_stage, (size_t)3 * (n / 2) * B, 256, c->stream, abc, z->tw_inv.as<Fr>(), n, B, 3u, h, 1);
+    ZK_LAUNCH(k_scale_rows, (size_t)3 * n * B, 256, c->stream, abc, z->coset.as<Fr>(), n, B, 3u);
+    for (uint32_t h = 1; h <= n / 2; h <<= 1)
+      ZK_LAUNCH(k_ntt_stage, (size_t)3 * (n / 2) * B, 256, c->stream, abc, z->tw_fwd.as<Fr>(), n, B, 3u, h, 0);
+    ZK_LAUNCH(k_join_abc, (size_t)n * B, 256, c->stream, abc, c->hsc.as<Fr>(), n, B);
+  }
+  G1Xyzz* r1 = c->res_g1.as<G1Xyzz>();
+  MsmShape sw = msm_shape(m, B);
+  { Stage st(c, "msm_sort_w"); TRY(msm_sort(c, w, sw)); }
+  { Stage st(c, "msm_A"); TRY(msm_run<Fq>(c, z->pA.as<G1Affine>(), sw, r1)); }
+  { Stage st(c, "msm_B1"); TRY(msm_run<Fq>(c, z->pB1.as<G1Affine>(), sw, r1 + B)); }
+  { Stage st(c, "msm_C"); TRY(msm_run<Fq>(c, z->pC.as<G1Affine>(), sw, r1 + 2 * (size_t)B)); }
+  { Stage st(c, "msm_B2"); TRY(msm_run<Fq2>(c, z->pB2.as<G2Affine>(), sw, c->res_g2.as<G2Xyzz>())); }
+  MsmShape sh = msm_shape(n, B);
+  { Stage st(c, "msm_sort_h"); TRY(msm_sort(c, c->hsc.as<Fr>(), sh)); }
+  { Stage st(c, "msm_H"); TRY(msm_run<Fq>(c, z->pH.as<G1Affine>(), sh, r1 + 3 * (size_t)B)); }
+  {
+    Stage st(c, "finalize");
+    TRY(c->t_g1.reserve(3 * (size_t)B * sizeof(G1Xyzz)));
+    TRY(c->t_g2.reserve((size_t)B * sizeof(G2Xyzz)));
+    TRY(c->pis.reserve(2 * (size_t)B * sizeof(G1Xyzz)));
+    TRY(c->var.reserve(2 * (size_t)B * sizeof(G1Xyzz)));
+    TRY(c->proofs.reserve((size_t)B * 256));
+    ZK_LAUNCH(k_fin_fixed, (size_t)B * 4, 32, c->stream, z->vk, rs_dev, B, c->t_g1.as<G1Xyzz>(), c->t_g2.as<G2Xyzz>());
+    ZK_LAUNCH(k_fin_var, (size_t)B * 2, 32, c->stream, z->vk, rs_dev, B, r1, c->t_g1.as<G1Xyzz>(), c->pis.as<G1Xyzz>(),
+              c->var.as<G1Xyzz>());
+    ZK_LAUNCH(k_fin_write, (size_t)B * 3, 32, c->stream, z->vk, B, r1, c->res_g2.as<G2Xyzz>(), c->t_g1.as<G1Xyzz>(),
+              c->t_g2.as<G2Xyzz>(), c->pis.as<G1Xyzz>(), c->var.as<G1Xyzz>(), c->proofs.as<Fq>());
+  }
+  CU(cudaGetLastError());
+  return 0;
+}
+
+static int stage_rs(zkfl_ctx* c, const uint8_t* rs, int B) {
+  std::vector<uint8_t> tmp;
+  if (!rs) {  // snarkjs: r, s <- Fr.random()
+    tmp.resize((size_t)B * 64);
+    FILE* f = fopen("/dev/urandom", "rb");
+    if (!f) return fail(ZKFL_ERR_ARG, "cannot open /dev/urandom");
+    for (size_t i = 0; i < (size_t)B * 2; i++) {
+      do {
+        if (fread(&tmp[32 * i], 1, 32, f) != 32) { fclose(f); return fail(ZKFL_ERR_ARG, "urandom read failed"); }
+        tmp[32 * i + 31] &= 0x3f;
+      } while (!fr_bytes_lt_mod(&tmp[32 * i]));
+    }
+    fclose(f);
+    rs = tmp.data();
+  } else {
+    for (size_t i = 0; i < (size_t)B * 2; i++)
+      if (!fr_bytes_lt_mod(rs + 32 * i)) return fail(ZKFL_ERR_ARG, "blinding scalar not reduced mod r");
+  }
+  TRY(c->stage_rs.reserve((size_t)B * 64));
+  CU(cudaMemcpyAsync(c->stage_rs.p, rs, (size_t)B * 64, cudaMemcpyHostToDevice, c->stream));
+  if (!tmp.empty()) CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+static int run_witness(zkfl_ctx* c, const zkfl_circuit* circ, const uint8_t* inputs_host, uint32_t B) {
+  Stage st(c, "witness");
+  TRY(c->w.reserve((size_t)circ->n_wires * B * sizeof(Fr)));
+  if (inputs_host) {
+    TRY(c->stage_in.reserve((size_t)circ->n_inputs * B * sizeof(Fr)));
+    CU(cudaMemcpyAsync(c->stage_in.p, inputs_host, (size_t)circ->n_inputs * B * sizeof(Fr), cudaMemcpyHostToDevice, c->stream));
+  }
+  ZK_LAUNCH(k_aos_to_soa, (size_t)circ->n_inputs * B, 256, c->stream, c->stage_in.as<Fr>(), c->w.as<Fr>(), circ->n_inputs, B, 1u);
+  ZK_LAUNCH(k_witness, B, 32, c->stream, circ->dev, c->w.as<Fr>(), B);
+  CU(cudaGetLastError());
+  return 0;
+}
+
+static int fetch_publics(zkfl_ctx* c, uint32_t n_public, uint32_t B, uint8_t* publics_out) {
+  if (!publics_out || !n_public) return 0;
+  TRY(c->pubs.reserve((size_t)n_public * B * sizeof(Fr)));
+  ZK_LAUNCH(k_soa_to_aos, (size_t)n_public * B, 256, c->stream, c->w.as<Fr>() + B, c->pubs.as<Fr>(), n_public, B);
+  CU(cudaMemcpyAsync(publics_out, c->pubs.p, (size_t)n_public * B * sizeof(Fr), cudaMemcpyDeviceToHost, c->stream));
+  return 0;
+}
+
+static int check_r1cs_device(zkfl_ctx* c, const zkfl_r1cs* r, uint32_t B, uint32_t* first_bad) {
+  Stage st(c, "r1cs_check");
+  TRY(c->bad.reserve((size_t)B * 4));
+  CU(cudaMemsetAsync(c->bad.p, 0xFF, (size_t)B * 4, c->stream));
+  ZK_LAUNCH(k_r1cs_check, (size_t)r->n_constraints * B, 128, c->stream, r->A.dev(), r->B.dev(), r->C.dev(), c->w.as<Fr>(),
+            r->n_constraints, B, c->bad.as<uint32_t>());
+  std::vector<uint32_t> host(B);
+  CU(cudaMemcpyAsync(host.data(), c->bad.p, (size_t)B * 4, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  int bad = 0;
+  for (uint32_t b = 0; b < B; b++) { if (first_bad) first_bad[b] = host[b]; if (host[b] != 0xFFFFFFFFu) bad++; }
+  if (bad) return fail(ZKFL_ERR_ASSERT, "Assert Failed: " + std::to_string(bad) + " of " + std::to_string(B) + " witnesses violate a constraint");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------ C ABI
+extern "C" {
+
+const char* zkfl_last_error(void) { return g_err.c_str(); }
+const char* zkfl_version(void) {
+#ifdef ZKFL_EMUL
+  return "zkfl 0.1.0 (host emulation, tests only)";
+#else
+  return "zkfl 0.1.0 (sm_100a)";
+#endif
+}
+uint64_t zkfl_launch_count(void) { return g_launches.load(); }
+
+int zkfl_ctx_create(int device, zkfl_ctx** out) {
+  if (!out) return fail(ZKFL_ERR_ARG, "out is NULL");
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) return fail(ZKFL_ERR_CUDA, "no CUDA device available (libzkfl has no CPU path)");
+  if (device < 0 || device >= n) return fail(ZKFL_ERR_ARG, "device index out of range");
+  CU(cudaSetDevice(device));
+  zkfl_ctx* c = new zkfl_ctx();
+  c->device = device;
+  cudaError_t e = cudaStreamCreate(&c->stream);
+  if (e != cudaSuccess) { delete c; return fail(ZKFL_ERR_CUDA, "cudaStreamCreate failed"); }
+  *out = c;
+  return 0;
+}
+void zkfl_ctx_free(zkfl_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  for (auto& r : c->pending) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int zkfl_prof_enable(zkfl_ctx* c, int on) {
+  if (!c) return fail(ZKFL_ERR_ARG, "ctx is NULL");
+  c->prof = on != 0;
+  if (on) { c->agg.clear(); c->order.clear(); }
+  return 0;
+}
+int zkfl_prof_read(zkfl_ctx* c, char* buf, size_t cap) {
+  if (!c || !buf || !cap) return fail(ZKFL_ERR_ARG, "bad argument");
+  CU(cudaStreamSynchronize(c->stream));
+  for (auto& r : c->pending) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, r.e0, r.e1);
+    if (!c->agg.count(r.name)) c->order.push_back(r.name);
+    ProfAgg& a = c->agg[r.name];
+    a.ms += ms; a.launches += r.launches; a.calls++;
+    cudaEventDestroy(r.e0); cudaEventDestroy(r.e1);
+  }
+  c->pending.clear();
+  std::string s;
+  for (auto& name : c->order) {
+    const ProfAgg& a = c->agg[name];
+    char line[256];
+    snprintf(line, sizeof line, "%s %.6f %llu %llu\n", name.c_str(), a.ms, (unsigned long long)a.launches, (unsigned long long)a.calls);
+    s += line;
+  }
+  if (s.size() + 1 > cap) return fail(ZKFL_ERR_ARG, "buffer too small");
+  memcpy(buf, s.c_str(), s.size() + 1);
+  return 0;
+}
+
+// ---- circuit (.zkwp)
+int zkfl_circuit_load(zkfl_ctx* c, const uint8_t* d, size_t len, zkfl_circuit** out) {
+  if (!c || !out) return fail(ZKFL_ERR_ARG, "bad argument");
+  std::map<uint32_t, Sec> S;
+  TRY(parse_sections(d, len, "zkwp", S));
+  for (uint32_t id = 1; id <= 7; id++) if (!S.count(id)) return fail(ZKFL_ERR_FORMAT, "zkwp: missing section");
+  if (S[1].len != 32) return fail(ZKFL_ERR_FORMAT, "zkwp: bad header");
+  uint32_t h[8]; memcpy(h, S[1].p, 32);
+  uint32_t n_lcs = h[4], n_terms = h[5], n_pos = h[6], n_widths = h[7];
+  if (S[2].len != 20ull * h[3] || S[3].len != 4ull * (n_lcs + 1) || S[4].len != 4ull * n_terms || S[5].len != 32ull * n_terms ||
+      S[6].len != 4ull * n_pos)
+    return fail(ZKFL_ERR_FORMAT, "zkwp: section size mismatch");
+  std::unique_ptr<zkfl_circuit> k(new zkfl_circuit());
+  k->ctx = c; k->n_wires = h[0]; k->n_public = h[1]; k->n_inputs = h[2]; k->n_ops = h[3];
+  CU(cudaSetDevice(c->device));
+  TRY(upload(c, k->ops, (const uint32_t*)S[2].p, 5 * (size_t)h[3]));
+  TRY(upload(c, k->lc_off, (const uint32_t*)S[3].p, (size_t)n_lcs + 1));
+  TRY(upload(c, k->lc_wire, (const uint32_t*)S[4].p, n_terms));
+  std::vector<Fr> coef(n_terms);
+  for (uint32_t i = 0; i < n_terms; i++) {
+    if (!fr_bytes_lt_mod(S[5].p + 32 * (size_t)i)) return fail(ZKFL_ERR_FORMAT, "zkwp: coefficient not reduced");
+    coef[i] = fr_from_bytes_canonical(S[5].p + 32 * (size_t)i).to_mont().to_mont();  // coef * R^2
+  }
+  TRY(upload(c, k->lc_coef, coef.data(), coef.size()));
+  TRY(upload(c, k->pos_in, (const uint32_t*)S[6].p, n_pos));
+  // poseidon constants -> Montgomery, one pool
+  std::vector<Fr> pool;
+  struct Pk { uint32_t t, rounds, rp; size_t c_off, m_off; };
+  std::vector<Pk> pks;
+  const uint8_t* q = S[7].p; const uint8_t* qe = q + S[7].len;
+  for (uint32_t w = 0; w < n_widths; w++) {
+    if (q + 16 > qe) return fail(ZKFL_ERR_FORMAT, "zkwp: truncated poseidon table");
+    uint32_t hh[4]; memcpy(hh, q, 16); q += 16;
+    Pk p; p.t = hh[0]; p.rounds = hh[1]; p.rp = hh[2];
+    if (p.t < 2 || p.t > 17 || p.rounds != 8 + p.rp) return fail(ZKFL_ERR_FORMAT, "zkwp: bad poseidon width");
+    size_t cnt = (size_t)p.rounds * p.t + (size_t)p.t * p.t;
+    if (q + 32 * cnt > qe) return fail(ZKFL_ERR_FORMAT, "zkwp: truncated poseidon constants");
+    p.c_off = pool.size(); p.m_off = p.c_off + (size_t)p.rounds * p.t;
+    for (size_t i = 0; i < cnt; i++) { pool.push_back(fr_from_bytes_canonical(q).to_mont()); q += 32; }
+    pks.push_back(p);
+  }
+  TRY(upload(c, k->pconst, pool.data(), pool.size()));
+  memset(&k->dev, 0, sizeof k->dev);
+  k->dev.n_wires = k->n_wires; k->dev.n_inputs = k->n_inputs; k->dev.n_ops = k->n_ops;
+  k->dev.ops = k->ops.as<uint32_t>(); k->dev.lc_off = k->lc_off.as<uint32_t>(); k->dev.lc_wire = k->lc_wire.as<uint32_t>();
+  k->dev.lc_coef = k->lc_coef.as<Fr>(); k->dev.pos_in = k->pos_in.as<uint32_t>();
+  for (auto& p : pks) {
+    k->dev.pk[p.t].rounds = p.rounds; k->dev.pk[p.t].rp = p.rp;
+    k->dev.pk[p.t].C = k->pconst.as<Fr>() + p.c_off; k->dev.pk[p.t].M = k->pconst.as<Fr>() + p.m_off;
+  }
+  // validate ops reference existing widths / wires
+  const uint32_t* ops = (const uint32_t*)S[2].p;
+  for (uint32_t o = 0; o < k->n_ops; o++) {
+    const uint32_t* op = ops + 5 * (size_t)o;
+    if (op[0] < 1 || op[0] > 4 || op[1] >= k->n_wires) return fail(ZKFL_ERR_FORMAT, "zkwp: bad op");
+    if (op[0] == 4 && (op[2] > 17 || !k->dev.pk[op[2]].C)) return fail(ZKFL_ERR_FORMAT, "zkwp: poseidon width without constants");
+  }
+  *out = k.release();
+  return 0;
+}
+void zkfl_circuit_free(zkfl_circuit* k) { if (k) { cudaSetDevice(k->ctx->device); delete k; } }
+int zkfl_circuit_info(const zkfl_circuit* k, uint32_t info[4]) {
+  if (!k || !info) return fail(ZKFL_ERR_ARG, "bad argument");
+  info[0] = k->n_wires; info[1] = k->n_public; info[2] = k->n_inputs; info[3] = k->n_ops;
+  return 0;
+}
+
+// ---- r1cs
+int zkfl_r1cs_load(zkfl_ctx* c, const uint8_t* d, size_t len, zkfl_r1cs** out) {
+  if (!c || !out) return fail(ZKFL_ERR_ARG, "bad argument");
+  std::map<uint32_t, Sec> S;
+  TRY(parse_sections(d, len, "r1cs", S));
+  if (!S.count(1) || !S.count(2) || S[1].len < 64) return fail(ZKFL_ERR_FORMAT, "r1cs: missing section");
+  const uint8_t* h = S[1].p;
+  uint32_t n8; memcpy(&n8, h, 4);
+  if (n8 != 32) return fail(ZKFL_ERR_FORMAT, "r1cs: field size");
+  uint32_t n_wires, n_constraints; memcpy(&n_wires, h + 36, 4); memcpy(&n_constraints, h + 60, 4);
+  std::vector<uint32_t> rows[3], wires[3]; std::vector<Fr> coefs[3];
+  const uint8_t* p = S[2].p; const uint8_t* pe = p + S[2].len;
+  for (uint32_t r = 0; r < n_constraints; r++)
+    for (int k = 0; k < 3; k++) {
+      if (p + 4 > pe) return fail(ZKFL_ERR_FORMAT, "r1cs: truncated");
+      uint32_t nt; memcpy(&nt, p, 4); p += 4;
+      if ((uint64_t)(pe - p) < 36ull * nt) return fail(ZKFL_ERR_FORMAT, "r1cs: truncated");
+      for (uint32_t t = 0; t < nt; t++) {
+        uint32_t wi; memcpy(&wi, p, 4);
+        if (wi >= n_wires) return fail(ZKFL_ERR_FORMAT, "r1cs: wire out of range");
+        rows[k].push_back(r); wires[k].push_back(wi);
+        coefs[k].push_back(fr_from_bytes_canonical(p + 4).to_mont().to_mont());
+        p += 36;
+      }
+    }
+  std::unique_ptr<zkfl_r1cs> r(new zkfl_r1cs());
+  r->ctx = c; r->n_wires = n_wires; r->n_constraints = n_constraints;
+  CU(cudaSetDevice(c->device));
+  CsrHost hA, hB, hC;
+  coo_to_csr(n_constraints, rows[0], wires[0], coefs[0], hA);
+  coo_to_csr(n_constraints, rows[1], wires[1], coefs[1], hB);
+  coo_to_csr(n_constraints, rows[2], wires[2], coefs[2], hC);
+  TRY(upload_csr(c, hA, r->A)); TRY(upload_csr(c, hB, r->B)); TRY(upload_csr(c, hC, r->C));
+  *out = r.release();
+  return 0;
+}
+void zkfl_r1cs_free(zkfl_r1cs* r) { if (r) { cudaSetDevice(r->ctx->device); delete r; } }
+
+// ---- zkey
+int zkfl_zkey_load(zkfl_ctx* c, const uint8_t* d, size_t len, zkfl_zkey** out) {
+  if (!c || !out) return fail(ZKFL_ERR_ARG, "bad argument");
+  std::map<uint32_t, Sec> S;
+  TRY(parse_sections(d, len, "zkey", S));
+  for (uint32_t id : {1u, 2u, 4u, 5u, 6u, 7u, 8u, 9u}) if (!S.count(id)) return fail(ZKFL_ERR_FORMAT, "zkey: missing section");
+  uint32_t proto; if (S[1].len < 4) return fail(ZKFL_ERR_FORMAT, "zkey: bad section 1");
+  memcpy(&proto, S[1].p, 4);
+  if (proto != 1) return fail(ZKFL_ERR_FORMAT, "zkey: not a groth16 key");
+  const uint8_t* h = S[2].p;
+  if (S[2].len != 84 + 64 * 3 + 128 * 3) return fail(ZKFL_ERR_FORMAT, "zkey: bad header size");
+  uint32_t n8q, n8r; memcpy(&n8q, h, 4); memcpy(&n8r, h + 36, 4);
+  if (n8q != 32 || n8r != 32) return fail(ZKFL_ERR_FORMAT, "zkey: not BN254");
+  for (int i = 0; i < 8; i++) {
+    uint32_t a, b; memcpy(&a, h + 4 + 4 * i, 4); memcpy(&b, h + 40 + 4 * i, 4);
+    if (a != FqP::mod(i) || b != FrP::mod(i)) return fail(ZKFL_ERR_FORMAT, "zkey: not BN254");
+  }
+  std::unique_ptr<zkfl_zkey> z(new zkfl_zkey());
+  z->ctx = c;
+  memcpy(&z->n_vars, h + 72, 4); memcpy(&z->n_public, h + 76, 4); memcpy(&z->domain, h + 80, 4);
+  uint32_t n = z->domain, m = z->n_vars, l = z->n_public;
+  if (n < 2 || (n & (n - 1)) || m <= l) return fail(ZKFL_ERR_FORMAT, "zkey: bad sizes");
+  z->log_n = 0; while ((1u << z->log_n) < n) z->log_n++;
+  if (z->log_n > 27) return fail(ZKFL_ERR_FORMAT, "zkey: domain too large");
+  size_t p = 84;
+  memcpy(&z->vk.alpha1, h + p, 64); p += 64;
+  memcpy(&z->vk.beta1, h + p, 64); p += 64;
+  memcpy(&z->vk.beta2, h + p, 128); p += 128;
+  p += 128;
+  memcpy(&z->vk.delta1, h + p, 64); p += 64;
+  memcpy(&z->vk.delta2, h + p, 128);
+  if (S[5].len != 64ull * m || S[6].len != 64ull * m || S[7].len != 128ull * m || S[8].len != 64ull * (m - l - 1) || S[9].len != 64ull * n)
+    return fail(ZKFL_ERR_FORMAT, "zkey: point section size mismatch");
+  uint32_t n_coef; if (S[4].len < 4) return fail(ZKFL_ERR_FORMAT, "zkey: bad coeffs");
+  memcpy(&n_coef, S[4].p, 4);
+  if (S[4].len != 4 + 44ull * n_coef) return fail(ZKFL_ERR_FORMAT, "zkey: coeff section size mismatch");
+  std::vector<uint32_t> rows[2], wires[2]; std::vector<Fr> coefs[2];
+  for (uint32_t i = 0; i < n_coef; i++) {
+    const uint8_t* e = S[4].p + 4 + 44 * (size_t)i;
+    uint32_t mt, cc, ss; memcpy(&mt, e, 4); memcpy(&cc, e + 4, 4); memcpy(&ss, e + 8, 4);
+    if (mt > 1 || cc >= n || ss >= m) return fail(ZKFL_ERR_FORMAT, "zkey: coefficient out of range");
+    rows[mt].push_back(cc); wires[mt].push_back(ss); coefs[mt].push_back(fr_from_bytes_canonical(e + 12));  // already coef * R^2
+  }
+  CU(cudaSetDevice(c->device));
+  CsrHost hA, hB;
+  coo_to_csr(n, rows[0], wires[0], coefs[0], hA);
+  coo_to_csr(n, rows[1], wires[1], coefs[1], hB);
+  TRY(upload_csr(c, hA, z->A)); TRY(upload_csr(c, hB, z->B));
+  TRY(upload(c, z->pA, S[5].p, S[5].len)); TRY(upload(c, z->pB1, S[6].p, S[6].len)); TRY(upload(c, z->pB2, S[7].p, S[7].len));
+  TRY(upload(c, z->pH, S[9].p, S[9].len));
+  {  // C bases padded to n_vars so all four witness MSMs share one sorted index list
+    std::vector<uint8_t> full(64 * (size_t)m, 0);
+    memcpy(full.data() + 64 * (size_t)(l + 1), S[8].p, S[8].len);
+    TRY(upload(c, z->pC, full.data(), full.size()));
+  }
+  {  // twiddles: w^k, w^-k (k < n/2); coset[p] = n^-1 * inc^bitrev(p), inc = w_{2n}
+    Fr wn = fr_root_of_unity((int)z->log_n), wi = wn.inv();
+    std::vector<Fr> f(n / 2), iv(n / 2), cs(n);
+    Fr a = Fr::one(), b = Fr::one();
+    for (uint32_t k = 0; k < n / 2; k++) { f[k] = a; iv[k] = b; a = a * wn; b = b * wi; }
+    Fr inc = fr_root_of_unity((int)z->log_n + 1);
+    Fr nn = Fr::zero(); nn.v[0] = n;
+    Fr cur = nn.to_mont().inv();
+    for (uint32_t i = 0; i < n; i++) {
+      uint32_t rev = 0;
+      for (uint32_t bit = 0; bit < z->log_n; bit++) if (i & (1u << bit)) rev |= 1u << (z->log_n - 1 - bit);
+      cs[rev] = cur;  // position rev holds coefficient i after the DIF pass
+      cur = cur * inc;
+    }
+    TRY(upload(c, z->tw_fwd, f.data(), f.size())); TRY(upload(c, z->tw_inv, iv.data(), iv.size()));
+    TRY(upload(c, z->coset, cs.data(), cs.size()));
+  }
+  *out = z.release();
+  return 0;
+}
+void zkfl_zkey_free(zkfl_zkey* z) { if (z) { cudaSetDevice(z->ctx->device); delete z; } }
+int zkfl_zkey_info(const zkfl_zkey* z, uint32_t info[3]) {
+  if (!z || !info) return fail(ZKFL_ERR_ARG, "bad argument");
+  info[0] = z->n_vars; info[1] = z->n_public; info[2] = z->domain;
+  return 0;
+}
+
+// ---- witness
+int zkfl_wtns_calculate_batch(zkfl_ctx* c, const zkfl_circuit* k, const zkfl_r1cs* r, const uint8_t* inputs, int B,
+                              uint8_t* wtns_out, uint32_t* first_bad) {
+  if (!c || !k || !inputs || B <= 0) return fail(ZKFL_ERR_ARG, "bad argument");
+  if (r && r->n_wires != k->n_wires) return fail(ZKFL_ERR_ARG, "r1cs does not match circuit");
+  for (size_t i = 0; i < (size_t)B * k->n_inputs; i++)
+    if (!fr_bytes_lt_mod(inputs + 32 * i)) return fail(ZKFL_ERR_ARG, "input not reduced mod r");
+  CU(cudaSetDevice(c->device));
+  TRY(run_witness(c, k, inputs, (uint32_t)B));
+  if (wtns_out) {
+    TRY(c->aos.reserve((size_t)k->n_wires * B * sizeof(Fr)));
+    ZK_LAUNCH(k_soa_to_aos, (size_t)k->n_wires * B, 256, c->stream, c->w.as<Fr>(), c->aos.as<Fr>(), k->n_wires, (uint32_t)B);
+    CU(cudaMemcpyAsync(wtns_out, c->aos.p, (size_t)k->n_wires * B * sizeof(Fr), cudaMemcpyDeviceToHost, c->stream));
+  }
+  int rc = 0;
+  if (r) rc = check_r1cs_device(c, r, (uint32_t)B, first_bad);
+  CU(cudaStreamSynchronize(c->stream));
+  return rc;
+}
+int zkfl_r1cs_check_batch(zkfl_ctx* c, const zkfl_r1cs* r, const uint8_t* wtns, int B, uint32_t* first_bad) {
+  if (!c || !r || !wtns || B <= 0) return fail(ZKFL_ERR_ARG, "bad argument");
+  CU(cudaSetDevice(c->device));
+  size_t cnt = (size_t)r->n_wires * B;
+  TRY(c->aos.reserve(cnt * sizeof(Fr))); TRY(c->w.reserve(cnt * sizeof(Fr)));
+  CU(cudaMemcpyAsync(c->aos.p, wtns, cnt * sizeof(Fr), cudaMemcpyHostToDevice, c->stream));
+  ZK_LAUNCH(k_aos_to_soa, cnt, 256, c->stream, c->aos.as<Fr>(), c->w.as<Fr>(), r->n_wires, (uint32_t)B, 0u);
+  return check_r1cs_device(c, r, (uint32_t)B, first_bad);
+}
+
+// ---- prove
+int zkfl_groth16_prove_batch(zkfl_ctx* c, const zkfl_zkey* z, const uint8_t* wtns, const uint8_t* rs, int B,
+                             uint8_t* proofs_out, uint8_t* publics_out) {
+  if (!c || !z || !wtns || !proofs_out || B <= 0) return fail(ZKFL_ERR_ARG, "bad argument");
+  CU(cudaSetDevice(c->device));
+  size_t cnt = (size_t)z->n_vars * B;
+  TRY(stage_rs(c, rs, B));
+  {
+    Stage st(c, "upload_wtns");
+    TRY(c->aos.reserve(cnt * sizeof(Fr))); TRY(c->w.reserve(cnt * sizeof(Fr)));
+    CU(cudaMemcpyAsync(c->aos.p, wtns, cnt * sizeof(Fr), cudaMemcpyHostToDevice, c->stream));
+    ZK_LAUNCH(k_aos_to_soa, cnt, 256, c->stream, c->aos.as<Fr>(), c->w.as<Fr>(), z->n_vars, (uint32_t)B, 0u);
+  }
+  TRY(prove_from_device_witness(c, z, c->stage_rs.as<Fr>(), (uint32_t)B));
+  CU(cudaMemcpyAsync(proofs_out, c->proofs.p, (size_t)B * 256, cudaMemcpyDeviceToHost, c->stream));
+  TRY(fetch_publics(c, z->n_public, (uint32_t)B, publics_out));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+int zkfl_groth16_full_prove_batch(zkfl_ctx* c, const zkfl_circuit* k, const zkfl_zkey* z, const uint8_t* inputs,
+                                  const uint8_t* rs, int B, uint8_t* proofs_out, uint8_t* publics_out) {
+  if (!c || !k || !z || !inputs || !proofs_out || B <= 0) return fail(ZKFL_ERR_ARG, "bad argument");
+  if (k->n_wires != z->n_vars || k->n_public != z->n_public) return fail(ZKFL_ERR_ARG, "circuit and zkey do not match");
+  CU(cudaSetDevice(c->device));
+  TRY(stage_rs(c, rs, B));
+  TRY(run_witness(c, k, inputs, (uint32_t)B));
+  TRY(prove_from_device_witness(c, z, c->stage_rs.as<Fr>(), (uint32_t)B));
+  CU(cudaMemcpyAsync(proofs_out, c->proofs.p, (size_t)B * 256, cudaMemcpyDeviceToHost, c->stream));
+  TRY(fetch_publics(c, z->n_public, (uint32_t)B, publics_out));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+int zkfl_full_prove_stage(zkfl_ctx* c, const zkfl_circuit* k, const zkfl_zkey* z, const uint8_t* inputs, const uint8_t* rs, int B) {
+  if (!c || !k || !z || !inputs || B <= 0) return fail(ZKFL_ERR_ARG, "bad argument");
+  if (k->n_wires != z->n_vars) return fail(ZKFL_ERR_ARG, "circuit and zkey do not match");
+  CU(cudaSetDevice(c->device));
+  TRY(stage_rs(c, rs, B));
+  TRY(c->stage_in.reserve((size_t)k->n_inputs * B * sizeof(Fr)));
+  CU(cudaMemcpyAsync(c->stage_in.p, inputs, (size_t)k->n_inputs * B * sizeof(Fr), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+int zkfl_full_prove_run(zkfl_ctx* c, const zkfl_circuit* k, const zkfl_zkey* z, int B) {
+  if (!c || !k || !z || B <= 0) return fail(ZKFL_ERR_ARG, "bad argument");
+  CU(cudaSetDevice(c->device));
+  TRY(run_witness(c, k, nullptr, (uint32_t)B));
+  TRY(prove_from_device_witness(c, z, c->stage_rs.as<Fr>(), (uint32_t)B));
+  return 0;  // asynchronous: the caller brackets with its own events / zkfl_full_prove_fetch
+}
+int zkfl_full_prove_fetch(zkfl_ctx* c, int B, uint8_t* proofs_out) {
+  if (!c || B <= 0) return fail(ZKFL_ERR_ARG, "bad argument");
+  CU(cudaSetDevice(c->device));
+  if (proofs_out) CU(cudaMemcpyAsync(proofs_out, c->proofs.p, (size_t)B * 256, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+// ---- standalone MSM
+int zkfl_msm_bases_load(zkfl_ctx* c, const uint8_t* bases, size_t n, int group, void** handle) {
+  if (!c || !bases || !handle || (group != 1 && group != 2) || n == 0 || n > 0x7FFFFFFFu) return fail(ZKFL_ERR_ARG, "bad argument");
+  CU(cudaSetDevice(c->device));
+  std::unique_ptr<MsmBases> b(new MsmBases());
+  b->ctx = c; b->group = group; b->n = n;
+  TRY(upload(c, b->pts, bases, n * (group == 1 ? 64 : 128)));
+  *handle = b.release();
+  return 0;
+}
+void zkfl_msm_bases_free(void* h) { if (h) { MsmBases* b = (MsmBases*)h; cudaSetDevice(b->ctx->device); delete b; } }
+int zkfl_msm_run(zkfl_ctx* c, void* handle, const uint8_t* scalars, size_t n, uint8_t* out) {
+  MsmBases* b = (MsmBases*)handle;
+  if (!c || !b || n == 0 || n > b->n) return fail(ZKFL_ERR_ARG, "bad argument");
+  CU(cudaSetDevice(c->device));
+  TRY(c->msm_sc.reserve(n * sizeof(Fr)));
+  if (scalars) CU(cudaMemcpyAsync(c->msm_sc.p, scalars, n * sizeof(Fr), cudaMemcpyHostToDevice, c->stream));
+  MsmShape s = msm_shape((uint32_t)n, 1);
+  { Stage st(c, "msm_sort"); TRY(msm_sort(c, c->msm_sc.as<Fr>(), s)); }
+  TRY(c->msm_out.reserve(sizeof(G2Xyzz) + sizeof(G2Affine)));
+  uint8_t* o = c->msm_out.as<uint8_t>();
+  if (b->group == 1) {
+    { Stage st(c, "msm_g1"); TRY(msm_run<Fq>(c, b->pts.as<G1Affine>(), s, (G1Xyzz*)o)); }
+    ZK_LAUNCH(k_to_affine_canonical<Fq>, 1, 32, c->stream, (const G1Xyzz*)o, (size_t)1, (G1Affine*)(o + sizeof(G2Xyzz)));
+  } else {
+    { Stage st(c, "msm_g2"); TRY(msm_run<Fq2>(c, b->pts.as<G2Affine>(), s, (G2Xyzz*)o)); }
+    ZK_LAUNCH(k_to_affine_canonical<Fq2>, 1, 32, c->stream, (const G2Xyzz*)o, (size_t)1, (G2Affine*)(o + sizeof(G2Xyzz)));
+  }
+  if (out) {
+    CU(cudaMemcpyAsync(out, o + sizeof(G2Xyzz), b->group == 1 ? 64 : 128, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+  }
+  return 0;
+}
+static int msm_oneshot(zkfl_ctx* c, const uint8_t* bases, const uint8_t* scalars, size_t n, int group, uint8_t* out) {
+  if (!scalars || !out) return fail(ZKFL_ERR_ARG, "bad argument");
+  void* h = nullptr;
+  TRY(zkfl_msm_bases_load(c, bases, n, group, &h));
+  int rc = zkfl_msm_run(c, h, scalars, n, out);
+  zkfl_msm_bases_free(h);
+  return rc;
+}
+int zkfl_g1_msm(zkfl_ctx* c, const uint8_t* bases, const uint8_t* scalars, size_t n, uint8_t out[64]) { return msm_oneshot(c, bases, scalars, n, 1, out); }
+int zkfl_g2_msm(zkfl_ctx* c, const uint8_t* bases, const uint8_t* scalars, size_t n, uint8_t out[128]) { return msm_oneshot(c, bases, scalars, n, 2, out); }
+
+// ---- setup support
+}  // extern "C"
+template <class F>
+static int gen_mul(zkfl_ctx* c, const Affine<F>& gen, const uint8_t* scalars, size_t n, uint8_t* out) {
+  if (!c || !scalars || !out || n == 0) return fail(ZKFL_ERR_ARG, "bad argument");
+  for (size_t i = 0; i < n; i++) if (!fr_bytes_lt_mod(scalars + 32 * i)) return fail(ZKFL_ERR_ARG, "scalar not reduced mod r");
+  CU(cudaSetDevice(c->device));
+  DevBuf sc, pts;
+  TRY(sc.reserve(n * sizeof(Fr))); TRY(pts.reserve(n * sizeof(Affine<F>)));
+  CU(cudaMemcpyAsync(sc.p, scalars, n * sizeof(Fr), cudaMemcpyHostToDevice, c->stream));
+  ZK_LAUNCH(k_gen_mul<F>, n, 64, c->stream, gen, sc.as<Fr>(), n, pts.as<Affine<F>>());
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(out, pts.p, n * sizeof(Affine<F>), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+static Fq fq_small(uint32_t v) { Fq r = Fq::zero(); r.v[0] = v; return r.to_mont(); }
+static Fq fq_words(const uint32_t (&w)[8]) { Fq r; for (int i = 0; i < 8; i++) r.v[i] = w[i]; return r.to_mont(); }
+extern "C" {
+int zkfl_g1_mul_generator(zkfl_ctx* c, const uint8_t* scalars, size_t n, uint8_t* out) {
+  G1Affine g; g.x = fq_small(1); g.y = fq_small(2);
+  return gen_mul<Fq>(c, g, scalars, n, out);
+}
+int zkfl_g2_mul_generator(zkfl_ctx* c, const uint8_t* scalars, size_t n, uint8_t* out) {
+  static const uint32_t X0[8] = {0xd992f6edu, 0x46debd5cu, 0xf75edaddu, 0x674322d4u, 0x5e5c4479u, 0x426a0066u, 0x121f1e76u, 0x1800deefu};
+  static const uint32_t X1[8] = {0xaef312c2u, 0x97e485b7u, 0x35a9e712u, 0xf1aa4933u, 0x31fb5d25u, 0x7260bfb7u, 0x920d483au, 0x198e9393u};
+  static const uint32_t Y0[8] = {0x66fa7daau, 0x4ce6cc01u, 0x0c43d37bu, 0xe3d1e769u, 0x8dcb408fu, 0x4aab7180u, 0xdb8c6debu, 0x12c85ea5u};
+  static const uint32_t Y1[8] = {0xd122975bu, 0x55acdadcu, 0x70b38ef3u, 0xbc4b3133u, 0x690c3395u, 0xec9e99adu, 0x585ff075u, 0x090689d0u};
+  G2Affine g; g.x.a = fq_words(X0); g.x.b = fq_words(X1); g.y.a = fq_words(Y0); g.y.b = fq_words(Y1);
+  return gen_mul<Fq2>(c, g, scalars, n, out);
+}
+
+int zkfl_bench_modmul(zkfl_ctx* c, size_t n_threads, uint32_t iters, float* ms_out) {
+  if (!c || !ms_out || n_threads == 0) return fail(ZKFL_ERR_ARG, "bad argument");
+  CU(cudaSetDevice(c->device));
+  DevBuf d;
+  TRY(d.reserve(n_threads * sizeof(Fq)));
+  CU(cudaMemsetAsync(d.p, 0x5a, n_threads * sizeof(Fq), c->stream));
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+  ZK_LAUNCH(k_bench_modmul, n_threads, 256, c->stream, d.as<Fq>(), n_threads, 4u);  // warm-up
+  CU(cudaEventRecord(e0, c->stream));
+  ZK_LAUNCH(k_bench_modmul, n_threads, 256, c->stream, d.as<Fq>(), n_threads, iters);
+  CU(cudaEventRecord(e1, c->stream));
+  CU(cudaEventSynchronize(e1));
+  CU(cudaEventElapsedTime(ms_out, e0, e1));
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  return 0;
+}
+
+}  // extern "C"

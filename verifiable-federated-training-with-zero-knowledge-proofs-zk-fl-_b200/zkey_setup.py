@@ -1,0 +1,141 @@
+"""`snarkjs groth16 setup <r1cs> <ptau> <zkey>` + `zkey contribute` replacement
+(tests/full_system_simulation.mjs:714-731).
+
+No `.ptau` exists in the reference tree and none can be fetched, so the structured reference string
+is derived from explicit toxic waste (tau, alpha, beta, delta; gamma = 1 as in snarkjs).  The field
+arithmetic that builds the key scalars runs on the host (Python ints, one-off per circuit); every
+scalar multiplication k*G1 / k*G2 runs on the GPU (`zkfl_g1_mul_generator`).  Output: a `.zkey` with
+the exact snarkjs section layout, including the nPublic+1 extra A rows and the
+odd-coset Lagrange H points the snarkjs prover expects.
+"""
+from __future__ import annotations
+
+import hashlib
+import struct
+
+from .formats import FQ, FR, read_container, write_container
+
+_R2 = pow(1 << 256, 2, FR)
+
+
+def toxic_from_seed(seed: bytes):
+    out = []
+    ctr = 0
+    while len(out) < 4:
+        v = int.from_bytes(hashlib.sha512(seed + bytes([ctr])).digest(), "little") % FR
+        ctr += 1
+        if v > 1:
+            out.append(v)
+    return tuple(out)  # tau, alpha, beta, delta
+
+
+def root_of_unity(power: int) -> int:
+    w = pow(5, (FR - 1) >> 28, FR)
+    for _ in range(28 - power):
+        w = w * w % FR
+    return w
+
+
+def _batch_inverse(vals):
+    pref, acc = [], 1
+    for v in vals:
+        pref.append(acc)
+        acc = acc * v % FR
+    inv = pow(acc, -1, FR)
+    out = [0] * len(vals)
+    for i in range(len(vals) - 1, -1, -1):
+        out[i] = inv * pref[i] % FR
+        inv = inv * vals[i] % FR
+    return out
+
+
+def lagrange_at(tau: int, lg: int):
+    n = 1 << lg
+    w = root_of_unity(lg)
+    pw, x = [], 1
+    for _ in range(n):
+        pw.append(x)
+        x = x * w % FR
+    zt = (pow(tau, n, FR) - 1) * pow(n, -1, FR) % FR
+    inv = _batch_inverse([(tau - p) % FR for p in pw])
+    return [zt * p % FR * i % FR for p, i in zip(pw, inv)]
+
+
+def parse_r1cs(data: bytes):
+    s = read_container(data, b"r1cs")
+    h = s[1]
+    if struct.unpack_from("<I", h, 0)[0] != 32 or int.from_bytes(h[4:36], "little") != FR:
+        raise ValueError("r1cs: not over the BN254 scalar field")
+    n_wires, n_pub_out, n_pub_in, n_prv_in, n_labels, n_constraints = struct.unpack_from("<IIIIQI", h, 36)
+    body = s[2]
+    mats = ([], [], [])  # per matrix: list of (row, wire, coef)
+    p = 0
+    for row in range(n_constraints):
+        for k in range(3):
+            nt = struct.unpack_from("<I", body, p)[0]
+            p += 4
+            for _ in range(nt):
+                wire = struct.unpack_from("<I", body, p)[0]
+                mats[k].append((row, wire, int.from_bytes(body[p + 4:p + 36], "little")))
+                p += 36
+    return {"n_wires": n_wires, "n_public": n_pub_out + n_pub_in, "n_constraints": n_constraints,
+            "A": mats[0], "B": mats[1], "C": mats[2]}
+
+
+def r1cs_info(data: bytes) -> dict:
+    s = read_container(data, b"r1cs")
+    n_wires, n_pub_out, n_pub_in, n_prv_in, n_labels, n_constraints = struct.unpack_from("<IIIIQI", s[1], 36)
+    return {"nWires": n_wires, "nConstraints": n_constraints, "nPrvInputs": n_prv_in,
+            "nPubInputs": n_pub_in, "nOutputs": n_pub_out, "nLabels": n_labels}
+
+
+def new_zkey(prover, r1cs_bytes: bytes, seed: bytes) -> bytes:
+    """prover: zkfl_b200.api.Prover (its GPU does the scalar multiplications)."""
+    r = parse_r1cs(r1cs_bytes)
+    m, l, nc = r["n_wires"], r["n_public"], r["n_constraints"]
+    tau, alpha, beta, delta = toxic_from_seed(seed)
+    lg = max((nc + l).bit_length(), 1)  # smallest 2^lg >= nc + l + 1
+    n = 1 << lg
+    L = lagrange_at(tau, lg)
+    At, Bt, Ct = [0] * m, [0] * m, [0] * m
+    for row, wire, k in r["A"]:
+        At[wire] = (At[wire] + k * L[row]) % FR
+    for row, wire, k in r["B"]:
+        Bt[wire] = (Bt[wire] + k * L[row]) % FR
+    for row, wire, k in r["C"]:
+        Ct[wire] = (Ct[wire] + k * L[row]) % FR
+    for s in range(l + 1):
+        At[s] = (At[s] + L[nc + s]) % FR
+    dinv = pow(delta, -1, FR)
+    comb = [(beta * a + alpha * b + c) % FR for a, b, c in zip(At, Bt, Ct)]
+    L2 = lagrange_at(tau, lg + 1)
+    h_sc = [L2[2 * i + 1] * dinv % FR for i in range(n)]
+    g1_scalars = ([alpha, beta, delta] + comb[:l + 1] + At + Bt + [c * dinv % FR for c in comb[l + 1:]] + h_sc)
+    g1 = prover.g1_mul_generator(g1_scalars)
+    g2 = prover.g2_mul_generator([beta, 1, delta] + Bt)
+    pos = 0
+
+    def take(cnt):
+        nonlocal pos
+        out = g1[64 * pos:64 * (pos + cnt)]
+        pos += cnt
+        return out
+
+    alpha1, beta1, delta1 = take(1), take(1), take(1)
+    ic, pa, pb1, pc, ph = take(l + 1), take(m), take(m), take(m - l - 1), take(n)
+    beta2, gamma2, delta2, pb2 = g2[:128], g2[128:256], g2[256:384], g2[384:]
+    hdr = (struct.pack("<I", 32) + FQ.to_bytes(32, "little") + struct.pack("<I", 32) + FR.to_bytes(32, "little")
+           + struct.pack("<III", m, l, n) + alpha1 + beta1 + beta2 + gamma2 + delta1 + delta2)
+    coeffs = bytearray()
+    n_coef = 0
+    for mtx, key in ((0, "A"), (1, "B")):
+        for row, wire, k in r[key]:
+            coeffs += struct.pack("<III", mtx, row, wire) + (k * _R2 % FR).to_bytes(32, "little")
+            n_coef += 1
+    for s in range(l + 1):
+        coeffs += struct.pack("<III", 0, nc + s, s) + (_R2 % FR).to_bytes(32, "little")
+        n_coef += 1
+    # snarkjs writes A and B interleaved in constraint order; the prover does not depend on the order
+    sections = [(1, struct.pack("<I", 1)), (2, hdr), (3, ic), (4, struct.pack("<I", n_coef) + bytes(coeffs)),
+                (5, pa), (6, pb1), (7, pb2), (8, pc), (9, ph), (10, bytes(64) + struct.pack("<I", 0))]
+    return write_container(b"zkey", 1, sections)
