@@ -112,8 +112,14 @@ uint64_t zkfl_launch_count(void);
  * table "stage ms launches\n..." into buf. */
 int zkfl_prof_enable(zkfl_ctx* ctx, int on);
 int zkfl_prof_read(zkfl_ctx* ctx, char* buf, size_t cap);
-/* integer-pipe microbenchmark: n threads x iters x 2 dependent Montgomery products; returns ms */
+/* device timer on the context's stream: begin() synchronises and records, end() records, waits, returns ms */
+int zkfl_timer_begin(zkfl_ctx* ctx);
+int zkfl_timer_end(zkfl_ctx* ctx, float* ms_out);
+/* integer-pipe microbenchmarks (roofline denominators), each returns the kernel's ms:
+ *   modmul: n threads x iters x 2 dependent Montgomery products (136 MAC each)
+ *   imad:   n threads x iters x 8 independent 32-bit multiply-adds */
 int zkfl_bench_modmul(zkfl_ctx* ctx, size_t n_threads, uint32_t iters, float* ms_out);
+int zkfl_bench_imad(zkfl_ctx* ctx, size_t n_threads, uint32_t iters, float* ms_out);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,120 @@
+"""Parity cases shared by the CPU suite (host emulation of the kernels) and the GPU suite (real library).
+Every case drives the C ABI through zkfl_b200.api.Prover and compares with the oracle bit for bit."""
+from __future__ import annotations
+
+import random
+
+import bn254_ref as bn
+import groth16_ref as g16
+import oracle_lib as ol
+import witness_ref as wr
+from zkfl_b200 import inputs as I
+from zkfl_b200.circuits import CircuitBuilder, build_circuit
+from zkfl_b200.circuits import templates as T
+from zkfl_b200.formats import export_verification_key
+
+
+def tiny_circuit():
+    c = CircuitBuilder("tiny")
+    out = c.input("out", public=True)
+    bound = c.input("bound", public=True)
+    x = c.input("x")
+    y = c.input("y")
+    z = c.mul(x, y)
+    c.assert_eq(out, c.mul(z, z, add=x))
+    c.assert_eq(T.less_than(c, 8, x, bound), 1)
+    c.poseidon([x, y])
+    return c.compile()
+
+
+def tiny_inputs():
+    return [{"out": str((3 * 5) ** 2 + 3), "bound": "17", "x": "3", "y": "5"},
+            {"out": str((4 * 9) ** 2 + 4), "bound": "200", "x": "4", "y": "9"},
+            {"out": "6", "bound": "3", "x": "2", "y": "-1"}]
+
+
+def case_generator_mul(P, n1=24, n2=8, seed=1):
+    rnd = random.Random(seed)
+    ks = [rnd.randrange(bn.R) for _ in range(n1)] + [0, 1, bn.R - 1]
+    assert P.g1_mul_generator(ks) == ol.g1_mul_gen(ol.fes(ks))
+    ks2 = ks[:n2] + [0, 1, bn.R - 1]
+    assert P.g2_mul_generator(ks2) == ol.g2_mul_gen(ol.fes(ks2))
+
+
+def edge_scalars(rnd, n):
+    sc = [rnd.randrange(bn.R) for _ in range(n)]
+    special = [0, 1, 2, bn.R - 1, bn.R - 2, 1 << 253, (1 << 253) - 1, 0xFFFF, 0x10000, 0x8000, 0x7FFF]
+    for i, v in enumerate(special[:n]):
+        sc[i] = v
+    return sc
+
+
+def case_g1_msm(P, n, seed=2, bases=None):
+    rnd = random.Random(seed)
+    if bases is None:
+        bases = ol.g1_mul_gen(ol.fes([rnd.randrange(bn.R) for _ in range(n)]))
+    sc = ol.fes(edge_scalars(rnd, n))
+    assert P.g1_msm(bases, sc) == ol.g1_msm(bases, sc)
+
+
+def case_g1_msm_degenerate(P):
+    """zero scalars, repeated points (doubling inside a bucket), P and -P in one bucket, infinity bases."""
+    rnd = random.Random(5)
+    one = ol.g1_mul_gen(ol.fes([7]))
+    neg = ol.g1_mul_gen(ol.fes([bn.R - 7]))
+    bases = one * 6 + neg * 2 + bytes(64) * 2
+    for sc in ([0] * 10, [5] * 10, [5, 5, 5, 5, 5, 5, 5, 5, 9, 9], [1, 2, 3, 4, 5, 6, 7, 8, 9, 10],
+               [rnd.randrange(bn.R) for _ in range(10)]):
+        assert P.g1_msm(bases, ol.fes(sc)) == ol.g1_msm(bases, ol.fes(sc)), sc
+
+
+def case_g2_msm(P, n, seed=3):
+    rnd = random.Random(seed)
+    bases = ol.g2_mul_gen(ol.fes([rnd.randrange(bn.R) for _ in range(n)]))
+    sc = ol.fes(edge_scalars(rnd, n))
+    assert P.g2_msm(bases, sc) == ol.g2_msm(bases, sc)
+
+
+def case_linearity(P, n=64, seed=4):
+    """size-independent property: MSM(a) + MSM(b) == MSM(a + b) (checked through the oracle's group law)."""
+    rnd = random.Random(seed)
+    bases = ol.g1_mul_gen(ol.fes([rnd.randrange(bn.R) for _ in range(n)]))
+    a = [rnd.randrange(bn.R) for _ in range(n)]
+    b = [rnd.randrange(bn.R) for _ in range(n)]
+    pa, pb = P.g1_msm(bases, ol.fes(a)), P.g1_msm(bases, ol.fes(b))
+    pab = P.g1_msm(bases, ol.fes([(x + y) % bn.R for x, y in zip(a, b)]))
+
+    def pt(bts):
+        return None if bts == bytes(64) else (bn.Fq1(int.from_bytes(bts[:32], "little")), bn.Fq1(int.from_bytes(bts[32:], "little")))
+    assert bn.ec_add(pt(pa), pt(pb)) == pt(pab)
+
+
+def case_witness(P, cc, ins, expect_assert_on=None):
+    circ = P.load_circuit(cc)
+    ws = P.calculate_witness(circ, ins)
+    ref = ol.witness_batch(cc.program_bytes(), circ.pack_inputs(ins), cc.n_inputs, cc.n_wires)
+    assert b"".join(ws) == ref
+    circ.close()
+    return ws
+
+
+def case_prove(P, cc, ins, rs, seed=b"zkfl-test", python_verify=1):
+    """setup on the device, witness + prove through the C ABI, compare with the C++ oracle, verify with the
+    oracle's pairing. Returns (zkey bytes, proofs, publics)."""
+    circ = P.load_circuit(cc)
+    zk = P.new_zkey(cc.r1cs_bytes(), seed)
+    Z = P.load_zkey(zk)
+    ws = P.calculate_witness(circ, ins)
+    proofs, pubs = P.prove(Z, ws, rs)
+    for b in range(len(ins)):
+        ref_p, ref_pub = ol.groth16_prove(zk, ws[b], *rs[b])
+        assert proofs[b] == ref_p, f"proof {b} differs"
+        assert pubs[b] == ref_pub
+    p2, pub2 = P.full_prove(circ, Z, ins, rs)
+    assert p2 == proofs and pub2 == pubs
+    vk = g16.vkey_from_json(export_verification_key(zk))
+    for b in range(min(python_verify, len(ins))):
+        assert g16.verify(vk, ol.ints(pubs[b]), g16.proof_from_bytes(proofs[b]))
+    Z.close()
+    circ.close()
+    return zk, proofs, pubs

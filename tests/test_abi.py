@@ -1,0 +1,54 @@
+"""The C-ABI library loads and exports every symbol include/zkfl.h declares (no compute calls)."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "zkfl.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(zkfl_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def test_header_and_binding_agree():
+    import zkfl_b200  # noqa: F401
+    from zkfl_b200 import _lib
+    assert declared_symbols() == sorted(_lib.SYMBOLS)
+
+
+def test_library_exports_every_declared_symbol():
+    import __graft_entry__ as ge
+    ge.build_cuda()   # no-op when libzkfl.so is newer than its sources
+    out = subprocess.check_output(["nm", "-D", "--defined-only", ge.LIB], text=True)
+    exported = {line.split()[-1] for line in out.splitlines() if line.strip()}
+    missing = [s for s in declared_symbols() if s not in exported]
+    assert not missing, missing
+    lib = ctypes.CDLL(ge.LIB)           # loads without a GPU (cudart is linked statically)
+    lib.zkfl_version.restype = ctypes.c_char_p
+    assert b"sm_100a" in lib.zkfl_version()
+
+
+def test_product_fails_loudly_without_a_device():
+    """no CPU fallback: on a box without a GPU the product context cannot be created."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import zkfl_b200  # noqa: F401
+    from zkfl_b200 import _lib
+    from zkfl_b200.api import Prover
+    with pytest.raises(_lib.ZkflError):
+        Prover(0)
+
+
+def test_product_does_not_import_the_oracle():
+    pkg = os.path.join(ROOT, "verifiable-federated-training-with-zero-knowledge-proofs-zk-fl-_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle_lib" not in src and "bn254_ref" not in src and "groth16_ref" not in src, f

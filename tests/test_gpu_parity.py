@@ -1,0 +1,109 @@
+"""GPU parity tests: the real sm_100a library through the C ABI versus the oracle, bit for bit."""
+import random
+
+import pytest
+
+import bn254_ref as bn
+import oracle_lib as ol
+import parity_cases as pc
+from zkfl_b200 import _lib
+from zkfl_b200 import inputs as I
+from zkfl_b200.circuits import build_circuit
+
+pytestmark = pytest.mark.gpu
+
+
+def test_library_is_the_cuda_build(gpu_prover):
+    assert b"sm_100a" in gpu_prover.lib.zkfl_version()
+    before = gpu_prover.launch_count()
+    gpu_prover.g1_mul_generator([5])
+    assert gpu_prover.launch_count() > before
+
+
+def test_generator_mul(gpu_prover):
+    pc.case_generator_mul(gpu_prover, n1=2000, n2=300)
+
+
+def test_g1_msm_sizes_and_edges(gpu_prover):
+    for n in (1, 2, 33, 1000, 1 << 14):
+        pc.case_g1_msm(gpu_prover, n)
+    pc.case_g1_msm_degenerate(gpu_prover)
+    pc.case_linearity(gpu_prover, n=4096)
+
+
+def test_g1_msm_2pow20_against_oracle(gpu_prover):
+    """BASELINE.json's MSM size. Bases k_i*G come from the (separately checked) device generator kernel."""
+    n = 1 << 20
+    rnd = random.Random(20)
+    bases = gpu_prover.g1_mul_generator(b"".join(rnd.randrange(bn.R).to_bytes(32, "little") for _ in range(n)))
+    spot = [0, 1, n // 2, n - 1]
+    ks = random.Random(20)
+    allk = [ks.randrange(bn.R) for _ in range(n)]
+    for i in spot:
+        assert bases[64 * i:64 * i + 64] == ol.g1_mul_gen(ol.fe(allk[i]))
+    sc = b"".join(rnd.randrange(bn.R).to_bytes(32, "little") for _ in range(n))
+    assert gpu_prover.g1_msm(bases, sc) == ol.g1_msm(bases, sc)
+
+
+def test_g2_msm(gpu_prover):
+    for n in (1, 40, 4096):
+        pc.case_g2_msm(gpu_prover, n)
+
+
+def test_tiny_circuit(gpu_prover):
+    cc = pc.tiny_circuit()
+    pc.case_witness(gpu_prover, cc, pc.tiny_inputs())
+    pc.case_prove(gpu_prover, cc, pc.tiny_inputs(), [(11, 22), (33, 44), (0, 0)])
+    circ = gpu_prover.load_circuit(cc)
+    with pytest.raises(_lib.AssertFailed):
+        gpu_prover.calculate_witness(circ, [{"out": "5", "bound": "17", "x": "3", "y": "5"}])
+    circ.close()
+
+
+def test_witness_all_circuits(gpu_prover):
+    clients = I.simulation_clients(3)
+    tr = [c.training_input([0] * 4) for c in clients]
+    cases = {
+        "balance_unified": [c.balance_input() for c in clients] + [I.balance_integration_input()],
+        "sgd_verified": tr + I.sgd_verified_batch(5, nonzero_weights=True),
+        "secure_masked_update": [c.secagg_input([j for j in (1, 2, 3) if j != c.id]) for c in clients],
+        "secure_agg_client": [I.secure_agg_client_input()],
+        "sgd_step_quick": [{k: v for k, v in t.items() if k not in ("weights", "expectedSummedGrad", "remainder", "root_W")}
+                           for t in tr],
+    }
+    for name, ins in cases.items():
+        pc.case_witness(gpu_prover, build_circuit(name), ins)
+
+
+def test_prove_sgd_verified_batch(gpu_prover):
+    """the metric circuit: 8 clients in one batch, fixed (r, s), bit-exact proofs, pairing-verified."""
+    ins = I.sgd_verified_batch(6) + I.sgd_verified_batch(2, nonzero_weights=True)
+    rnd = random.Random(9)
+    rs = [(1, 2)] + [(rnd.randrange(bn.R), rnd.randrange(bn.R)) for _ in range(7)]
+    pc.case_prove(gpu_prover, build_circuit("sgd_verified"), ins, rs, python_verify=2)
+
+
+def test_prove_other_circuits(gpu_prover):
+    clients = I.simulation_clients(3)
+    for c in clients:
+        c.training_input([0] * 4)
+    pc.case_prove(gpu_prover, build_circuit("balance_unified"), [c.balance_input() for c in clients[:2]], [(7, 8), (9, 10)])
+    pc.case_prove(gpu_prover, build_circuit("secure_masked_update"),
+                  [c.secagg_input([j for j in (1, 2, 3) if j != c.id]) for c in clients], [(1, 1), (2, 3), (5, 8)])
+    pc.case_prove(gpu_prover, build_circuit("secure_agg_client"), [I.secure_agg_client_input()], [(4, 4)])
+
+
+def test_random_blinding_still_verifies(gpu_prover):
+    """rs = NULL -> r, s from the OS like snarkjs; proofs differ per call but verify."""
+    import groth16_ref as g16
+    from zkfl_b200.formats import export_verification_key
+    cc = pc.tiny_circuit()
+    circ = gpu_prover.load_circuit(cc)
+    zk = gpu_prover.new_zkey(cc.r1cs_bytes(), b"rnd")
+    Z = gpu_prover.load_zkey(zk)
+    p1, pub1 = gpu_prover.full_prove(circ, Z, pc.tiny_inputs()[:1])
+    p2, _ = gpu_prover.full_prove(circ, Z, pc.tiny_inputs()[:1])
+    assert p1 != p2
+    vk = g16.vkey_from_json(export_verification_key(zk))
+    assert g16.verify(vk, ol.ints(pub1[0]), g16.proof_from_bytes(p1[0]))
+    assert g16.verify(vk, ol.ints(pub1[0]), g16.proof_from_bytes(p2[0]))

@@ -18,10 +18,11 @@ SYMBOLS = [
     "zkfl_groth16_prove_batch", "zkfl_groth16_full_prove_batch", "zkfl_full_prove_stage",
     "zkfl_full_prove_run", "zkfl_full_prove_fetch", "zkfl_g1_msm", "zkfl_g2_msm", "zkfl_msm_bases_load",
     "zkfl_msm_bases_free", "zkfl_msm_run", "zkfl_g1_mul_generator", "zkfl_g2_mul_generator",
-    "zkfl_launch_count", "zkfl_prof_enable", "zkfl_prof_read", "zkfl_bench_modmul",
+    "zkfl_launch_count", "zkfl_prof_enable", "zkfl_prof_read", "zkfl_bench_modmul", "zkfl_bench_imad",
+    "zkfl_timer_begin", "zkfl_timer_end",
 ]
 
-_lib = None
+_libs = {}
 
 
 class ZkflError(RuntimeError):
@@ -38,11 +39,10 @@ def library_path() -> str:
     return os.environ.get("ZKFL_LIBRARY_PATH") or DEFAULT_PATH
 
 
-def load():
-    global _lib
-    if _lib is not None:
-        return _lib
-    path = library_path()
+def load(path: str | None = None):
+    path = path or library_path()
+    if path in _libs:
+        return _libs[path]
     if not os.path.exists(path):
         raise ImportError(f"{path} not found: build the CUDA library first (python -c 'import __graft_entry__ as g; g.build()'); "
                           "zkfl_b200 has no CPU fallback")
@@ -71,18 +71,20 @@ def load():
         "zkfl_launch_count": (u64, []),
         "zkfl_prof_enable": (i, [vp, i]), "zkfl_prof_read": (i, [vp, vp, sz]),
         "zkfl_bench_modmul": (i, [vp, sz, ctypes.c_uint32, ctypes.POINTER(ctypes.c_float)]),
+        "zkfl_bench_imad": (i, [vp, sz, ctypes.c_uint32, ctypes.POINTER(ctypes.c_float)]),
+        "zkfl_timer_begin": (i, [vp]), "zkfl_timer_end": (i, [vp, ctypes.POINTER(ctypes.c_float)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    _lib = lib
+    _libs[path] = lib
     return lib
 
 
-def check(rc: int):
+def check(rc: int, lib=None):
     if rc != 0:
-        msg = load().zkfl_last_error().decode(errors="replace")
+        msg = (lib or load()).zkfl_last_error().decode(errors="replace")
         raise (AssertFailed if rc == -5 else ZkflError)(rc, msg)
 
 

@@ -26,13 +26,13 @@ class Circuit:
         lib = prover.lib
         self.handle = ctypes.c_void_p()
         self._zkwp = zkwp
-        _lib.check(lib.zkfl_circuit_load(prover.ctx, _lib.as_ptr(zkwp), len(zkwp), ctypes.byref(self.handle)))
+        prover._check(lib.zkfl_circuit_load(prover.ctx, _lib.as_ptr(zkwp), len(zkwp), ctypes.byref(self.handle)))
         info = (ctypes.c_uint32 * 4)()
-        _lib.check(lib.zkfl_circuit_info(self.handle, info))
+        prover._check(lib.zkfl_circuit_info(self.handle, info))
         self.n_wires, self.n_public, self.n_inputs, self.n_ops = info[0], info[1], info[2], info[3]
         self.r1cs_handle = ctypes.c_void_p()
         if r1cs is not None:
-            _lib.check(lib.zkfl_r1cs_load(prover.ctx, _lib.as_ptr(r1cs), len(r1cs), ctypes.byref(self.r1cs_handle)))
+            prover._check(lib.zkfl_r1cs_load(prover.ctx, _lib.as_ptr(r1cs), len(r1cs), ctypes.byref(self.r1cs_handle)))
         self.compiled = compiled
         if compiled is not None:
             self.meta = compiled.input_map()
@@ -80,9 +80,9 @@ class Zkey:
     def __init__(self, prover: "Prover", data: bytes):
         self.prover = prover
         self.handle = ctypes.c_void_p()
-        _lib.check(prover.lib.zkfl_zkey_load(prover.ctx, _lib.as_ptr(data), len(data), ctypes.byref(self.handle)))
+        prover._check(prover.lib.zkfl_zkey_load(prover.ctx, _lib.as_ptr(data), len(data), ctypes.byref(self.handle)))
         info = (ctypes.c_uint32 * 3)()
-        _lib.check(prover.lib.zkfl_zkey_info(self.handle, info))
+        prover._check(prover.lib.zkfl_zkey_info(self.handle, info))
         self.n_vars, self.n_public, self.domain = info[0], info[1], info[2]
 
     def close(self):
@@ -92,11 +92,14 @@ class Zkey:
 
 
 class Prover:
-    def __init__(self, device: int = 0):
-        self.lib = _lib.load()
+    def __init__(self, device: int = 0, lib_path: str | None = None):
+        self.lib = _lib.load(lib_path)
         self.ctx = ctypes.c_void_p()
-        _lib.check(self.lib.zkfl_ctx_create(device, ctypes.byref(self.ctx)))
+        self._check(self.lib.zkfl_ctx_create(device, ctypes.byref(self.ctx)))
         self.device = device
+
+    def _check(self, rc: int):
+        _lib.check(rc, self.lib)
 
     def close(self):
         if self.ctx:
@@ -128,7 +131,7 @@ class Prover:
         out = ctypes.create_string_buffer(32 * circuit.n_wires * B)
         bad = (ctypes.c_uint32 * B)()
         r1 = circuit.r1cs_handle if (check and circuit.r1cs_handle) else None
-        _lib.check(self.lib.zkfl_wtns_calculate_batch(self.ctx, circuit.handle, r1, _lib.as_ptr(packed), B, out, bad))
+        self._check(self.lib.zkfl_wtns_calculate_batch(self.ctx, circuit.handle, r1, _lib.as_ptr(packed), B, out, bad))
         sz = 32 * circuit.n_wires
         return [out.raw[b * sz:(b + 1) * sz] for b in range(B)]
 
@@ -151,7 +154,7 @@ class Prover:
         B = len(wtns)
         proofs = ctypes.create_string_buffer(256 * B)
         pubs = ctypes.create_string_buffer(max(32 * zkey.n_public * B, 1))
-        _lib.check(self.lib.zkfl_groth16_prove_batch(self.ctx, zkey.handle, _lib.as_ptr(b"".join(wtns)),
+        self._check(self.lib.zkfl_groth16_prove_batch(self.ctx, zkey.handle, _lib.as_ptr(b"".join(wtns)),
                                                      _lib.as_ptr(self._pack_rs(rs, B)), B, proofs, pubs))
         psz = 32 * zkey.n_public
         return ([proofs.raw[256 * b:256 * (b + 1)] for b in range(B)], [pubs.raw[psz * b:psz * (b + 1)] for b in range(B)])
@@ -161,7 +164,7 @@ class Prover:
         B = len(packed) // (32 * circuit.n_inputs)
         proofs = ctypes.create_string_buffer(256 * B)
         pubs = ctypes.create_string_buffer(max(32 * zkey.n_public * B, 1))
-        _lib.check(self.lib.zkfl_groth16_full_prove_batch(self.ctx, circuit.handle, zkey.handle, _lib.as_ptr(packed),
+        self._check(self.lib.zkfl_groth16_full_prove_batch(self.ctx, circuit.handle, zkey.handle, _lib.as_ptr(packed),
                                                           _lib.as_ptr(self._pack_rs(rs, B)), B, proofs, pubs))
         psz = 32 * zkey.n_public
         return ([proofs.raw[256 * b:256 * (b + 1)] for b in range(B)], [pubs.raw[psz * b:psz * (b + 1)] for b in range(B)])
@@ -169,40 +172,78 @@ class Prover:
     # ---------------------------------------------------------------- MSM / setup support
     def g1_msm(self, bases: bytes, scalars: bytes) -> bytes:
         out = ctypes.create_string_buffer(64)
-        _lib.check(self.lib.zkfl_g1_msm(self.ctx, _lib.as_ptr(bases), _lib.as_ptr(scalars), len(scalars) // 32, out))
+        self._check(self.lib.zkfl_g1_msm(self.ctx, _lib.as_ptr(bases), _lib.as_ptr(scalars), len(scalars) // 32, out))
         return out.raw
 
     def g2_msm(self, bases: bytes, scalars: bytes) -> bytes:
         out = ctypes.create_string_buffer(128)
-        _lib.check(self.lib.zkfl_g2_msm(self.ctx, _lib.as_ptr(bases), _lib.as_ptr(scalars), len(scalars) // 32, out))
+        self._check(self.lib.zkfl_g2_msm(self.ctx, _lib.as_ptr(bases), _lib.as_ptr(scalars), len(scalars) // 32, out))
         return out.raw
 
     def g1_mul_generator(self, scalars) -> bytes:
         sc = scalars if isinstance(scalars, (bytes, bytearray)) else _fe_bytes(scalars)
         n = len(sc) // 32
         out = ctypes.create_string_buffer(64 * n)
-        _lib.check(self.lib.zkfl_g1_mul_generator(self.ctx, _lib.as_ptr(sc), n, out))
+        self._check(self.lib.zkfl_g1_mul_generator(self.ctx, _lib.as_ptr(sc), n, out))
         return out.raw
 
     def g2_mul_generator(self, scalars) -> bytes:
         sc = scalars if isinstance(scalars, (bytes, bytearray)) else _fe_bytes(scalars)
         n = len(sc) // 32
         out = ctypes.create_string_buffer(128 * n)
-        _lib.check(self.lib.zkfl_g2_mul_generator(self.ctx, _lib.as_ptr(sc), n, out))
+        self._check(self.lib.zkfl_g2_mul_generator(self.ctx, _lib.as_ptr(sc), n, out))
         return out.raw
 
     # ---------------------------------------------------------------- measurement
     def prof_enable(self, on: bool = True):
-        _lib.check(self.lib.zkfl_prof_enable(self.ctx, 1 if on else 0))
+        self._check(self.lib.zkfl_prof_enable(self.ctx, 1 if on else 0))
 
     def prof_read(self) -> dict:
         buf = ctypes.create_string_buffer(1 << 16)
-        _lib.check(self.lib.zkfl_prof_read(self.ctx, buf, len(buf)))
+        self._check(self.lib.zkfl_prof_read(self.ctx, buf, len(buf)))
         out = {}
         for line in buf.value.decode().splitlines():
             name, ms, launches, calls = line.split()
             out[name] = {"ms": float(ms), "launches": int(launches), "calls": int(calls)}
         return out
+
+    def timer_begin(self):
+        self._check(self.lib.zkfl_timer_begin(self.ctx))
+
+    def timer_end(self) -> float:
+        ms = ctypes.c_float()
+        self._check(self.lib.zkfl_timer_end(self.ctx, ctypes.byref(ms)))
+        return ms.value
+
+    def bench_imad(self, n_threads: int, iters: int) -> float:
+        """-> measured 32-bit multiply-adds per second"""
+        ms = ctypes.c_float()
+        self._check(self.lib.zkfl_bench_imad(self.ctx, n_threads, iters, ctypes.byref(ms)))
+        return n_threads * iters * 8 / (ms.value * 1e-3)
+
+    def bench_modmul(self, n_threads: int, iters: int) -> float:
+        """-> measured Montgomery products per second"""
+        ms = ctypes.c_float()
+        self._check(self.lib.zkfl_bench_modmul(self.ctx, n_threads, iters, ctypes.byref(ms)))
+        return n_threads * iters * 2 / (ms.value * 1e-3)
+
+    # resident (steady-state) full-prove: inputs staged once, proofs left in HBM
+    def stage(self, circuit: Circuit, zkey: Zkey, packed_inputs, rs_packed, B: int):
+        self._check(self.lib.zkfl_full_prove_stage(self.ctx, circuit.handle, zkey.handle, _lib.as_ptr(packed_inputs),
+                                                   _lib.as_ptr(rs_packed), B))
+
+    def run_staged(self, circuit: Circuit, zkey: Zkey, B: int):
+        self._check(self.lib.zkfl_full_prove_run(self.ctx, circuit.handle, zkey.handle, B))
+
+    def fetch(self, B: int, out=None):
+        buf = out if out is not None else ctypes.create_string_buffer(256 * B)
+        self._check(self.lib.zkfl_full_prove_fetch(self.ctx, B, _lib.as_ptr(buf) if out is not None else buf))
+        return buf
+
+    def full_prove_raw(self, circuit: Circuit, zkey: Zkey, inputs_ptr, rs_ptr, B: int, proofs_ptr, pubs_ptr):
+        """pointer-level call (pinned host buffers) used by the end-to-end benchmark"""
+        self._check(self.lib.zkfl_groth16_full_prove_batch(self.ctx, circuit.handle, zkey.handle, _lib.as_ptr(inputs_ptr),
+                                                          _lib.as_ptr(rs_ptr), B, _lib.as_ptr(proofs_ptr), _lib.as_ptr(pubs_ptr)))
 
     def launch_count(self) -> int:
         return int(self.lib.zkfl_launch_count())

@@ -94,7 +94,7 @@ struct alignas(16) Fp {
   ZK_HD Fp to_mont() const { return *this * r2(); }
   ZK_HD Fp from_mont() const { Fp o = zero(); o.v[0] = 1; return *this * o; }
 
-  ZK_HD Fp inv() const {  // Fermat, exponent p - 2 (setup / affine conversion only)
+  ZK_HD_NOINLINE Fp inv() const {  // Fermat, exponent p - 2 (setup / affine conversion only)
     Fp r = one();
     ZK_NOUNROLL for (int i = 253; i >= 0; i--) {
       r = r.sqr();
@@ -143,7 +143,7 @@ template <class F> struct alignas(16) Xyzz {
   }
 };
 
-template <class F> ZK_HD Xyzz<F> xyzz_dbl(const Xyzz<F>& p) {  // dbl-2008-s-1, a = 0
+template <class F> ZK_HD_NOINLINE Xyzz<F> xyzz_dbl(const Xyzz<F>& p) {  // dbl-2008-s-1, a = 0
   if (p.is_inf()) return p;
   F U = p.Y.dbl(), V = U.sqr(), W = U * V, S = p.X * V;
   F M = p.X.sqr(); M = M.dbl() + M;
@@ -154,7 +154,7 @@ template <class F> ZK_HD Xyzz<F> xyzz_dbl(const Xyzz<F>& p) {  // dbl-2008-s-1, 
   r.ZZZ = W * p.ZZZ;
   return r;
 }
-template <class F> ZK_HD Xyzz<F> xyzz_dbl_affine(const Affine<F>& p) {  // mdbl-2008-s-1
+template <class F> ZK_HD_NOINLINE Xyzz<F> xyzz_dbl_affine(const Affine<F>& p) {  // mdbl-2008-s-1
   F U = p.y.dbl(), V = U.sqr(), W = U * V, S = p.x * V;
   F M = p.x.sqr(); M = M.dbl() + M;
   Xyzz<F> r;
@@ -183,7 +183,7 @@ template <class F> ZK_HD void xyzz_madd(Xyzz<F>& acc, const Affine<F>& q0, bool 
   acc.ZZ = acc.ZZ * PP;
   acc.ZZZ = acc.ZZZ * PPP;
 }
-template <class F> ZK_HD void xyzz_add(Xyzz<F>& acc, const Xyzz<F>& q) {  // add-2008-s
+template <class F> ZK_HD_NOINLINE void xyzz_add(Xyzz<F>& acc, const Xyzz<F>& q) {  // add-2008-s
   if (q.is_inf()) return;
   if (acc.is_inf()) { acc = q; return; }
   F U1 = acc.X * q.ZZ, U2 = q.X * acc.ZZ, S1 = acc.Y * q.ZZZ, S2 = q.Y * acc.ZZZ;
@@ -202,7 +202,7 @@ template <class F> ZK_HD void xyzz_add(Xyzz<F>& acc, const Xyzz<F>& q) {  // add
 template <class F> ZK_HD Xyzz<F> xyzz_neg(const Xyzz<F>& p) { Xyzz<F> r = p; r.Y = p.Y.neg(); return r; }
 
 // Montgomery-form affine; infinity -> (0,0)
-template <class F> ZK_HD Affine<F> xyzz_to_affine(const Xyzz<F>& p) {
+template <class F> ZK_HD_NOINLINE Affine<F> xyzz_to_affine(const Xyzz<F>& p) {
   Affine<F> r;
   if (p.is_inf()) { r.x = F::zero(); r.y = F::zero(); return r; }
   F i3 = p.ZZZ.inv();
@@ -212,7 +212,7 @@ template <class F> ZK_HD Affine<F> xyzz_to_affine(const Xyzz<F>& p) {
   return r;
 }
 // k * p, k = 8 canonical little-endian words (< 2^254)
-template <class F> ZK_HD Xyzz<F> xyzz_scalar_mul(const Xyzz<F>& p, const uint32_t* k) {
+template <class F> ZK_HD_NOINLINE Xyzz<F> xyzz_scalar_mul(const Xyzz<F>& p, const uint32_t* k) {
   Xyzz<F> r = Xyzz<F>::infinity();
   ZK_NOUNROLL for (int i = 253; i >= 0; i--) {
     r = xyzz_dbl(r);

@@ -441,4 +441,17 @@ ZK_GLOBAL void k_bench_modmul(Fq* __restrict__ data, size_t n, uint32_t iters) {
   data[i] = x + y;
 }
 
+// raw IMAD-chain microbenchmark: 8 independent 32-bit multiply-add chains per thread, iters steps each
+ZK_GLOBAL void k_bench_imad(uint32_t* __restrict__ data, size_t n, uint32_t iters) {
+  size_t i = ZK_TID;
+  if (i >= n) return;
+  uint32_t a0 = data[i], a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const uint32_t m = a0 | 1u, c = a0 ^ 0x9e3779b9u;
+  ZK_NOUNROLL for (uint32_t k = 0; k < iters; k++) {
+    a0 = a0 * m + c; a1 = a1 * m + c; a2 = a2 * m + c; a3 = a3 * m + c;
+    a4 = a4 * m + c; a5 = a5 * m + c; a6 = a6 * m + c; a7 = a7 * m + c;
+  }
+  data[i] = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7;
+}
+
 }  // namespace zk

@@ -72,6 +72,7 @@ struct zkfl_ctx {
   DevBuf counts, offsets, cursors, chunk_sums, sorted, buckets, Rs, Ts, win;
   DevBuf res_g1, res_g2, t_g1, t_g2, pis, var, proofs, pubs, bad;
   DevBuf msm_sc, msm_out;
+  cudaEvent_t t0 = nullptr, t1 = nullptr;
 };
 
 struct Stage {
@@ -230,15 +231,19 @@ static int msm_sort(zkfl_ctx* c, const Fr* scalars, const MsmShape& s) {
 }
 // buckets -> per-proof sums out[B]; uses the lists left by msm_sort
 template <class F>
-static int msm_run(zkfl_ctx* c, const Affine<F>* bases, const MsmShape& s, Xyzz<F>* out) {
+static int msm_run(zkfl_ctx* c, const Affine<F>* bases, const MsmShape& s, Xyzz<F>* out, const char* acc_tag, const char* red_tag) {
   size_t rows = (size_t)s.B * s.W;
   uint32_t L = reduce_chunk(s), nchunk = s.nb / L;
   TRY(c->buckets.reserve(rows * s.nb * sizeof(Xyzz<F>)));
   TRY(c->Rs.reserve(rows * nchunk * sizeof(Xyzz<F>)));
   TRY(c->Ts.reserve(rows * nchunk * sizeof(Xyzz<F>)));
   TRY(c->win.reserve(rows * sizeof(Xyzz<F>)));
-  ZK_LAUNCH(k_msm_accumulate<F>, rows * s.nb, 128, c->stream, bases, c->sorted.as<uint32_t>(), c->offsets.as<uint32_t>(),
-            c->counts.as<uint32_t>(), s, c->buckets.as<Xyzz<F>>());
+  {
+    Stage st(c, acc_tag);
+    ZK_LAUNCH(k_msm_accumulate<F>, rows * s.nb, 128, c->stream, bases, c->sorted.as<uint32_t>(), c->offsets.as<uint32_t>(),
+              c->counts.as<uint32_t>(), s, c->buckets.as<Xyzz<F>>());
+  }
+  Stage st2(c, red_tag);
   ZK_LAUNCH(k_msm_reduce_chunks<F>, rows * nchunk, 128, c->stream, c->buckets.as<Xyzz<F>>(), s, L, c->Rs.as<Xyzz<F>>(),
             c->Ts.as<Xyzz<F>>());
   ZK_LAUNCH(k_msm_reduce_rows<F>, rows, 64, c->stream, c->Rs.as<Xyzz<F>>(), c->Ts.as<Xyzz<F>>(), s, L, c->win.as<Xyzz<F>>());
@@ -272,13 +277,13 @@ static int prove_from_device_witness(zkfl_ctx* c, const zkfl_zkey* z, const Fr* 
   G1Xyzz* r1 = c->res_g1.as<G1Xyzz>();
   MsmShape sw = msm_shape(m, B);
   { Stage st(c, "msm_sort_w"); TRY(msm_sort(c, w, sw)); }
-  { Stage st(c, "msm_A"); TRY(msm_run<Fq>(c, z->pA.as<G1Affine>(), sw, r1)); }
-  { Stage st(c, "msm_B1"); TRY(msm_run<Fq>(c, z->pB1.as<G1Affine>(), sw, r1 + B)); }
-  { Stage st(c, "msm_C"); TRY(msm_run<Fq>(c, z->pC.as<G1Affine>(), sw, r1 + 2 * (size_t)B)); }
-  { Stage st(c, "msm_B2"); TRY(msm_run<Fq2>(c, z->pB2.as<G2Affine>(), sw, c->res_g2.as<G2Xyzz>())); }
+  TRY(msm_run<Fq>(c, z->pA.as<G1Affine>(), sw, r1, "msm_acc_g1", "msm_reduce_g1"));
+  TRY(msm_run<Fq>(c, z->pB1.as<G1Affine>(), sw, r1 + B, "msm_acc_g1", "msm_reduce_g1"));
+  TRY(msm_run<Fq>(c, z->pC.as<G1Affine>(), sw, r1 + 2 * (size_t)B, "msm_acc_g1", "msm_reduce_g1"));
+  TRY(msm_run<Fq2>(c, z->pB2.as<G2Affine>(), sw, c->res_g2.as<G2Xyzz>(), "msm_acc_g2", "msm_reduce_g2"));
   MsmShape sh = msm_shape(n, B);
   { Stage st(c, "msm_sort_h"); TRY(msm_sort(c, c->hsc.as<Fr>(), sh)); }
-  { Stage st(c, "msm_H"); TRY(msm_run<Fq>(c, z->pH.as<G1Affine>(), sh, r1 + 3 * (size_t)B)); }
+  TRY(msm_run<Fq>(c, z->pH.as<G1Affine>(), sh, r1 + 3 * (size_t)B, "msm_acc_g1", "msm_reduce_g1"));
   {
     Stage st(c, "finalize");
     TRY(c->t_g1.reserve(3 * (size_t)B * sizeof(G1Xyzz)));
@@ -387,6 +392,7 @@ void zkfl_ctx_free(zkfl_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   for (auto& r : c->pending) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  if (c->t0) { cudaEventDestroy(c->t0); cudaEventDestroy(c->t1); }
   cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -716,10 +722,10 @@ int zkfl_msm_run(zkfl_ctx* c, void* handle, const uint8_t* scalars, size_t n, ui
   TRY(c->msm_out.reserve(sizeof(G2Xyzz) + sizeof(G2Affine)));
   uint8_t* o = c->msm_out.as<uint8_t>();
   if (b->group == 1) {
-    { Stage st(c, "msm_g1"); TRY(msm_run<Fq>(c, b->pts.as<G1Affine>(), s, (G1Xyzz*)o)); }
+    TRY(msm_run<Fq>(c, b->pts.as<G1Affine>(), s, (G1Xyzz*)o, "msm_acc_g1", "msm_reduce_g1"));
     ZK_LAUNCH(k_to_affine_canonical<Fq>, 1, 32, c->stream, (const G1Xyzz*)o, (size_t)1, (G1Affine*)(o + sizeof(G2Xyzz)));
   } else {
-    { Stage st(c, "msm_g2"); TRY(msm_run<Fq2>(c, b->pts.as<G2Affine>(), s, (G2Xyzz*)o)); }
+    TRY(msm_run<Fq2>(c, b->pts.as<G2Affine>(), s, (G2Xyzz*)o, "msm_acc_g2", "msm_reduce_g2"));
     ZK_LAUNCH(k_to_affine_canonical<Fq2>, 1, 32, c->stream, (const G2Xyzz*)o, (size_t)1, (G2Affine*)(o + sizeof(G2Xyzz)));
   }
   if (out) {
@@ -771,6 +777,38 @@ int zkfl_g2_mul_generator(zkfl_ctx* c, const uint8_t* scalars, size_t n, uint8_t
   return gen_mul<Fq2>(c, g, scalars, n, out);
 }
 
+int zkfl_timer_begin(zkfl_ctx* c) {
+  if (!c) return fail(ZKFL_ERR_ARG, "ctx is NULL");
+  CU(cudaSetDevice(c->device));
+  if (!c->t0) { CU(cudaEventCreate(&c->t0)); CU(cudaEventCreate(&c->t1)); }
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaEventRecord(c->t0, c->stream));
+  return 0;
+}
+int zkfl_timer_end(zkfl_ctx* c, float* ms_out) {
+  if (!c || !ms_out || !c->t0) return fail(ZKFL_ERR_ARG, "timer not started");
+  CU(cudaEventRecord(c->t1, c->stream));
+  CU(cudaEventSynchronize(c->t1));
+  CU(cudaEventElapsedTime(ms_out, c->t0, c->t1));
+  return 0;
+}
+int zkfl_bench_imad(zkfl_ctx* c, size_t n_threads, uint32_t iters, float* ms_out) {
+  if (!c || !ms_out || n_threads == 0) return fail(ZKFL_ERR_ARG, "bad argument");
+  CU(cudaSetDevice(c->device));
+  DevBuf d;
+  TRY(d.reserve(n_threads * 4));
+  CU(cudaMemsetAsync(d.p, 0x5a, n_threads * 4, c->stream));
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+  ZK_LAUNCH(k_bench_imad, n_threads, 256, c->stream, d.as<uint32_t>(), n_threads, 16u);
+  CU(cudaEventRecord(e0, c->stream));
+  ZK_LAUNCH(k_bench_imad, n_threads, 256, c->stream, d.as<uint32_t>(), n_threads, iters);
+  CU(cudaEventRecord(e1, c->stream));
+  CU(cudaEventSynchronize(e1));
+  CU(cudaEventElapsedTime(ms_out, e0, e1));
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  return 0;
+}
 int zkfl_bench_modmul(zkfl_ctx* c, size_t n_threads, uint32_t iters, float* ms_out) {
   if (!c || !ms_out || n_threads == 0) return fail(ZKFL_ERR_ARG, "bad argument");
   CU(cudaSetDevice(c->device));

@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 #define ZK_HD __host__ __device__ __forceinline__
 #define ZK_D __device__ __forceinline__
+#define ZK_HD_NOINLINE __host__ __device__ __noinline__
 #define ZK_GLOBAL __global__
 #define ZK_UNROLL _Pragma("unroll")
 #define ZK_NOUNROLL _Pragma("unroll 1")
@@ -43,6 +44,7 @@ inline const char* err_str(cudaError_t e) { return cudaGetErrorString(e); }
 #include <vector>
 #define ZK_HD inline
 #define ZK_D inline
+#define ZK_HD_NOINLINE inline
 #define ZK_GLOBAL static
 #define ZK_UNROLL
 #define ZK_NOUNROLL
