@@ -75,7 +75,10 @@ struct alignas(16) Fp {
   ZK_HD Fp dbl() const { return *this + *this; }
 
   // Montgomery product a*b/R, CIOS; p < 2^254 keeps the running value in 9 words.
-  friend ZK_HD Fp operator*(const Fp& a, const Fp& b) {
+  // `mul_inline` is the body; `operator*` is a by-value LEAF CALL on the device (operands and result
+  // travel in registers, no stack frame), which keeps the many group-law call sites compact.  The hot
+  // bucket-accumulation path uses mul_inline directly so ptxas can schedule across products.
+  static ZK_HD Fp mul_inline(const Fp& a, const Fp& b) {
     uint32_t t[9];
     ZK_UNROLL for (int i = 0; i < 9; i++) t[i] = 0;
     ZK_UNROLL for (int i = 0; i < 8; i++) {
@@ -90,11 +93,13 @@ struct alignas(16) Fp {
     }
     return reduce_once(t);
   }
+  static ZK_HD_NOINLINE Fp mul_call(Fp a, Fp b) { return mul_inline(a, b); }
+  friend ZK_HD Fp operator*(const Fp& a, const Fp& b) { return mul_call(a, b); }
   ZK_HD Fp sqr() const { return *this * *this; }
   ZK_HD Fp to_mont() const { return *this * r2(); }
   ZK_HD Fp from_mont() const { Fp o = zero(); o.v[0] = 1; return *this * o; }
 
-  ZK_HD_NOINLINE Fp inv() const {  // Fermat, exponent p - 2 (setup / affine conversion only)
+  ZK_HD Fp inv() const {  // Fermat, exponent p - 2 (setup / affine conversion only)
     Fp r = one();
     ZK_NOUNROLL for (int i = 253; i >= 0; i--) {
       r = r.sqr();
@@ -124,6 +129,10 @@ struct alignas(16) Fq2 {
     Fq2 r; r.a = aa - bb; r.b = s - aa - bb; return r;
   }
   ZK_HD Fq2 sqr() const { Fq t = a * b; Fq2 r; r.a = (a + b) * (a - b); r.b = t.dbl(); return r; }
+  static ZK_HD Fq2 mul_inline(const Fq2& x, const Fq2& y) {
+    Fq aa = Fq::mul_inline(x.a, y.a), bb = Fq::mul_inline(x.b, y.b), s = Fq::mul_inline(x.a + x.b, y.a + y.b);
+    Fq2 r; r.a = aa - bb; r.b = s - aa - bb; return r;
+  }
   ZK_HD Fq2 inv() const { Fq d = (a.sqr() + b.sqr()).inv(); Fq2 r; r.a = a * d; r.b = (b * d).neg(); return r; }
   ZK_HD Fq2 from_mont() const { Fq2 r; r.a = a.from_mont(); r.b = b.from_mont(); return r; }
 };
@@ -143,7 +152,7 @@ template <class F> struct alignas(16) Xyzz {
   }
 };
 
-template <class F> ZK_HD_NOINLINE Xyzz<F> xyzz_dbl(const Xyzz<F>& p) {  // dbl-2008-s-1, a = 0
+template <class F> ZK_HD Xyzz<F> xyzz_dbl(const Xyzz<F>& p) {  // dbl-2008-s-1, a = 0
   if (p.is_inf()) return p;
   F U = p.Y.dbl(), V = U.sqr(), W = U * V, S = p.X * V;
   F M = p.X.sqr(); M = M.dbl() + M;
@@ -154,7 +163,7 @@ template <class F> ZK_HD_NOINLINE Xyzz<F> xyzz_dbl(const Xyzz<F>& p) {  // dbl-2
   r.ZZZ = W * p.ZZZ;
   return r;
 }
-template <class F> ZK_HD_NOINLINE Xyzz<F> xyzz_dbl_affine(const Affine<F>& p) {  // mdbl-2008-s-1
+template <class F> ZK_HD Xyzz<F> xyzz_dbl_affine(const Affine<F>& p) {  // mdbl-2008-s-1
   F U = p.y.dbl(), V = U.sqr(), W = U * V, S = p.x * V;
   F M = p.x.sqr(); M = M.dbl() + M;
   Xyzz<F> r;
@@ -164,26 +173,27 @@ template <class F> ZK_HD_NOINLINE Xyzz<F> xyzz_dbl_affine(const Affine<F>& p) { 
   r.ZZZ = W;
   return r;
 }
-// acc += q (affine, not infinity unless flagged); `negate` flips q first
+// acc += q (affine; infinity bases are skipped); `negate` flips q first.  Hot path of the MSM bucket
+// accumulation: products are inlined (mul_inline) so ptxas can interleave the independent IMAD chains.
 template <class F> ZK_HD void xyzz_madd(Xyzz<F>& acc, const Affine<F>& q0, bool negate) {  // madd-2008-s
   if (q0.is_inf()) return;
   Affine<F> q = q0;
   if (negate) q.y = q.y.neg();
   if (acc.is_inf()) { acc = Xyzz<F>::from_affine(q); return; }
-  F U2 = q.x * acc.ZZ, S2 = q.y * acc.ZZZ;
+  F U2 = F::mul_inline(q.x, acc.ZZ), S2 = F::mul_inline(q.y, acc.ZZZ);
   F Pp = U2 - acc.X, Rr = S2 - acc.Y;
   if (Pp.is_zero()) {
     if (Rr.is_zero()) acc = xyzz_dbl_affine(q); else acc = Xyzz<F>::infinity();
     return;
   }
-  F PP = Pp.sqr(), PPP = Pp * PP, Qq = acc.X * PP;
-  F X3 = Rr.sqr() - PPP - Qq.dbl();
-  acc.Y = Rr * (Qq - X3) - acc.Y * PPP;
+  F PP = F::mul_inline(Pp, Pp), PPP = F::mul_inline(Pp, PP), Qq = F::mul_inline(acc.X, PP);
+  F X3 = F::mul_inline(Rr, Rr) - PPP - Qq.dbl();
+  acc.Y = F::mul_inline(Rr, Qq - X3) - F::mul_inline(acc.Y, PPP);
   acc.X = X3;
-  acc.ZZ = acc.ZZ * PP;
-  acc.ZZZ = acc.ZZZ * PPP;
+  acc.ZZ = F::mul_inline(acc.ZZ, PP);
+  acc.ZZZ = F::mul_inline(acc.ZZZ, PPP);
 }
-template <class F> ZK_HD_NOINLINE void xyzz_add(Xyzz<F>& acc, const Xyzz<F>& q) {  // add-2008-s
+template <class F> ZK_HD void xyzz_add(Xyzz<F>& acc, const Xyzz<F>& q) {  // add-2008-s
   if (q.is_inf()) return;
   if (acc.is_inf()) { acc = q; return; }
   F U1 = acc.X * q.ZZ, U2 = q.X * acc.ZZ, S1 = acc.Y * q.ZZZ, S2 = q.Y * acc.ZZZ;
@@ -202,7 +212,7 @@ template <class F> ZK_HD_NOINLINE void xyzz_add(Xyzz<F>& acc, const Xyzz<F>& q) 
 template <class F> ZK_HD Xyzz<F> xyzz_neg(const Xyzz<F>& p) { Xyzz<F> r = p; r.Y = p.Y.neg(); return r; }
 
 // Montgomery-form affine; infinity -> (0,0)
-template <class F> ZK_HD_NOINLINE Affine<F> xyzz_to_affine(const Xyzz<F>& p) {
+template <class F> ZK_HD Affine<F> xyzz_to_affine(const Xyzz<F>& p) {
   Affine<F> r;
   if (p.is_inf()) { r.x = F::zero(); r.y = F::zero(); return r; }
   F i3 = p.ZZZ.inv();
@@ -212,7 +222,7 @@ template <class F> ZK_HD_NOINLINE Affine<F> xyzz_to_affine(const Xyzz<F>& p) {
   return r;
 }
 // k * p, k = 8 canonical little-endian words (< 2^254)
-template <class F> ZK_HD_NOINLINE Xyzz<F> xyzz_scalar_mul(const Xyzz<F>& p, const uint32_t* k) {
+template <class F> ZK_HD Xyzz<F> xyzz_scalar_mul(const Xyzz<F>& p, const uint32_t* k) {
   Xyzz<F> r = Xyzz<F>::infinity();
   ZK_NOUNROLL for (int i = 253; i >= 0; i--) {
     r = xyzz_dbl(r);

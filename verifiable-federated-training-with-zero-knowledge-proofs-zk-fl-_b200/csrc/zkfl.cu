@@ -23,6 +23,20 @@ static thread_local std::string g_err;
 static std::atomic<uint64_t> g_launches(0);
 namespace zkrt {
 void note_launch(const char*) { g_launches.fetch_add(1, std::memory_order_relaxed); }
+bool debug_sync() {
+  static int on = -1;
+  if (on < 0) { const char* v = getenv("ZKFL_DEBUG_SYNC"); on = (v && *v && *v != '0') ? 1 : 0; }
+  return on == 1;
+}
+void debug_check(const char* name, cudaStream_t stream) {
+#ifndef ZKFL_EMUL
+  cudaError_t e = cudaStreamSynchronize(stream);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  fprintf(stderr, "[zkfl] %-40s %s\n", name, e == cudaSuccess ? "ok" : cudaGetErrorString(e));
+#else
+  (void)name; (void)stream;
+#endif
+}
 }  // namespace zkrt
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
 
@@ -380,6 +394,13 @@ int zkfl_ctx_create(int device, zkfl_ctx** out) {
   if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) return fail(ZKFL_ERR_CUDA, "no CUDA device available (libzkfl has no CPU path)");
   if (device < 0 || device >= n) return fail(ZKFL_ERR_ARG, "device index out of range");
   CU(cudaSetDevice(device));
+#ifndef ZKFL_EMUL
+  {  // the group-law helpers are real calls (noinline): give their frames room
+    const char* v = getenv("ZKFL_STACK_BYTES");
+    size_t want = v && *v ? (size_t)strtoul(v, nullptr, 10) : 0;
+    if (want) CU(cudaDeviceSetLimit(cudaLimitStackSize, want));
+  }
+#endif
   zkfl_ctx* c = new zkfl_ctx();
   c->device = device;
   cudaError_t e = cudaStreamCreate(&c->stream);

@@ -33,6 +33,7 @@ inline const char* err_str(cudaError_t e) { return cudaGetErrorString(e); }
       unsigned _grid = (unsigned)((_tot + (block)-1) / (block));                             \
       kernel<<<_grid, (block), 0, (stream)>>>(__VA_ARGS__);                                  \
       zkrt::note_launch(#kernel);                                                            \
+      if (zkrt::debug_sync()) zkrt::debug_check(#kernel, (stream));                          \
     }                                                                                        \
   } while (0)
 
@@ -119,4 +120,6 @@ inline void emul_run(size_t total, Fn fn) {
 
 namespace zkrt {
 void note_launch(const char* name);  // defined in zkfl.cu: counts launches for gpu_launches / profiling
+bool debug_sync();                   // ZKFL_DEBUG_SYNC=1: synchronise and check after every launch
+void debug_check(const char* name, cudaStream_t stream);
 }
