@@ -40,6 +40,22 @@ struct FrP {
   static ZK_HD uint32_t inv() { return 0xefffffffu; }
 };
 
+// ------------------------------------------------------------------------------ PTX carry-chain helpers (device)
+#if defined(__CUDA_ARCH__) && !defined(ZKFL_PORTABLE_MUL)
+#define ZKFL_PTX_MUL 1
+namespace ptx {
+__device__ __forceinline__ uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("mad.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+__device__ __forceinline__ uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("madc.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+__device__ __forceinline__ uint32_t mad_hi_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("mad.hi.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+__device__ __forceinline__ uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("madc.hi.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+__device__ __forceinline__ uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("madc.hi.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+__device__ __forceinline__ uint32_t addc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("addc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ uint32_t sub_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("sub.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ uint32_t subc_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("subc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ uint32_t subc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("subc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+}  // namespace ptx
+#endif
+
 // ------------------------------------------------------------------------------ prime field
 template <class P>
 struct alignas(16) Fp {
@@ -79,6 +95,37 @@ struct alignas(16) Fp {
   // travel in registers, no stack frame), which keeps the many group-law call sites compact.  The hot
   // bucket-accumulation path uses mul_inline directly so ptxas can schedule across products.
   static ZK_HD Fp mul_inline(const Fp& a, const Fp& b) {
+#ifdef ZKFL_PTX_MUL
+    // 32-bit IMAD carry chains: per row one lo chain and one hi chain (16 IMAD + 1 ADDC), 16 rows + 8 products
+    // for the quotient words = 280 integer-pipe instructions per product, nothing on the half-rate IMAD.WIDE path.
+    uint32_t t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0, t5 = 0, t6 = 0, t7 = 0, t8;
+    ZK_UNROLL for (int i = 0; i < 8; i++) {
+      const uint32_t bi = b.v[i];
+      t0 = ptx::mad_lo_cc(a.v[0], bi, t0); t1 = ptx::madc_lo_cc(a.v[1], bi, t1); t2 = ptx::madc_lo_cc(a.v[2], bi, t2);
+      t3 = ptx::madc_lo_cc(a.v[3], bi, t3); t4 = ptx::madc_lo_cc(a.v[4], bi, t4); t5 = ptx::madc_lo_cc(a.v[5], bi, t5);
+      t6 = ptx::madc_lo_cc(a.v[6], bi, t6); t7 = ptx::madc_lo_cc(a.v[7], bi, t7); t8 = ptx::addc(0, 0);
+      t1 = ptx::mad_hi_cc(a.v[0], bi, t1); t2 = ptx::madc_hi_cc(a.v[1], bi, t2); t3 = ptx::madc_hi_cc(a.v[2], bi, t3);
+      t4 = ptx::madc_hi_cc(a.v[3], bi, t4); t5 = ptx::madc_hi_cc(a.v[4], bi, t5); t6 = ptx::madc_hi_cc(a.v[5], bi, t6);
+      t7 = ptx::madc_hi_cc(a.v[6], bi, t7); t8 = ptx::madc_hi(a.v[7], bi, t8);
+      const uint32_t m = t0 * P::inv();
+      t0 = ptx::mad_lo_cc(m, P::mod(0), t0); t1 = ptx::madc_lo_cc(m, P::mod(1), t1); t2 = ptx::madc_lo_cc(m, P::mod(2), t2);
+      t3 = ptx::madc_lo_cc(m, P::mod(3), t3); t4 = ptx::madc_lo_cc(m, P::mod(4), t4); t5 = ptx::madc_lo_cc(m, P::mod(5), t5);
+      t6 = ptx::madc_lo_cc(m, P::mod(6), t6); t7 = ptx::madc_lo_cc(m, P::mod(7), t7); t8 = ptx::addc(t8, 0);
+      // t0 is now 0: drop it (divide by 2^32) while adding the hi chain
+      t0 = ptx::mad_hi_cc(m, P::mod(0), t1); t1 = ptx::madc_hi_cc(m, P::mod(1), t2); t2 = ptx::madc_hi_cc(m, P::mod(2), t3);
+      t3 = ptx::madc_hi_cc(m, P::mod(3), t4); t4 = ptx::madc_hi_cc(m, P::mod(4), t5); t5 = ptx::madc_hi_cc(m, P::mod(5), t6);
+      t6 = ptx::madc_hi_cc(m, P::mod(6), t7); t7 = ptx::madc_hi(m, P::mod(7), t8);
+    }
+    // t < 2p: one conditional subtraction
+    uint32_t s0 = ptx::sub_cc(t0, P::mod(0)), s1 = ptx::subc_cc(t1, P::mod(1)), s2 = ptx::subc_cc(t2, P::mod(2)),
+             s3 = ptx::subc_cc(t3, P::mod(3)), s4 = ptx::subc_cc(t4, P::mod(4)), s5 = ptx::subc_cc(t5, P::mod(5)),
+             s6 = ptx::subc_cc(t6, P::mod(6)), s7 = ptx::subc_cc(t7, P::mod(7));
+    const uint32_t borrow = ptx::subc(0, 0);  // 0xffffffff when t < p
+    Fp r;
+    r.v[0] = borrow ? t0 : s0; r.v[1] = borrow ? t1 : s1; r.v[2] = borrow ? t2 : s2; r.v[3] = borrow ? t3 : s3;
+    r.v[4] = borrow ? t4 : s4; r.v[5] = borrow ? t5 : s5; r.v[6] = borrow ? t6 : s6; r.v[7] = borrow ? t7 : s7;
+    return r;
+#else
     uint32_t t[9];
     ZK_UNROLL for (int i = 0; i < 9; i++) t[i] = 0;
     ZK_UNROLL for (int i = 0; i < 8; i++) {
@@ -92,9 +139,15 @@ struct alignas(16) Fp {
       c += t[8]; t[7] = (uint32_t)c; t[8] = (uint32_t)(c >> 32);
     }
     return reduce_once(t);
+#endif
   }
   static ZK_HD_NOINLINE Fp mul_call(Fp a, Fp b) { return mul_inline(a, b); }
   friend ZK_HD Fp operator*(const Fp& a, const Fp& b) { return mul_call(a, b); }
+#ifdef ZKFL_MADD_INLINE_MUL
+  static ZK_HD Fp mul_hot(const Fp& a, const Fp& b) { return mul_inline(a, b); }
+#else
+  static ZK_HD Fp mul_hot(const Fp& a, const Fp& b) { return mul_call(a, b); }
+#endif
   ZK_HD Fp sqr() const { return *this * *this; }
   ZK_HD Fp to_mont() const { return *this * r2(); }
   ZK_HD Fp from_mont() const { Fp o = zero(); o.v[0] = 1; return *this * o; }
@@ -129,8 +182,8 @@ struct alignas(16) Fq2 {
     Fq2 r; r.a = aa - bb; r.b = s - aa - bb; return r;
   }
   ZK_HD Fq2 sqr() const { Fq t = a * b; Fq2 r; r.a = (a + b) * (a - b); r.b = t.dbl(); return r; }
-  static ZK_HD Fq2 mul_inline(const Fq2& x, const Fq2& y) {
-    Fq aa = Fq::mul_inline(x.a, y.a), bb = Fq::mul_inline(x.b, y.b), s = Fq::mul_inline(x.a + x.b, y.a + y.b);
+  static ZK_HD Fq2 mul_hot(const Fq2& x, const Fq2& y) {
+    Fq aa = Fq::mul_hot(x.a, y.a), bb = Fq::mul_hot(x.b, y.b), s = Fq::mul_hot(x.a + x.b, y.a + y.b);
     Fq2 r; r.a = aa - bb; r.b = s - aa - bb; return r;
   }
   ZK_HD Fq2 inv() const { Fq d = (a.sqr() + b.sqr()).inv(); Fq2 r; r.a = a * d; r.b = (b * d).neg(); return r; }
@@ -174,24 +227,24 @@ template <class F> ZK_HD Xyzz<F> xyzz_dbl_affine(const Affine<F>& p) {  // mdbl-
   return r;
 }
 // acc += q (affine; infinity bases are skipped); `negate` flips q first.  Hot path of the MSM bucket
-// accumulation: products are inlined (mul_inline) so ptxas can interleave the independent IMAD chains.
+// accumulation (products go through mul_hot: a leaf call by default so the loop body stays inside the instruction cache).
 template <class F> ZK_HD void xyzz_madd(Xyzz<F>& acc, const Affine<F>& q0, bool negate) {  // madd-2008-s
   if (q0.is_inf()) return;
   Affine<F> q = q0;
   if (negate) q.y = q.y.neg();
   if (acc.is_inf()) { acc = Xyzz<F>::from_affine(q); return; }
-  F U2 = F::mul_inline(q.x, acc.ZZ), S2 = F::mul_inline(q.y, acc.ZZZ);
+  F U2 = F::mul_hot(q.x, acc.ZZ), S2 = F::mul_hot(q.y, acc.ZZZ);
   F Pp = U2 - acc.X, Rr = S2 - acc.Y;
   if (Pp.is_zero()) {
     if (Rr.is_zero()) acc = xyzz_dbl_affine(q); else acc = Xyzz<F>::infinity();
     return;
   }
-  F PP = F::mul_inline(Pp, Pp), PPP = F::mul_inline(Pp, PP), Qq = F::mul_inline(acc.X, PP);
-  F X3 = F::mul_inline(Rr, Rr) - PPP - Qq.dbl();
-  acc.Y = F::mul_inline(Rr, Qq - X3) - F::mul_inline(acc.Y, PPP);
+  F PP = F::mul_hot(Pp, Pp), PPP = F::mul_hot(Pp, PP), Qq = F::mul_hot(acc.X, PP);
+  F X3 = F::mul_hot(Rr, Rr) - PPP - Qq.dbl();
+  acc.Y = F::mul_hot(Rr, Qq - X3) - F::mul_hot(acc.Y, PPP);
   acc.X = X3;
-  acc.ZZ = F::mul_inline(acc.ZZ, PP);
-  acc.ZZZ = F::mul_inline(acc.ZZZ, PPP);
+  acc.ZZ = F::mul_hot(acc.ZZ, PP);
+  acc.ZZZ = F::mul_hot(acc.ZZZ, PPP);
 }
 template <class F> ZK_HD void xyzz_add(Xyzz<F>& acc, const Xyzz<F>& q) {  // add-2008-s
   if (q.is_inf()) return;

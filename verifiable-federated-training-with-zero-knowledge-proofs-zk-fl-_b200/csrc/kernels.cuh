@@ -221,11 +221,14 @@ ZK_HD int32_t signed_digit(const uint32_t* k, uint32_t j, uint32_t c, uint32_t& 
   return (int32_t)d;
 }
 
-// pass 1: bucket histogram. scalars: canonical [m][B]. counts: [B*W][nb]
-ZK_GLOBAL void k_msm_count(const Fr* __restrict__ scalars, MsmShape s, uint32_t* __restrict__ counts) {
+// pass 1: bucket histogram. scalars: canonical [m][B]. counts: [B*W][nb]. skip[i] != 0 drops point i
+// (bases that are the point at infinity: wires absent from the B matrix, public wires of the C query).
+ZK_GLOBAL void k_msm_count(const Fr* __restrict__ scalars, const uint8_t* __restrict__ skip, MsmShape s,
+                           uint32_t* __restrict__ counts) {
   size_t tid = ZK_TID;
   if (tid >= (size_t)s.m * s.B) return;
-  uint32_t b = (uint32_t)(tid % s.B);
+  uint32_t i = (uint32_t)(tid / s.B), b = (uint32_t)(tid % s.B);
+  if (skip && skip[i]) return;
   Fr k = scalars[tid];
   if (k.is_zero()) return;
   uint32_t carry = 0;
@@ -266,12 +269,14 @@ ZK_GLOBAL void k_msm_scan_write(const uint32_t* __restrict__ counts, const uint3
     acc += counts[row * s.nb + k];
   }
 }
-// pass 3: scatter point references into bucket order. sorted: [B*W][cap], entry = point | sign << 31
-ZK_GLOBAL void k_msm_scatter(const Fr* __restrict__ scalars, MsmShape s, uint32_t* __restrict__ cursors,
-                             uint32_t* __restrict__ sorted) {
+// pass 3: scatter point references into bucket order. sorted: [B*W][cap], entry = point | sign << 31;
+// skey: the bucket index of every entry (lets pass 4 walk the list in fixed-size chunks)
+ZK_GLOBAL void k_msm_scatter(const Fr* __restrict__ scalars, const uint8_t* __restrict__ skip, MsmShape s,
+                             uint32_t* __restrict__ cursors, uint32_t* __restrict__ sorted, uint16_t* __restrict__ skey) {
   size_t tid = ZK_TID;
   if (tid >= (size_t)s.m * s.B) return;
   uint32_t i = (uint32_t)(tid / s.B), b = (uint32_t)(tid % s.B);
+  if (skip && skip[i]) return;
   Fr k = scalars[tid];
   if (k.is_zero()) return;
   uint32_t carry = 0;
@@ -282,24 +287,69 @@ ZK_GLOBAL void k_msm_scatter(const Fr* __restrict__ scalars, MsmShape s, uint32_
     size_t row = (size_t)b * s.W + j;
     uint32_t pos = ZK_ATOMIC_ADD(cursors + row * s.nb + (mag - 1), 1u);
     sorted[row * s.cap + pos] = i | (d < 0 ? 0x80000000u : 0u);
+    skey[row * s.cap + pos] = (uint16_t)(mag - 1);
   }
 }
-// pass 4: bucket accumulation, one thread per (row, bucket): mixed adds of gathered affine bases.
+// pass 4: BALANCED bucket accumulation. One thread per (row, chunk of S consecutive sorted entries): every thread
+// performs exactly S mixed adds whatever the bucket-size distribution (witness scalars are far from uniform:
+// bits, small values, and the partial top window concentrate thousands of entries in a few buckets).
+// A bucket lying inside one chunk is written directly; a bucket cut by chunk borders leaves partial sums
+// (head = run containing the chunk's first entry, tail = run containing its last entry) for pass 4b.
 template <class F>
-ZK_GLOBAL void k_msm_accumulate(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ sorted,
-                                const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ counts, MsmShape s,
-                                Xyzz<F>* __restrict__ buckets) {
+ZK_GLOBAL void k_msm_accumulate_chunks(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ sorted,
+                                       const uint16_t* __restrict__ skey, const uint32_t* __restrict__ offsets,
+                                       const uint32_t* __restrict__ counts, MsmShape s, uint32_t S, uint32_t chunks_per_row,
+                                       Xyzz<F>* __restrict__ buckets, Xyzz<F>* __restrict__ head, Xyzz<F>* __restrict__ tail) {
+  size_t tid = ZK_TID;
+  if (tid >= (size_t)s.B * s.W * chunks_per_row) return;
+  size_t row = tid / chunks_per_row;
+  uint32_t ch = (uint32_t)(tid % chunks_per_row);
+  const uint32_t* off = offsets + row * s.nb;
+  const uint32_t* cnt = counts + row * s.nb;
+  uint32_t total = off[s.nb - 1] + cnt[s.nb - 1];
+  uint32_t pos0 = ch * S;
+  if (pos0 >= total) return;
+  uint32_t pos1 = pos0 + S < total ? pos0 + S : total;
+  const uint32_t* list = sorted + row * s.cap;
+  const uint16_t* keys = skey + row * s.cap;
+  uint32_t cur = keys[pos0];
+  bool first = true;
+  Xyzz<F> acc = Xyzz<F>::infinity();
+  for (uint32_t pos = pos0; pos < pos1; pos++) {
+    uint32_t k = keys[pos];
+    if (k != cur) {
+      // the run of bucket `cur` ends inside this chunk; it is whole unless it began in an earlier chunk
+      if (first && off[cur] < pos0) head[tid] = acc; else buckets[row * s.nb + cur] = acc;
+      acc = Xyzz<F>::infinity();
+      cur = k;
+      first = false;
+    }
+    uint32_t e = list[pos];
+    xyzz_madd(acc, bases[e & 0x7FFFFFFFu], (e >> 31) != 0);
+  }
+  bool starts_here = !(first && off[cur] < pos0);
+  bool ends_here = off[cur] + cnt[cur] <= pos1;
+  if (starts_here && ends_here) buckets[row * s.nb + cur] = acc;
+  else if (first) head[tid] = acc;   // run covers the chunk's first entry (possibly the whole chunk)
+  else tail[tid] = acc;              // run started here and continues in the next chunk
+}
+// pass 4b: one thread per (row, bucket): empty buckets become infinity, buckets spread over several chunks are
+// summed from the partials those chunks left.
+template <class F>
+ZK_GLOBAL void k_msm_fixup(const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ counts, MsmShape s, uint32_t S,
+                           uint32_t chunks_per_row, const Xyzz<F>* __restrict__ head, const Xyzz<F>* __restrict__ tail,
+                           Xyzz<F>* __restrict__ buckets) {
   size_t tid = ZK_TID;
   if (tid >= (size_t)s.B * s.W * s.nb) return;
   size_t row = tid / s.nb;
-  uint32_t start = offsets[tid], cnt = counts[tid];
-  const uint32_t* list = sorted + row * s.cap + start;
-  Xyzz<F> acc = Xyzz<F>::infinity();
-  for (uint32_t q = 0; q < cnt; q++) {
-    uint32_t e = list[q];
-    Affine<F> p = bases[e & 0x7FFFFFFFu];
-    xyzz_madd(acc, p, (e >> 31) != 0);
-  }
+  uint32_t st = offsets[tid], cnt = counts[tid];
+  if (cnt == 0) { buckets[tid] = Xyzz<F>::infinity(); return; }
+  uint32_t c0 = st / S, c1 = (st + cnt - 1) / S;
+  if (c0 == c1) return;  // written whole by its chunk
+  const Xyzz<F>* h = head + row * chunks_per_row;
+  const Xyzz<F>* t = tail + row * chunks_per_row;
+  Xyzz<F> acc = (st > c0 * S) ? t[c0] : h[c0];
+  for (uint32_t ch = c0 + 1; ch <= c1; ch++) xyzz_add(acc, h[ch]);
   buckets[tid] = acc;
 }
 // pass 5a: running sums over chunks of L buckets: R = sum B_k, T = sum (k - k0) * B_k  (k0 = chunk*L, k from 1)

@@ -83,7 +83,7 @@ struct zkfl_ctx {
   std::vector<std::string> order;
   // workspace (grow-only)
   DevBuf w, abc, hsc, stage_in, stage_rs, aos;
-  DevBuf counts, offsets, cursors, chunk_sums, sorted, buckets, Rs, Ts, win;
+  DevBuf counts, offsets, cursors, chunk_sums, sorted, skey, buckets, head, tail, Rs, Ts, win;
   DevBuf res_g1, res_g2, t_g1, t_g2, pis, var, proofs, pubs, bad;
   DevBuf msm_sc, msm_out;
   cudaEvent_t t0 = nullptr, t1 = nullptr;
@@ -194,7 +194,7 @@ struct zkfl_zkey {
   zkfl_ctx* ctx;
   uint32_t n_vars, n_public, domain, log_n;
   CsrBufs A, B;
-  DevBuf pA, pB1, pB2, pC, pH, tw_fwd, tw_inv, coset;
+  DevBuf pA, pB1, pB2, pC, pH, skipB, tw_fwd, tw_inv, coset;
   VkDev vk;
 };
 struct MsmBases {
@@ -226,7 +226,9 @@ static uint32_t reduce_chunk(const MsmShape& s) {
   return L;
 }
 
-static int msm_sort(zkfl_ctx* c, const Fr* scalars, const MsmShape& s) {
+static uint32_t accumulate_chunk() { uint32_t S = env_u32("ZKFL_MSM_CHUNK", 32); return S < 4 ? 4 : S; }
+
+static int msm_sort(zkfl_ctx* c, const Fr* scalars, const uint8_t* skip, const MsmShape& s) {
   size_t rows = (size_t)s.B * s.W;
   uint32_t nchunk = (s.nb + ZK_SCAN_CHUNK - 1) / ZK_SCAN_CHUNK;
   TRY(c->counts.reserve(rows * s.nb * 4));
@@ -234,12 +236,14 @@ static int msm_sort(zkfl_ctx* c, const Fr* scalars, const MsmShape& s) {
   TRY(c->cursors.reserve(rows * s.nb * 4));
   TRY(c->chunk_sums.reserve(rows * nchunk * 4));
   TRY(c->sorted.reserve(rows * s.cap * 4));
+  TRY(c->skey.reserve(rows * s.cap * 2));
   CU(cudaMemsetAsync(c->counts.p, 0, rows * s.nb * 4, c->stream));
-  ZK_LAUNCH(k_msm_count, (size_t)s.m * s.B, 256, c->stream, scalars, s, c->counts.as<uint32_t>());
+  ZK_LAUNCH(k_msm_count, (size_t)s.m * s.B, 256, c->stream, scalars, skip, s, c->counts.as<uint32_t>());
   ZK_LAUNCH(k_msm_scan_chunks, rows * nchunk, 128, c->stream, c->counts.as<uint32_t>(), s, c->chunk_sums.as<uint32_t>());
   ZK_LAUNCH(k_msm_scan_write, rows * nchunk, 128, c->stream, c->counts.as<uint32_t>(), c->chunk_sums.as<uint32_t>(), s,
             c->offsets.as<uint32_t>(), c->cursors.as<uint32_t>());
-  ZK_LAUNCH(k_msm_scatter, (size_t)s.m * s.B, 256, c->stream, scalars, s, c->cursors.as<uint32_t>(), c->sorted.as<uint32_t>());
+  ZK_LAUNCH(k_msm_scatter, (size_t)s.m * s.B, 256, c->stream, scalars, skip, s, c->cursors.as<uint32_t>(), c->sorted.as<uint32_t>(),
+            c->skey.as<uint16_t>());
   CU(cudaGetLastError());
   return 0;
 }
@@ -252,10 +256,16 @@ static int msm_run(zkfl_ctx* c, const Affine<F>* bases, const MsmShape& s, Xyzz<
   TRY(c->Rs.reserve(rows * nchunk * sizeof(Xyzz<F>)));
   TRY(c->Ts.reserve(rows * nchunk * sizeof(Xyzz<F>)));
   TRY(c->win.reserve(rows * sizeof(Xyzz<F>)));
+  const uint32_t S = accumulate_chunk(), cpr = (s.cap + S - 1) / S;
+  TRY(c->head.reserve(rows * cpr * sizeof(Xyzz<F>)));
+  TRY(c->tail.reserve(rows * cpr * sizeof(Xyzz<F>)));
   {
     Stage st(c, acc_tag);
-    ZK_LAUNCH(k_msm_accumulate<F>, rows * s.nb, 128, c->stream, bases, c->sorted.as<uint32_t>(), c->offsets.as<uint32_t>(),
-              c->counts.as<uint32_t>(), s, c->buckets.as<Xyzz<F>>());
+    ZK_LAUNCH(k_msm_accumulate_chunks<F>, rows * cpr, 128, c->stream, bases, c->sorted.as<uint32_t>(), c->skey.as<uint16_t>(),
+              c->offsets.as<uint32_t>(), c->counts.as<uint32_t>(), s, S, cpr, c->buckets.as<Xyzz<F>>(), c->head.as<Xyzz<F>>(),
+              c->tail.as<Xyzz<F>>());
+    ZK_LAUNCH(k_msm_fixup<F>, rows * s.nb, 128, c->stream, c->offsets.as<uint32_t>(), c->counts.as<uint32_t>(), s, S, cpr,
+              c->head.as<Xyzz<F>>(), c->tail.as<Xyzz<F>>(), c->buckets.as<Xyzz<F>>());
   }
   Stage st2(c, red_tag);
   ZK_LAUNCH(k_msm_reduce_chunks<F>, rows * nchunk, 128, c->stream, c->buckets.as<Xyzz<F>>(), s, L, c->Rs.as<Xyzz<F>>(),
@@ -290,13 +300,14 @@ static int prove_from_device_witness(zkfl_ctx* c, const zkfl_zkey* z, const Fr* 
   }
   G1Xyzz* r1 = c->res_g1.as<G1Xyzz>();
   MsmShape sw = msm_shape(m, B);
-  { Stage st(c, "msm_sort_w"); TRY(msm_sort(c, w, sw)); }
+  { Stage st(c, "msm_sort_w"); TRY(msm_sort(c, w, nullptr, sw)); }
   TRY(msm_run<Fq>(c, z->pA.as<G1Affine>(), sw, r1, "msm_acc_g1", "msm_reduce_g1"));
-  TRY(msm_run<Fq>(c, z->pB1.as<G1Affine>(), sw, r1 + B, "msm_acc_g1", "msm_reduce_g1"));
   TRY(msm_run<Fq>(c, z->pC.as<G1Affine>(), sw, r1 + 2 * (size_t)B, "msm_acc_g1", "msm_reduce_g1"));
+  { Stage st(c, "msm_sort_w"); TRY(msm_sort(c, w, z->skipB.as<uint8_t>(), sw)); }
+  TRY(msm_run<Fq>(c, z->pB1.as<G1Affine>(), sw, r1 + B, "msm_acc_g1", "msm_reduce_g1"));
   TRY(msm_run<Fq2>(c, z->pB2.as<G2Affine>(), sw, c->res_g2.as<G2Xyzz>(), "msm_acc_g2", "msm_reduce_g2"));
   MsmShape sh = msm_shape(n, B);
-  { Stage st(c, "msm_sort_h"); TRY(msm_sort(c, c->hsc.as<Fr>(), sh)); }
+  { Stage st(c, "msm_sort_h"); TRY(msm_sort(c, c->hsc.as<Fr>(), nullptr, sh)); }
   TRY(msm_run<Fq>(c, z->pH.as<G1Affine>(), sh, r1 + 3 * (size_t)B, "msm_acc_g1", "msm_reduce_g1"));
   {
     Stage st(c, "finalize");
@@ -603,6 +614,12 @@ int zkfl_zkey_load(zkfl_ctx* c, const uint8_t* d, size_t len, zkfl_zkey** out) {
   TRY(upload_csr(c, hA, z->A)); TRY(upload_csr(c, hB, z->B));
   TRY(upload(c, z->pA, S[5].p, S[5].len)); TRY(upload(c, z->pB1, S[6].p, S[6].len)); TRY(upload(c, z->pB2, S[7].p, S[7].len));
   TRY(upload(c, z->pH, S[9].p, S[9].len));
+  {  // wires without a B-query point (absent from the B matrix): dropped when sorting for the B1 / B2 MSMs
+    std::vector<uint8_t> skip(m, 0);
+    static const uint8_t zero64[64] = {0};
+    for (uint32_t i = 0; i < m; i++) skip[i] = memcmp(S[6].p + 64 * (size_t)i, zero64, 64) == 0;
+    TRY(upload(c, z->skipB, skip.data(), skip.size()));
+  }
   {  // C bases padded to n_vars so all four witness MSMs share one sorted index list
     std::vector<uint8_t> full(64 * (size_t)m, 0);
     memcpy(full.data() + 64 * (size_t)(l + 1), S[8].p, S[8].len);
@@ -739,7 +756,7 @@ int zkfl_msm_run(zkfl_ctx* c, void* handle, const uint8_t* scalars, size_t n, ui
   TRY(c->msm_sc.reserve(n * sizeof(Fr)));
   if (scalars) CU(cudaMemcpyAsync(c->msm_sc.p, scalars, n * sizeof(Fr), cudaMemcpyHostToDevice, c->stream));
   MsmShape s = msm_shape((uint32_t)n, 1);
-  { Stage st(c, "msm_sort"); TRY(msm_sort(c, c->msm_sc.as<Fr>(), s)); }
+  { Stage st(c, "msm_sort"); TRY(msm_sort(c, c->msm_sc.as<Fr>(), nullptr, s)); }
   TRY(c->msm_out.reserve(sizeof(G2Xyzz) + sizeof(G2Affine)));
   uint8_t* o = c->msm_out.as<uint8_t>();
   if (b->group == 1) {
