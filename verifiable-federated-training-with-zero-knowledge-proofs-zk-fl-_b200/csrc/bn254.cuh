@@ -49,6 +49,8 @@ __device__ __forceinline__ uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t 
 __device__ __forceinline__ uint32_t mad_hi_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("mad.hi.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
 __device__ __forceinline__ uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("madc.hi.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
 __device__ __forceinline__ uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("madc.hi.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+__device__ __forceinline__ uint32_t add_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ uint32_t addc_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
 __device__ __forceinline__ uint32_t addc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("addc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
 __device__ __forceinline__ uint32_t sub_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("sub.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
 __device__ __forceinline__ uint32_t subc_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("subc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
@@ -96,27 +98,54 @@ struct alignas(16) Fp {
   // bucket-accumulation path uses mul_inline directly so ptxas can schedule across products.
   static ZK_HD Fp mul_inline(const Fp& a, const Fp& b) {
 #ifdef ZKFL_PTX_MUL
-    // 32-bit IMAD carry chains: per row one lo chain and one hi chain (16 IMAD + 1 ADDC), 16 rows + 8 products
-    // for the quotient words = 280 integer-pipe instructions per product, nothing on the half-rate IMAD.WIDE path.
-    uint32_t t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0, t5 = 0, t6 = 0, t7 = 0, t8;
+    // Even/odd paired carry chains: every 32x32->64 product is a (mad.lo.cc, madc.hi.cc) pair on two ADJACENT
+    // accumulator words, which ptxas fuses into one IMAD.WIDE.U32(.X) with the carry in a predicate. Products of
+    // the even limbs accumulate in ev[] (word k has weight 2^(32k)), products of the odd limbs in od[] (word k has
+    // weight 2^(32(k+1))); after each Montgomery step the arrays swap roles (division by 2^32).  128 wide MACs +
+    // 8 quotient products per modular product; measured IMAD.WIDE rate on B200: ~35 per clock per SM.
+    uint32_t ev[8], od[8];
     ZK_UNROLL for (int i = 0; i < 8; i++) {
+      uint32_t* X = (i & 1) ? od : ev;   // plays "even" in this step
+      uint32_t* Y = (i & 1) ? ev : od;   // plays "odd"
       const uint32_t bi = b.v[i];
-      t0 = ptx::mad_lo_cc(a.v[0], bi, t0); t1 = ptx::madc_lo_cc(a.v[1], bi, t1); t2 = ptx::madc_lo_cc(a.v[2], bi, t2);
-      t3 = ptx::madc_lo_cc(a.v[3], bi, t3); t4 = ptx::madc_lo_cc(a.v[4], bi, t4); t5 = ptx::madc_lo_cc(a.v[5], bi, t5);
-      t6 = ptx::madc_lo_cc(a.v[6], bi, t6); t7 = ptx::madc_lo_cc(a.v[7], bi, t7); t8 = ptx::addc(0, 0);
-      t1 = ptx::mad_hi_cc(a.v[0], bi, t1); t2 = ptx::madc_hi_cc(a.v[1], bi, t2); t3 = ptx::madc_hi_cc(a.v[2], bi, t3);
-      t4 = ptx::madc_hi_cc(a.v[3], bi, t4); t5 = ptx::madc_hi_cc(a.v[4], bi, t5); t6 = ptx::madc_hi_cc(a.v[5], bi, t6);
-      t7 = ptx::madc_hi_cc(a.v[6], bi, t7); t8 = ptx::madc_hi(a.v[7], bi, t8);
-      const uint32_t m = t0 * P::inv();
-      t0 = ptx::mad_lo_cc(m, P::mod(0), t0); t1 = ptx::madc_lo_cc(m, P::mod(1), t1); t2 = ptx::madc_lo_cc(m, P::mod(2), t2);
-      t3 = ptx::madc_lo_cc(m, P::mod(3), t3); t4 = ptx::madc_lo_cc(m, P::mod(4), t4); t5 = ptx::madc_lo_cc(m, P::mod(5), t5);
-      t6 = ptx::madc_lo_cc(m, P::mod(6), t6); t7 = ptx::madc_lo_cc(m, P::mod(7), t7); t8 = ptx::addc(t8, 0);
-      // t0 is now 0: drop it (divide by 2^32) while adding the hi chain
-      t0 = ptx::mad_hi_cc(m, P::mod(0), t1); t1 = ptx::madc_hi_cc(m, P::mod(1), t2); t2 = ptx::madc_hi_cc(m, P::mod(2), t3);
-      t3 = ptx::madc_hi_cc(m, P::mod(3), t4); t4 = ptx::madc_hi_cc(m, P::mod(4), t5); t5 = ptx::madc_hi_cc(m, P::mod(5), t6);
-      t6 = ptx::madc_hi_cc(m, P::mod(6), t7); t7 = ptx::madc_hi(m, P::mod(7), t8);
+      if (i == 0) {
+        ZK_UNROLL for (int j = 0; j < 8; j += 2) {
+          Y[j] = a.v[j + 1] * bi; Y[j + 1] = __umulhi(a.v[j + 1], bi);
+          X[j] = a.v[j] * bi;     X[j + 1] = __umulhi(a.v[j], bi);
+        }
+      } else {
+        // previous total / 2^32: Y[0] is zero, Y[1] joins X[0], Y shifts down two words while taking the odd products
+        X[0] = ptx::add_cc(X[0], Y[1]);
+        ZK_UNROLL for (int j = 0; j < 6; j += 2) {
+          Y[j] = ptx::madc_lo_cc(a.v[j + 1], bi, Y[j + 2]);
+          Y[j + 1] = ptx::madc_hi_cc(a.v[j + 1], bi, Y[j + 3]);
+        }
+        Y[6] = ptx::madc_lo_cc(a.v[7], bi, 0);
+        Y[7] = ptx::madc_hi(a.v[7], bi, 0);
+        X[0] = ptx::mad_lo_cc(a.v[0], bi, X[0]); X[1] = ptx::madc_hi_cc(a.v[0], bi, X[1]);
+        ZK_UNROLL for (int j = 2; j < 8; j += 2) {
+          X[j] = ptx::madc_lo_cc(a.v[j], bi, X[j]);
+          X[j + 1] = ptx::madc_hi_cc(a.v[j], bi, X[j + 1]);
+        }
+        Y[7] = ptx::addc(Y[7], 0);
+      }
+      const uint32_t m = X[0] * P::inv();
+      Y[0] = ptx::mad_lo_cc(m, P::mod(1), Y[0]); Y[1] = ptx::madc_hi_cc(m, P::mod(1), Y[1]);
+      ZK_UNROLL for (int j = 2; j < 8; j += 2) {
+        Y[j] = ptx::madc_lo_cc(m, P::mod(j + 1), Y[j]);
+        Y[j + 1] = ptx::madc_hi_cc(m, P::mod(j + 1), Y[j + 1]);
+      }
+      X[0] = ptx::mad_lo_cc(m, P::mod(0), X[0]); X[1] = ptx::madc_hi_cc(m, P::mod(0), X[1]);
+      ZK_UNROLL for (int j = 2; j < 8; j += 2) {
+        X[j] = ptx::madc_lo_cc(m, P::mod(j), X[j]);
+        X[j + 1] = ptx::madc_hi_cc(m, P::mod(j), X[j + 1]);
+      }
+      Y[7] = ptx::addc(Y[7], 0);
     }
-    // t < 2p: one conditional subtraction
+    // after 8 steps od[] played "even" last (od[0] == 0): result = ev + od / 2^32, below 2p
+    uint32_t t0 = ptx::add_cc(ev[0], od[1]), t1 = ptx::addc_cc(ev[1], od[2]), t2 = ptx::addc_cc(ev[2], od[3]),
+             t3 = ptx::addc_cc(ev[3], od[4]), t4 = ptx::addc_cc(ev[4], od[5]), t5 = ptx::addc_cc(ev[5], od[6]),
+             t6 = ptx::addc_cc(ev[6], od[7]), t7 = ptx::addc(ev[7], 0);
     uint32_t s0 = ptx::sub_cc(t0, P::mod(0)), s1 = ptx::subc_cc(t1, P::mod(1)), s2 = ptx::subc_cc(t2, P::mod(2)),
              s3 = ptx::subc_cc(t3, P::mod(3)), s4 = ptx::subc_cc(t4, P::mod(4)), s5 = ptx::subc_cc(t5, P::mod(5)),
              s6 = ptx::subc_cc(t6, P::mod(6)), s7 = ptx::subc_cc(t7, P::mod(7));
