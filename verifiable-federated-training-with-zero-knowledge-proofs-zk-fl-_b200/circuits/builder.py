@@ -295,12 +295,44 @@ class CircuitBuilder:
         return LC.wire(base + n_internal - 1)
 
     # ------------------------------------------------------------------ output
+    def _schedule(self):
+        """Dependency levels of the witness ops: ops of one level are independent, so the GPU evaluator runs a
+        level as one launch over (ops of the level) x (client instances). Returns (ops sorted by level, offsets)."""
+        wire_level = [0] * self.n_wires
+        levels = []
+        for op in self.ops:
+            code, dst, a, b, c = op
+            if code == OP_POSEIDON:
+                ins = self.pos_in[b:b + a - 1]
+                n_out = 3 * pp.num_sboxes(a) + 1
+            else:
+                ins = list(self.lcs[a].t)
+                if code == OP_MULADD:
+                    ins += list(self.lcs[b].t)
+                    if c != NONE:
+                        ins += list(self.lcs[c].t)
+                n_out = b if code == OP_BITS else 1
+            lvl = 1 + max((wire_level[w] for w in ins), default=0)
+            for w in range(dst, dst + n_out):
+                wire_level[w] = lvl
+            levels.append(lvl)
+        order = sorted(range(len(self.ops)), key=lambda i: levels[i])   # stable: keeps program order inside a level
+        ops = [self.ops[i] for i in order]
+        offs, cur = [0], 1
+        for k, i in enumerate(order):
+            while levels[i] > cur:
+                offs.append(k)
+                cur += 1
+        offs.append(len(ops))
+        return ops, offs
+
     def compile(self) -> "CompiledCircuit":
         n_pub = sum(i.size for i in self.inputs if i.public)
         n_in = sum(i.size for i in self.inputs)
+        ops, level_off = self._schedule()
         return CompiledCircuit(self.name, self.n_wires, n_pub, n_in, self.n_constraints,
-                               self.A, self.B, self.C, self.inputs, self.ops, self.lcs,
-                               self.pos_in, sorted(self.widths))
+                               self.A, self.B, self.C, self.inputs, ops, self.lcs,
+                               self.pos_in, sorted(self.widths), level_off)
 
 
 def _fr_bytes(v: int) -> bytes:
@@ -330,6 +362,7 @@ class CompiledCircuit:
     lcs: list
     pos_in: list
     widths: list
+    level_off: list
 
     # -- `.r1cs` (iden3 binfile v1)
     def r1cs_bytes(self) -> bytes:
@@ -390,6 +423,7 @@ class CompiledCircuit:
             (6, struct.pack(f"<{len(self.pos_in)}I", *self.pos_in)),
             (7, bytes(pos)),
             (8, json.dumps(self.input_map()).encode()),
+            (9, struct.pack(f"<{len(self.level_off)}I", *self.level_off)),
         ]
         return _container(b"zkwp", 1, sections)
 

@@ -66,56 +66,62 @@ ZK_D Fr lc_eval(const ProgramDev& p, uint32_t k, const Fr* __restrict__ w, uint3
   return acc;
 }
 
-// one thread = one client instance; all threads run the same op stream (no divergence).
-// w: canonical witness [n_wires][B]; rows 1..n_inputs already hold the inputs.
-ZK_GLOBAL void k_witness(ProgramDev p, Fr* __restrict__ w, uint32_t B) {
+// w[0][b] = 1 for every client instance
+ZK_GLOBAL void k_witness_init(Fr* __restrict__ w, uint32_t B) {
   uint32_t b = (uint32_t)ZK_TID;
   if (b >= B) return;
   Fr one_c = Fr::zero(); one_c.v[0] = 1;
   w[b] = one_c;
-  for (uint32_t o = 0; o < p.n_ops; o++) {
-    const uint32_t* op = p.ops + 5 * (size_t)o;
-    const uint32_t code = ZK_LDG(op), dst = ZK_LDG(op + 1), a = ZK_LDG(op + 2), bb = ZK_LDG(op + 3), c = ZK_LDG(op + 4);
-    if (code == 1) {
-      w[(size_t)dst * B + b] = lc_eval(p, a, w, B, b).from_mont();
-    } else if (code == 2) {
-      Fr v = lc_eval(p, a, w, B, b) * lc_eval(p, bb, w, B, b);
-      if (c != 0xFFFFFFFFu) v = v + lc_eval(p, c, w, B, b);
-      w[(size_t)dst * B + b] = v.from_mont();
-    } else if (code == 3) {
-      Fr v = lc_eval(p, a, w, B, b).from_mont();
-      for (uint32_t i = 0; i < bb; i++) {
-        Fr bit = Fr::zero();
-        bit.v[0] = (v.v[i >> 5] >> (i & 31)) & 1u;
-        w[(size_t)(dst + i) * B + b] = bit;
-      }
-    } else if (code == 4) {
-      const uint32_t t = a;
-      const PoseidonDev K = p.pk[t];
-      Fr st[17], nx[17];
-      st[0] = Fr::zero();
-      for (uint32_t i = 1; i < t; i++) st[i] = w[(size_t)ZK_LDG(p.pos_in + bb + i - 1) * B + b].to_mont();
-      size_t k = dst;
-      for (uint32_t r = 0; r < K.rounds; r++) {
-        for (uint32_t i = 0; i < t; i++) st[i] = st[i] + K.C[r * t + i];
-        const uint32_t lanes = (r < 4 || r >= 4 + K.rp) ? t : 1;
-        for (uint32_t i = 0; i < lanes; i++) {
-          Fr x2 = st[i].sqr(), x4 = x2.sqr(), x5 = x4 * st[i];
-          w[k * B + b] = x2.from_mont();
-          w[(k + 1) * B + b] = x4.from_mont();
-          w[(k + 2) * B + b] = x5.from_mont();
-          k += 3;
-          st[i] = x5;
-        }
-        for (uint32_t i = 0; i < t; i++) {
-          Fr acc = Fr::zero();
-          for (uint32_t j = 0; j < t; j++) acc = acc + K.M[i * t + j] * st[j];
-          nx[i] = acc;
-        }
-        for (uint32_t i = 0; i < t; i++) st[i] = nx[i];
-      }
-      w[k * B + b] = st[0].from_mont();
+}
+// One dependency level of the witness program: thread = (op of the level, client instance), clients minor, so a warp
+// runs ONE op for 32 clients in lock-step (no divergence) and all its loads/stores are coalesced. The compiler
+// (circuits/builder.py) sorts ops by level; ops inside a level are independent of each other.
+// w: canonical witness [n_wires][B]; rows 1..n_inputs hold the inputs.
+ZK_GLOBAL void k_witness_level(ProgramDev p, Fr* __restrict__ w, uint32_t B, uint32_t op_lo, uint32_t op_hi) {
+  size_t tid = ZK_TID;
+  if (tid >= (size_t)(op_hi - op_lo) * B) return;
+  const uint32_t o = op_lo + (uint32_t)(tid / B), b = (uint32_t)(tid % B);
+  const uint32_t* op = p.ops + 5 * (size_t)o;
+  const uint32_t code = ZK_LDG(op), dst = ZK_LDG(op + 1), a = ZK_LDG(op + 2), bb = ZK_LDG(op + 3), c = ZK_LDG(op + 4);
+  if (code == 1) {
+    w[(size_t)dst * B + b] = lc_eval(p, a, w, B, b).from_mont();
+  } else if (code == 2) {
+    Fr v = lc_eval(p, a, w, B, b) * lc_eval(p, bb, w, B, b);
+    if (c != 0xFFFFFFFFu) v = v + lc_eval(p, c, w, B, b);
+    w[(size_t)dst * B + b] = v.from_mont();
+  } else if (code == 3) {
+    Fr v = lc_eval(p, a, w, B, b).from_mont();
+    for (uint32_t i = 0; i < bb; i++) {
+      Fr bit = Fr::zero();
+      bit.v[0] = (v.v[i >> 5] >> (i & 31)) & 1u;
+      w[(size_t)(dst + i) * B + b] = bit;
     }
+  } else if (code == 4) {
+    const uint32_t t = a;
+    const PoseidonDev K = p.pk[t];
+    Fr st[17], nx[17];
+    st[0] = Fr::zero();
+    for (uint32_t i = 1; i < t; i++) st[i] = w[(size_t)ZK_LDG(p.pos_in + bb + i - 1) * B + b].to_mont();
+    size_t k = dst;
+    for (uint32_t r = 0; r < K.rounds; r++) {
+      for (uint32_t i = 0; i < t; i++) st[i] = st[i] + K.C[r * t + i];
+      const uint32_t lanes = (r < 4 || r >= 4 + K.rp) ? t : 1;
+      for (uint32_t i = 0; i < lanes; i++) {
+        Fr x2 = st[i].sqr(), x4 = x2.sqr(), x5 = x4 * st[i];
+        w[k * B + b] = x2.from_mont();
+        w[(k + 1) * B + b] = x4.from_mont();
+        w[(k + 2) * B + b] = x5.from_mont();
+        k += 3;
+        st[i] = x5;
+      }
+      for (uint32_t i = 0; i < t; i++) {
+        Fr acc = Fr::zero();
+        for (uint32_t j = 0; j < t; j++) acc = acc + K.M[i * t + j] * st[j];
+        nx[i] = acc;
+      }
+      for (uint32_t i = 0; i < t; i++) st[i] = nx[i];
+    }
+    w[k * B + b] = st[0].from_mont();
   }
 }
 
@@ -199,12 +205,14 @@ ZK_GLOBAL void k_join_abc(const Fr* __restrict__ abc, Fr* __restrict__ out, uint
 
 // ================================================================================ K6/K7: Pippenger MSM
 // Batched over B proofs that share the bases. Signed c-bit digits: W = 254/c + 1 windows,
-// nb = 2^(c-1) buckets per window, row = b*W + j identifies one (proof, window) bucket set.
+// nb = 2^(c-1) buckets per bucket set, row = b*R + (R == 1 ? 0 : j) identifies one bucket set.
 struct MsmShape {
   uint32_t m;    // points
   uint32_t B;    // proofs
   uint32_t c, W, nb;
-  uint32_t cap;  // entries reserved per row in the sorted index list (= m)
+  uint32_t R;    // bucket sets ("rows") per proof: W (one per window) or 1 (all windows share one set: the bases
+                 // table then holds 2^(c*j) * P_i at index j*m + i, so no doublings are needed after the reduction)
+  uint32_t cap;  // entries reserved per row in the sorted index list (m, or m*W when R == 1)
 };
 ZK_HD uint32_t scalar_bits(const uint32_t* k, uint32_t pos, uint32_t c) {
   uint32_t word = pos >> 5, off = pos & 31;
@@ -236,7 +244,8 @@ ZK_GLOBAL void k_msm_count(const Fr* __restrict__ scalars, const uint8_t* __rest
     int32_t d = signed_digit(k.v, j, s.c, carry);
     if (d == 0) continue;
     uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
-    ZK_ATOMIC_ADD(counts + ((size_t)b * s.W + j) * s.nb + (mag - 1), 1u);
+    size_t row = s.R == 1 ? (size_t)b : (size_t)b * s.W + j;
+    ZK_ATOMIC_ADD(counts + row * s.nb + (mag - 1), 1u);
   }
 }
 // pass 2a: per-row chunk sums (chunk = SCAN_CHUNK buckets)
@@ -244,7 +253,7 @@ ZK_GLOBAL void k_msm_count(const Fr* __restrict__ scalars, const uint8_t* __rest
 ZK_GLOBAL void k_msm_scan_chunks(const uint32_t* __restrict__ counts, MsmShape s, uint32_t* __restrict__ chunk_sums) {
   size_t tid = ZK_TID;
   uint32_t nchunk = (s.nb + ZK_SCAN_CHUNK - 1) / ZK_SCAN_CHUNK;
-  if (tid >= (size_t)s.B * s.W * nchunk) return;
+  if (tid >= (size_t)s.B * s.R * nchunk) return;
   size_t row = tid / nchunk;
   uint32_t ch = (uint32_t)(tid % nchunk);
   uint32_t lo = ch * ZK_SCAN_CHUNK, hi = lo + ZK_SCAN_CHUNK < s.nb ? lo + ZK_SCAN_CHUNK : s.nb;
@@ -257,7 +266,7 @@ ZK_GLOBAL void k_msm_scan_write(const uint32_t* __restrict__ counts, const uint3
                                 uint32_t* __restrict__ offsets, uint32_t* __restrict__ cursors) {
   size_t tid = ZK_TID;
   uint32_t nchunk = (s.nb + ZK_SCAN_CHUNK - 1) / ZK_SCAN_CHUNK;
-  if (tid >= (size_t)s.B * s.W * nchunk) return;
+  if (tid >= (size_t)s.B * s.R * nchunk) return;
   size_t row = tid / nchunk;
   uint32_t ch = (uint32_t)(tid % nchunk);
   uint32_t acc = 0;
@@ -284,9 +293,10 @@ ZK_GLOBAL void k_msm_scatter(const Fr* __restrict__ scalars, const uint8_t* __re
     int32_t d = signed_digit(k.v, j, s.c, carry);
     if (d == 0) continue;
     uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
-    size_t row = (size_t)b * s.W + j;
+    size_t row = s.R == 1 ? (size_t)b : (size_t)b * s.W + j;
     uint32_t pos = ZK_ATOMIC_ADD(cursors + row * s.nb + (mag - 1), 1u);
-    sorted[row * s.cap + pos] = i | (d < 0 ? 0x80000000u : 0u);
+    uint32_t ref = s.R == 1 ? j * s.m + i : i;
+    sorted[(size_t)row * s.cap + pos] = ref | (d < 0 ? 0x80000000u : 0u);
     skey[row * s.cap + pos] = (uint16_t)(mag - 1);
   }
 }
@@ -301,7 +311,7 @@ ZK_GLOBAL void k_msm_accumulate_chunks(const Affine<F>* __restrict__ bases, cons
                                        const uint32_t* __restrict__ counts, MsmShape s, uint32_t S, uint32_t chunks_per_row,
                                        Xyzz<F>* __restrict__ buckets, Xyzz<F>* __restrict__ head, Xyzz<F>* __restrict__ tail) {
   size_t tid = ZK_TID;
-  if (tid >= (size_t)s.B * s.W * chunks_per_row) return;
+  if (tid >= (size_t)s.B * s.R * chunks_per_row) return;
   size_t row = tid / chunks_per_row;
   uint32_t ch = (uint32_t)(tid % chunks_per_row);
   const uint32_t* off = offsets + row * s.nb;
@@ -340,7 +350,7 @@ ZK_GLOBAL void k_msm_fixup(const uint32_t* __restrict__ offsets, const uint32_t*
                            uint32_t chunks_per_row, const Xyzz<F>* __restrict__ head, const Xyzz<F>* __restrict__ tail,
                            Xyzz<F>* __restrict__ buckets) {
   size_t tid = ZK_TID;
-  if (tid >= (size_t)s.B * s.W * s.nb) return;
+  if (tid >= (size_t)s.B * s.R * s.nb) return;
   size_t row = tid / s.nb;
   uint32_t st = offsets[tid], cnt = counts[tid];
   if (cnt == 0) { buckets[tid] = Xyzz<F>::infinity(); return; }
@@ -358,7 +368,7 @@ ZK_GLOBAL void k_msm_reduce_chunks(const Xyzz<F>* __restrict__ buckets, MsmShape
                                    Xyzz<F>* __restrict__ Ts) {
   size_t tid = ZK_TID;
   uint32_t nchunk = s.nb / L;
-  if (tid >= (size_t)s.B * s.W * nchunk) return;
+  if (tid >= (size_t)s.B * s.R * nchunk) return;
   size_t row = tid / nchunk;
   uint32_t ch = (uint32_t)(tid % nchunk);
   const Xyzz<F>* bk = buckets + row * s.nb + (size_t)ch * L;
@@ -375,7 +385,7 @@ template <class F>
 ZK_GLOBAL void k_msm_reduce_rows(const Xyzz<F>* __restrict__ Rs, const Xyzz<F>* __restrict__ Ts, MsmShape s, uint32_t L,
                                  Xyzz<F>* __restrict__ win) {
   size_t row = ZK_TID;
-  if (row >= (size_t)s.B * s.W) return;
+  if (row >= (size_t)s.B * s.R) return;
   uint32_t nchunk = s.nb / L;
   const Xyzz<F>* R = Rs + row * nchunk;
   const Xyzz<F>* T = Ts + row * nchunk;
@@ -394,12 +404,52 @@ template <class F>
 ZK_GLOBAL void k_msm_combine(const Xyzz<F>* __restrict__ win, MsmShape s, Xyzz<F>* __restrict__ out) {
   size_t b = ZK_TID;
   if (b >= s.B) return;
-  Xyzz<F> acc = win[b * s.W + (s.W - 1)];
-  for (int j = (int)s.W - 2; j >= 0; j--) {
+  Xyzz<F> acc = win[b * s.R + (s.R - 1)];
+  for (int j = (int)s.R - 2; j >= 0; j--) {
     for (uint32_t q = 0; q < s.c; q++) acc = xyzz_dbl(acc);
-    xyzz_add(acc, win[b * s.W + j]);
+    xyzz_add(acc, win[b * s.R + j]);
   }
   out[b] = acc;
+}
+
+// ================================================================================ per-zkey precomputation
+// table[j*m + i] = 2^(c*j) * P_i for j < W (affine Montgomery): the bases are per-circuit constants shared by every
+// proof, so the window shifts are paid once at zkey load instead of c doublings per window per proof.
+template <class F>
+ZK_GLOBAL void k_precompute_windows(const Affine<F>* __restrict__ bases, uint32_t m, uint32_t c, uint32_t W,
+                                    Affine<F>* __restrict__ table) {
+  size_t i = ZK_TID;
+  if (i >= m) return;
+  Affine<F> p = bases[i];
+  table[i] = p;
+  Xyzz<F> q = Xyzz<F>::from_affine(p);
+  for (uint32_t j = 1; j < W; j++) {
+    for (uint32_t k = 0; k < c; k++) q = xyzz_dbl(q);
+    Affine<F> a = xyzz_to_affine(q);
+    table[(size_t)j * m + i] = a;
+    q = Xyzz<F>::from_affine(a);
+  }
+}
+// fixed-base byte-window table: tab[j*256 + d] = (d << 8j) * base, j < 32 (entry d = 0 is infinity)
+template <class F>
+ZK_GLOBAL void k_fixed_base_table(Affine<F> base, Affine<F>* __restrict__ tab) {
+  size_t tid = ZK_TID;
+  if (tid >= 32 * 256) return;
+  uint32_t j = (uint32_t)(tid >> 8), d = (uint32_t)(tid & 255);
+  uint32_t k[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  k[j >> 2] = d << (8 * (j & 3));
+  if (j == 31 && d >= 64) { Affine<F> z; z.x = F::zero(); z.y = F::zero(); tab[tid] = z; return; }  // beyond 254 bits
+  tab[tid] = xyzz_to_affine(xyzz_scalar_mul(Xyzz<F>::from_affine(base), k));
+}
+// k * base from the byte-window table: 32 mixed adds
+template <class F>
+ZK_D Xyzz<F> fixed_base_mul(const Affine<F>* __restrict__ tab, const uint32_t* k) {
+  Xyzz<F> acc = Xyzz<F>::infinity();
+  for (uint32_t j = 0; j < 32; j++) {
+    uint32_t d = (k[j >> 2] >> (8 * (j & 3))) & 255u;
+    if (d) xyzz_madd(acc, tab[j * 256 + d], false);
+  }
+  return acc;
 }
 
 // ================================================================================ K8: blinding / finalisation
@@ -409,17 +459,18 @@ struct VkDev {
 };
 // phase 1: fixed-base terms. thread (b, k): k=0 r*delta1, 1 s*delta1, 2 -(r*s)*delta1 (G1) ; k=3 s*delta2 (G2)
 // rs: canonical [B][2] (host order: r then s). t_g1: [B][3], t_g2: [B]
-ZK_GLOBAL void k_fin_fixed(VkDev vk, const Fr* __restrict__ rs, uint32_t B, G1Xyzz* __restrict__ t_g1, G2Xyzz* __restrict__ t_g2) {
+ZK_GLOBAL void k_fin_fixed(const G1Affine* __restrict__ tab_d1, const G2Affine* __restrict__ tab_d2, const Fr* __restrict__ rs,
+                           uint32_t B, G1Xyzz* __restrict__ t_g1, G2Xyzz* __restrict__ t_g2) {
   size_t tid = ZK_TID;
   if (tid >= (size_t)B * 4) return;
   uint32_t b = (uint32_t)(tid / 4), k = (uint32_t)(tid % 4);
   Fr r = rs[2 * (size_t)b], sv = rs[2 * (size_t)b + 1];
-  if (k == 0) t_g1[3 * (size_t)b] = xyzz_scalar_mul(G1Xyzz::from_affine(vk.delta1), r.v);
-  else if (k == 1) t_g1[3 * (size_t)b + 1] = xyzz_scalar_mul(G1Xyzz::from_affine(vk.delta1), sv.v);
+  if (k == 0) t_g1[3 * (size_t)b] = fixed_base_mul<Fq>(tab_d1, r.v);
+  else if (k == 1) t_g1[3 * (size_t)b + 1] = fixed_base_mul<Fq>(tab_d1, sv.v);
   else if (k == 2) {
     Fr nrs = (r.to_mont() * sv.to_mont()).neg().from_mont();
-    t_g1[3 * (size_t)b + 2] = xyzz_scalar_mul(G1Xyzz::from_affine(vk.delta1), nrs.v);
-  } else t_g2[b] = xyzz_scalar_mul(G2Xyzz::from_affine(vk.delta2), sv.v);
+    t_g1[3 * (size_t)b + 2] = fixed_base_mul<Fq>(tab_d1, nrs.v);
+  } else t_g2[b] = fixed_base_mul<Fq2>(tab_d2, sv.v);
 }
 // phase 2: thread (b, k): k=0: pi_a = A + alpha + r*delta1, then s*pi_a ; k=1: pi_b1 = B1 + beta1 + s*delta1, then r*pi_b1
 // msm_g1: [4][B] = A, B1, C, H results. outputs pis[B][2] (pi_a, pi_b1) and var[B][2] (s*pi_a, r*pi_b1)

@@ -183,6 +183,7 @@ struct zkfl_circuit {
   zkfl_ctx* ctx;
   uint32_t n_wires, n_public, n_inputs, n_ops;
   DevBuf ops, lc_off, lc_wire, lc_coef, pos_in, pconst;
+  std::vector<uint32_t> level_off;  // ops [level_off[k], level_off[k+1]) form dependency level k
   ProgramDev dev;
 };
 struct zkfl_r1cs {
@@ -194,7 +195,8 @@ struct zkfl_zkey {
   zkfl_ctx* ctx;
   uint32_t n_vars, n_public, domain, log_n;
   CsrBufs A, B;
-  DevBuf pA, pB1, pB2, pC, pH, skipB, tw_fwd, tw_inv, coset;
+  DevBuf pA, pB1, pB2, pC, pH, skipB, tw_fwd, tw_inv, coset, tab_d1, tab_d2;
+  uint32_t c_w = 0, c_h = 0;  // window sizes the precomputed tables were built for
   VkDev vk;
 };
 struct MsmBases {
@@ -206,17 +208,20 @@ static uint32_t env_u32(const char* name, uint32_t dflt) {
   const char* v = getenv(name);
   return v && *v ? (uint32_t)strtoul(v, nullptr, 10) : dflt;
 }
-static MsmShape msm_shape(uint32_t m, uint32_t B) {
+// shared = all windows of a proof accumulate into ONE bucket set (bases table precomputed with the window shifts)
+static MsmShape msm_shape(uint32_t m, uint32_t B, bool shared, uint32_t force_c = 0) {
   uint32_t best_c = 4; double best = 1e300;
   for (uint32_t c = 4; c <= 16; c++) {
     double W = 254 / c + 1, nb = (double)(1u << (c - 1));
-    double cost = W * ((double)m + 2.6 * nb);
+    double cost = shared ? W * (double)m + 2.6 * nb : W * ((double)m + 2.6 * nb);
     if (cost < best) { best = cost; best_c = c; }
   }
-  uint32_t c = env_u32("ZKFL_MSM_C", best_c);
+  uint32_t c = force_c ? force_c : env_u32(shared ? "ZKFL_MSM_C_SHARED" : "ZKFL_MSM_C", best_c);
   if (c < 2) c = 2;
   if (c > 16) c = 16;
-  MsmShape s; s.m = m; s.B = B; s.c = c; s.W = 254 / c + 1; s.nb = 1u << (c - 1); s.cap = m;
+  MsmShape s; s.m = m; s.B = B; s.c = c; s.W = 254 / c + 1; s.nb = 1u << (c - 1);
+  s.R = shared ? 1 : s.W;
+  s.cap = shared ? m * s.W : m;
   return s;
 }
 static uint32_t reduce_chunk(const MsmShape& s) {
@@ -229,7 +234,7 @@ static uint32_t reduce_chunk(const MsmShape& s) {
 static uint32_t accumulate_chunk() { uint32_t S = env_u32("ZKFL_MSM_CHUNK", 32); return S < 4 ? 4 : S; }
 
 static int msm_sort(zkfl_ctx* c, const Fr* scalars, const uint8_t* skip, const MsmShape& s) {
-  size_t rows = (size_t)s.B * s.W;
+  size_t rows = (size_t)s.B * s.R;
   uint32_t nchunk = (s.nb + ZK_SCAN_CHUNK - 1) / ZK_SCAN_CHUNK;
   TRY(c->counts.reserve(rows * s.nb * 4));
   TRY(c->offsets.reserve(rows * s.nb * 4));
@@ -250,7 +255,7 @@ static int msm_sort(zkfl_ctx* c, const Fr* scalars, const uint8_t* skip, const M
 // buckets -> per-proof sums out[B]; uses the lists left by msm_sort
 template <class F>
 static int msm_run(zkfl_ctx* c, const Affine<F>* bases, const MsmShape& s, Xyzz<F>* out, const char* acc_tag, const char* red_tag) {
-  size_t rows = (size_t)s.B * s.W;
+  size_t rows = (size_t)s.B * s.R;
   uint32_t L = reduce_chunk(s), nchunk = s.nb / L;
   TRY(c->buckets.reserve(rows * s.nb * sizeof(Xyzz<F>)));
   TRY(c->Rs.reserve(rows * nchunk * sizeof(Xyzz<F>)));
@@ -299,14 +304,14 @@ static int prove_from_device_witness(zkfl_ctx* c, const zkfl_zkey* z, const Fr* 
     ZK_LAUNCH(k_join_abc, (size_t)n * B, 256, c->stream, abc, c->hsc.as<Fr>(), n, B);
   }
   G1Xyzz* r1 = c->res_g1.as<G1Xyzz>();
-  MsmShape sw = msm_shape(m, B);
+  MsmShape sw = msm_shape(m, B, true, z->c_w);
   { Stage st(c, "msm_sort_w"); TRY(msm_sort(c, w, nullptr, sw)); }
   TRY(msm_run<Fq>(c, z->pA.as<G1Affine>(), sw, r1, "msm_acc_g1", "msm_reduce_g1"));
   TRY(msm_run<Fq>(c, z->pC.as<G1Affine>(), sw, r1 + 2 * (size_t)B, "msm_acc_g1", "msm_reduce_g1"));
   { Stage st(c, "msm_sort_w"); TRY(msm_sort(c, w, z->skipB.as<uint8_t>(), sw)); }
   TRY(msm_run<Fq>(c, z->pB1.as<G1Affine>(), sw, r1 + B, "msm_acc_g1", "msm_reduce_g1"));
   TRY(msm_run<Fq2>(c, z->pB2.as<G2Affine>(), sw, c->res_g2.as<G2Xyzz>(), "msm_acc_g2", "msm_reduce_g2"));
-  MsmShape sh = msm_shape(n, B);
+  MsmShape sh = msm_shape(n, B, true, z->c_h);
   { Stage st(c, "msm_sort_h"); TRY(msm_sort(c, c->hsc.as<Fr>(), nullptr, sh)); }
   TRY(msm_run<Fq>(c, z->pH.as<G1Affine>(), sh, r1 + 3 * (size_t)B, "msm_acc_g1", "msm_reduce_g1"));
   {
@@ -316,7 +321,8 @@ static int prove_from_device_witness(zkfl_ctx* c, const zkfl_zkey* z, const Fr* 
     TRY(c->pis.reserve(2 * (size_t)B * sizeof(G1Xyzz)));
     TRY(c->var.reserve(2 * (size_t)B * sizeof(G1Xyzz)));
     TRY(c->proofs.reserve((size_t)B * 256));
-    ZK_LAUNCH(k_fin_fixed, (size_t)B * 4, 32, c->stream, z->vk, rs_dev, B, c->t_g1.as<G1Xyzz>(), c->t_g2.as<G2Xyzz>());
+    ZK_LAUNCH(k_fin_fixed, (size_t)B * 4, 32, c->stream, z->tab_d1.as<G1Affine>(), z->tab_d2.as<G2Affine>(), rs_dev, B,
+              c->t_g1.as<G1Xyzz>(), c->t_g2.as<G2Xyzz>());
     ZK_LAUNCH(k_fin_var, (size_t)B * 2, 32, c->stream, z->vk, rs_dev, B, r1, c->t_g1.as<G1Xyzz>(), c->pis.as<G1Xyzz>(),
               c->var.as<G1Xyzz>());
     ZK_LAUNCH(k_fin_write, (size_t)B * 3, 32, c->stream, z->vk, B, r1, c->res_g2.as<G2Xyzz>(), c->t_g1.as<G1Xyzz>(),
@@ -358,7 +364,11 @@ static int run_witness(zkfl_ctx* c, const zkfl_circuit* circ, const uint8_t* inp
     CU(cudaMemcpyAsync(c->stage_in.p, inputs_host, (size_t)circ->n_inputs * B * sizeof(Fr), cudaMemcpyHostToDevice, c->stream));
   }
   ZK_LAUNCH(k_aos_to_soa, (size_t)circ->n_inputs * B, 256, c->stream, c->stage_in.as<Fr>(), c->w.as<Fr>(), circ->n_inputs, B, 1u);
-  ZK_LAUNCH(k_witness, B, 32, c->stream, circ->dev, c->w.as<Fr>(), B);
+  ZK_LAUNCH(k_witness_init, B, 128, c->stream, c->w.as<Fr>(), B);
+  for (size_t k = 0; k + 1 < circ->level_off.size(); k++) {
+    uint32_t lo = circ->level_off[k], hi = circ->level_off[k + 1];
+    ZK_LAUNCH(k_witness_level, (size_t)(hi - lo) * B, 64, c->stream, circ->dev, c->w.as<Fr>(), B, lo, hi);
+  }
   CU(cudaGetLastError());
   return 0;
 }
@@ -465,6 +475,7 @@ int zkfl_circuit_load(zkfl_ctx* c, const uint8_t* d, size_t len, zkfl_circuit** 
   std::map<uint32_t, Sec> S;
   TRY(parse_sections(d, len, "zkwp", S));
   for (uint32_t id = 1; id <= 7; id++) if (!S.count(id)) return fail(ZKFL_ERR_FORMAT, "zkwp: missing section");
+  if (!S.count(9) || S[9].len < 8 || S[9].len % 4) return fail(ZKFL_ERR_FORMAT, "zkwp: missing level schedule");
   if (S[1].len != 32) return fail(ZKFL_ERR_FORMAT, "zkwp: bad header");
   uint32_t h[8]; memcpy(h, S[1].p, 32);
   uint32_t n_lcs = h[4], n_terms = h[5], n_pos = h[6], n_widths = h[7];
@@ -509,6 +520,11 @@ int zkfl_circuit_load(zkfl_ctx* c, const uint8_t* d, size_t len, zkfl_circuit** 
     k->dev.pk[p.t].rounds = p.rounds; k->dev.pk[p.t].rp = p.rp;
     k->dev.pk[p.t].C = k->pconst.as<Fr>() + p.c_off; k->dev.pk[p.t].M = k->pconst.as<Fr>() + p.m_off;
   }
+  k->level_off.resize(S[9].len / 4);
+  memcpy(k->level_off.data(), S[9].p, S[9].len);
+  if (k->level_off.front() != 0 || k->level_off.back() != k->n_ops) return fail(ZKFL_ERR_FORMAT, "zkwp: bad level schedule");
+  for (size_t i = 0; i + 1 < k->level_off.size(); i++)
+    if (k->level_off[i] > k->level_off[i + 1]) return fail(ZKFL_ERR_FORMAT, "zkwp: bad level schedule");
   // validate ops reference existing widths / wires
   const uint32_t* ops = (const uint32_t*)S[2].p;
   for (uint32_t o = 0; o < k->n_ops; o++) {
@@ -612,8 +628,30 @@ int zkfl_zkey_load(zkfl_ctx* c, const uint8_t* d, size_t len, zkfl_zkey** out) {
   coo_to_csr(n, rows[0], wires[0], coefs[0], hA);
   coo_to_csr(n, rows[1], wires[1], coefs[1], hB);
   TRY(upload_csr(c, hA, z->A)); TRY(upload_csr(c, hB, z->B));
-  TRY(upload(c, z->pA, S[5].p, S[5].len)); TRY(upload(c, z->pB1, S[6].p, S[6].len)); TRY(upload(c, z->pB2, S[7].p, S[7].len));
-  TRY(upload(c, z->pH, S[9].p, S[9].len));
+  // bases -> window-shifted tables 2^(c*j) * P_i (built on the device once per key)
+  z->c_w = msm_shape(m, 1, true).c;
+  z->c_h = msm_shape(n, 1, true).c;
+  auto build_table = [&](const uint8_t* pts, size_t bytes, uint32_t cnt, uint32_t cw, bool g2, DevBuf& out) -> int {
+    DevBuf raw;
+    TRY(upload(c, raw, pts, bytes));
+    uint32_t W = 254 / cw + 1;
+    TRY(out.reserve((size_t)W * bytes));
+    if (g2) ZK_LAUNCH(k_precompute_windows<Fq2>, cnt, 64, c->stream, raw.as<G2Affine>(), cnt, cw, W, out.as<G2Affine>());
+    else ZK_LAUNCH(k_precompute_windows<Fq>, cnt, 64, c->stream, raw.as<G1Affine>(), cnt, cw, W, out.as<G1Affine>());
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+  };
+  TRY(build_table(S[5].p, S[5].len, m, z->c_w, false, z->pA));
+  TRY(build_table(S[6].p, S[6].len, m, z->c_w, false, z->pB1));
+  TRY(build_table(S[7].p, S[7].len, m, z->c_w, true, z->pB2));
+  TRY(build_table(S[9].p, S[9].len, n, z->c_h, false, z->pH));
+  TRY(z->tab_d1.reserve(32 * 256 * sizeof(G1Affine)));
+  TRY(z->tab_d2.reserve(32 * 256 * sizeof(G2Affine)));
+  ZK_LAUNCH(k_fixed_base_table<Fq>, 32 * 256, 64, c->stream, z->vk.delta1, z->tab_d1.as<G1Affine>());
+  ZK_LAUNCH(k_fixed_base_table<Fq2>, 32 * 256, 64, c->stream, z->vk.delta2, z->tab_d2.as<G2Affine>());
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(c->stream));
   {  // wires without a B-query point (absent from the B matrix): dropped when sorting for the B1 / B2 MSMs
     std::vector<uint8_t> skip(m, 0);
     static const uint8_t zero64[64] = {0};
@@ -623,7 +661,7 @@ int zkfl_zkey_load(zkfl_ctx* c, const uint8_t* d, size_t len, zkfl_zkey** out) {
   {  // C bases padded to n_vars so all four witness MSMs share one sorted index list
     std::vector<uint8_t> full(64 * (size_t)m, 0);
     memcpy(full.data() + 64 * (size_t)(l + 1), S[8].p, S[8].len);
-    TRY(upload(c, z->pC, full.data(), full.size()));
+    TRY(build_table(full.data(), full.size(), m, z->c_w, false, z->pC));
   }
   {  // twiddles: w^k, w^-k (k < n/2); coset[p] = n^-1 * inc^bitrev(p), inc = w_{2n}
     Fr wn = fr_root_of_unity((int)z->log_n), wi = wn.inv();
@@ -755,7 +793,7 @@ int zkfl_msm_run(zkfl_ctx* c, void* handle, const uint8_t* scalars, size_t n, ui
   CU(cudaSetDevice(c->device));
   TRY(c->msm_sc.reserve(n * sizeof(Fr)));
   if (scalars) CU(cudaMemcpyAsync(c->msm_sc.p, scalars, n * sizeof(Fr), cudaMemcpyHostToDevice, c->stream));
-  MsmShape s = msm_shape((uint32_t)n, 1);
+  MsmShape s = msm_shape((uint32_t)n, 1, false);
   { Stage st(c, "msm_sort"); TRY(msm_sort(c, c->msm_sc.as<Fr>(), nullptr, s)); }
   TRY(c->msm_out.reserve(sizeof(G2Xyzz) + sizeof(G2Affine)));
   uint8_t* o = c->msm_out.as<uint8_t>();
