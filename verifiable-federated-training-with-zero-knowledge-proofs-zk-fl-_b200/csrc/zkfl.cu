@@ -83,25 +83,30 @@ struct zkfl_ctx {
   std::vector<std::string> order;
   // workspace (grow-only)
   DevBuf w, abc, hsc, stage_in, stage_rs, aos;
-  DevBuf counts, offsets, cursors, chunk_sums, sorted, skey, buckets, head, tail, Rs, Ts, win;
+  DevBuf counts, offsets, cursors, chunk_sums, sorted, skey, head, tail;
+  // five MSMs per proof batch (A, C, B1, H on G1; B2 on G2): own bucket / reduction buffers each, so the
+  // latency-bound bucket reduction of one MSM runs on `side` while the next MSM accumulates on `stream`
+  DevBuf buckets[5], Rs[5], Ts[5], win[5];
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_acc[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}, ev_done = nullptr;
   DevBuf res_g1, res_g2, t_g1, t_g2, pis, var, proofs, pubs, bad;
   DevBuf msm_sc, msm_out;
   cudaEvent_t t0 = nullptr, t1 = nullptr;
 };
 
 struct Stage {
-  zkfl_ctx* c; size_t idx = (size_t)-1; uint64_t l0;
-  Stage(zkfl_ctx* c_, const char* name) : c(c_) {
+  zkfl_ctx* c; size_t idx = (size_t)-1; uint64_t l0; cudaStream_t st;
+  Stage(zkfl_ctx* c_, const char* name, cudaStream_t stream = nullptr) : c(c_), st(stream ? stream : c_->stream) {
     if (!c->prof) return;
     ProfRec r; r.name = name; r.launches = 0;
     cudaEventCreate(&r.e0); cudaEventCreate(&r.e1);
-    cudaEventRecord(r.e0, c->stream);
+    cudaEventRecord(r.e0, st);
     l0 = g_launches.load();
     c->pending.push_back(r); idx = c->pending.size() - 1;
   }
   ~Stage() {
     if (idx == (size_t)-1) return;
-    cudaEventRecord(c->pending[idx].e1, c->stream);
+    cudaEventRecord(c->pending[idx].e1, st);
     c->pending[idx].launches = g_launches.load() - l0;
   }
 };
@@ -252,33 +257,50 @@ static int msm_sort(zkfl_ctx* c, const Fr* scalars, const uint8_t* skip, const M
   CU(cudaGetLastError());
   return 0;
 }
-// buckets -> per-proof sums out[B]; uses the lists left by msm_sort
+// bucket accumulation of one MSM (slot = which of the five buffer sets), on the main stream; uses the lists left by msm_sort
 template <class F>
-static int msm_run(zkfl_ctx* c, const Affine<F>* bases, const MsmShape& s, Xyzz<F>* out, const char* acc_tag, const char* red_tag) {
+static int msm_accumulate(zkfl_ctx* c, const Affine<F>* bases, const MsmShape& s, int slot, const char* tag) {
   size_t rows = (size_t)s.B * s.R;
-  uint32_t L = reduce_chunk(s), nchunk = s.nb / L;
-  TRY(c->buckets.reserve(rows * s.nb * sizeof(Xyzz<F>)));
-  TRY(c->Rs.reserve(rows * nchunk * sizeof(Xyzz<F>)));
-  TRY(c->Ts.reserve(rows * nchunk * sizeof(Xyzz<F>)));
-  TRY(c->win.reserve(rows * sizeof(Xyzz<F>)));
+  TRY(c->buckets[slot].reserve(rows * s.nb * sizeof(Xyzz<F>)));
   const uint32_t S = accumulate_chunk(), cpr = (s.cap + S - 1) / S;
   TRY(c->head.reserve(rows * cpr * sizeof(Xyzz<F>)));
   TRY(c->tail.reserve(rows * cpr * sizeof(Xyzz<F>)));
-  {
-    Stage st(c, acc_tag);
-    ZK_LAUNCH(k_msm_accumulate_chunks<F>, rows * cpr, 128, c->stream, bases, c->sorted.as<uint32_t>(), c->skey.as<uint16_t>(),
-              c->offsets.as<uint32_t>(), c->counts.as<uint32_t>(), s, S, cpr, c->buckets.as<Xyzz<F>>(), c->head.as<Xyzz<F>>(),
-              c->tail.as<Xyzz<F>>());
-    ZK_LAUNCH(k_msm_fixup<F>, rows * s.nb, 128, c->stream, c->offsets.as<uint32_t>(), c->counts.as<uint32_t>(), s, S, cpr,
-              c->head.as<Xyzz<F>>(), c->tail.as<Xyzz<F>>(), c->buckets.as<Xyzz<F>>());
-  }
-  Stage st2(c, red_tag);
-  ZK_LAUNCH(k_msm_reduce_chunks<F>, rows * nchunk, 128, c->stream, c->buckets.as<Xyzz<F>>(), s, L, c->Rs.as<Xyzz<F>>(),
-            c->Ts.as<Xyzz<F>>());
-  ZK_LAUNCH(k_msm_reduce_rows<F>, rows, 64, c->stream, c->Rs.as<Xyzz<F>>(), c->Ts.as<Xyzz<F>>(), s, L, c->win.as<Xyzz<F>>());
-  ZK_LAUNCH(k_msm_combine<F>, s.B, 32, c->stream, c->win.as<Xyzz<F>>(), s, out);
+  Stage st(c, tag);
+  ZK_LAUNCH(k_msm_accumulate_chunks<F>, rows * cpr, 128, c->stream, bases, c->sorted.as<uint32_t>(), c->skey.as<uint16_t>(),
+            c->offsets.as<uint32_t>(), c->counts.as<uint32_t>(), s, S, cpr, c->buckets[slot].as<Xyzz<F>>(), c->head.as<Xyzz<F>>(),
+            c->tail.as<Xyzz<F>>());
+  ZK_LAUNCH(k_msm_fixup<F>, rows * s.nb, 128, c->stream, c->offsets.as<uint32_t>(), c->counts.as<uint32_t>(), s, S, cpr,
+            c->head.as<Xyzz<F>>(), c->tail.as<Xyzz<F>>(), c->buckets[slot].as<Xyzz<F>>());
   CU(cudaGetLastError());
   return 0;
+}
+static int msm_reserve_reduce(zkfl_ctx* c, const MsmShape& s, int slot, size_t elem) {
+  size_t rows = (size_t)s.B * s.R;
+  uint32_t L = reduce_chunk(s), nchunk = s.nb / L;
+  TRY(c->Rs[slot].reserve(rows * nchunk * elem));
+  TRY(c->Ts[slot].reserve(rows * nchunk * elem));
+  TRY(c->win[slot].reserve(rows * elem));
+  return 0;
+}
+// bucket reduction sum_k k * B_k of one MSM on `stream` -> out[B]. Buffers must have been reserved (msm_reserve_reduce).
+template <class F>
+static int msm_reduce(zkfl_ctx* c, const MsmShape& s, int slot, Xyzz<F>* out, cudaStream_t stream, const char* tag) {
+  size_t rows = (size_t)s.B * s.R;
+  uint32_t L = reduce_chunk(s), nchunk = s.nb / L;
+  Stage st(c, tag, stream);
+  ZK_LAUNCH(k_msm_reduce_chunks<F>, rows * nchunk, 64, stream, c->buckets[slot].as<Xyzz<F>>(), s, L, c->Rs[slot].as<Xyzz<F>>(),
+            c->Ts[slot].as<Xyzz<F>>());
+  ZK_LAUNCH(k_msm_reduce_rows<F>, rows, 32, stream, c->Rs[slot].as<Xyzz<F>>(), c->Ts[slot].as<Xyzz<F>>(), s, L,
+            c->win[slot].as<Xyzz<F>>());
+  ZK_LAUNCH(k_msm_combine<F>, s.B, 32, stream, c->win[slot].as<Xyzz<F>>(), s, out);
+  CU(cudaGetLastError());
+  return 0;
+}
+template <class F>
+static int msm_run(zkfl_ctx* c, const Affine<F>* bases, const MsmShape& s, Xyzz<F>* out, const char* acc_tag, const char* red_tag) {
+  TRY(msm_accumulate<F>(c, bases, s, 0, acc_tag));
+  TRY(msm_reserve_reduce(c, s, 0, sizeof(Xyzz<F>)));
+  return msm_reduce<F>(c, s, 0, out, c->stream, red_tag);
 }
 
 // ------------------------------------------------------------------------------------ prove pipeline (witness in c->w)
@@ -304,16 +326,44 @@ static int prove_from_device_witness(zkfl_ctx* c, const zkfl_zkey* z, const Fr* 
     ZK_LAUNCH(k_join_abc, (size_t)n * B, 256, c->stream, abc, c->hsc.as<Fr>(), n, B);
   }
   G1Xyzz* r1 = c->res_g1.as<G1Xyzz>();
+  G2Xyzz* r2 = c->res_g2.as<G2Xyzz>();
   MsmShape sw = msm_shape(m, B, true, z->c_w);
-  { Stage st(c, "msm_sort_w"); TRY(msm_sort(c, w, nullptr, sw)); }
-  TRY(msm_run<Fq>(c, z->pA.as<G1Affine>(), sw, r1, "msm_acc_g1", "msm_reduce_g1"));
-  TRY(msm_run<Fq>(c, z->pC.as<G1Affine>(), sw, r1 + 2 * (size_t)B, "msm_acc_g1", "msm_reduce_g1"));
-  { Stage st(c, "msm_sort_w"); TRY(msm_sort(c, w, z->skipB.as<uint8_t>(), sw)); }
-  TRY(msm_run<Fq>(c, z->pB1.as<G1Affine>(), sw, r1 + B, "msm_acc_g1", "msm_reduce_g1"));
-  TRY(msm_run<Fq2>(c, z->pB2.as<G2Affine>(), sw, c->res_g2.as<G2Xyzz>(), "msm_acc_g2", "msm_reduce_g2"));
   MsmShape sh = msm_shape(n, B, true, z->c_h);
+  // slots: 0 = A, 1 = C, 2 = B1, 3 = H (G1), 4 = B2 (G2). All allocations happen before any side-stream work
+  // (cudaMalloc / cudaFree inside reserve() would serialise the device).
+  for (int slot = 0; slot < 3; slot++) TRY(msm_reserve_reduce(c, sw, slot, sizeof(G1Xyzz)));
+  TRY(msm_reserve_reduce(c, sh, 3, sizeof(G1Xyzz)));
+  TRY(msm_reserve_reduce(c, sw, 4, sizeof(G2Xyzz)));
+  if (!c->side) {
+    CU(cudaStreamCreate(&c->side));
+    for (int i = 0; i < 5; i++) CU(cudaEventCreate(&c->ev_acc[i]));
+    CU(cudaEventCreate(&c->ev_done));
+  }
+  { Stage st(c, "msm_sort_w"); TRY(msm_sort(c, w, nullptr, sw)); }
+  TRY(msm_accumulate<Fq>(c, z->pA.as<G1Affine>(), sw, 0, "msm_acc_g1"));
+  CU(cudaEventRecord(c->ev_acc[0], c->stream));
+  CU(cudaStreamWaitEvent(c->side, c->ev_acc[0], 0));
+  TRY(msm_reduce<Fq>(c, sw, 0, r1, c->side, "msm_reduce_g1"));
+  TRY(msm_accumulate<Fq>(c, z->pC.as<G1Affine>(), sw, 1, "msm_acc_g1"));
+  CU(cudaEventRecord(c->ev_acc[1], c->stream));
+  CU(cudaStreamWaitEvent(c->side, c->ev_acc[1], 0));
+  TRY(msm_reduce<Fq>(c, sw, 1, r1 + 2 * (size_t)B, c->side, "msm_reduce_g1"));
+  { Stage st(c, "msm_sort_w"); TRY(msm_sort(c, w, z->skipB.as<uint8_t>(), sw)); }
+  TRY(msm_accumulate<Fq>(c, z->pB1.as<G1Affine>(), sw, 2, "msm_acc_g1"));
+  CU(cudaEventRecord(c->ev_acc[2], c->stream));
+  CU(cudaStreamWaitEvent(c->side, c->ev_acc[2], 0));
+  TRY(msm_reduce<Fq>(c, sw, 2, r1 + B, c->side, "msm_reduce_g1"));
+  TRY(msm_accumulate<Fq2>(c, z->pB2.as<G2Affine>(), sw, 4, "msm_acc_g2"));
+  CU(cudaEventRecord(c->ev_acc[4], c->stream));
+  CU(cudaStreamWaitEvent(c->side, c->ev_acc[4], 0));
+  TRY(msm_reduce<Fq2>(c, sw, 4, r2, c->side, "msm_reduce_g2"));
   { Stage st(c, "msm_sort_h"); TRY(msm_sort(c, c->hsc.as<Fr>(), nullptr, sh)); }
-  TRY(msm_run<Fq>(c, z->pH.as<G1Affine>(), sh, r1 + 3 * (size_t)B, "msm_acc_g1", "msm_reduce_g1"));
+  TRY(msm_accumulate<Fq>(c, z->pH.as<G1Affine>(), sh, 3, "msm_acc_g1"));
+  CU(cudaEventRecord(c->ev_acc[3], c->stream));
+  CU(cudaStreamWaitEvent(c->side, c->ev_acc[3], 0));
+  TRY(msm_reduce<Fq>(c, sh, 3, r1 + 3 * (size_t)B, c->side, "msm_reduce_g1"));
+  CU(cudaEventRecord(c->ev_done, c->side));
+  CU(cudaStreamWaitEvent(c->stream, c->ev_done, 0));
   {
     Stage st(c, "finalize");
     TRY(c->t_g1.reserve(3 * (size_t)B * sizeof(G1Xyzz)));
@@ -435,6 +485,12 @@ void zkfl_ctx_free(zkfl_ctx* c) {
   cudaStreamSynchronize(c->stream);
   for (auto& r : c->pending) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
   if (c->t0) { cudaEventDestroy(c->t0); cudaEventDestroy(c->t1); }
+  if (c->side) {
+    cudaStreamSynchronize(c->side);
+    for (int i = 0; i < 5; i++) cudaEventDestroy(c->ev_acc[i]);
+    cudaEventDestroy(c->ev_done);
+    cudaStreamDestroy(c->side);
+  }
   cudaStreamDestroy(c->stream);
   delete c;
 }

@@ -79,6 +79,7 @@ inline int cudaGetLastError() { return 0; }
 inline int cudaEventCreate(void** e) { *e = nullptr; return 0; }
 inline int cudaEventDestroy(void*) { return 0; }
 inline int cudaEventRecord(void*, void*) { return 0; }
+inline int cudaStreamWaitEvent(void*, void*, unsigned) { return 0; }
 inline int cudaEventSynchronize(void*) { return 0; }
 inline int cudaEventElapsedTime(float* ms, void*, void*) { *ms = 0.f; return 0; }
 inline int cudaGetDeviceCount(int* n) { *n = 1; return 0; }
