@@ -89,6 +89,24 @@ int zkfl_full_prove_stage(zkfl_ctx* ctx, const zkfl_circuit* c, const zkfl_zkey*
 int zkfl_full_prove_run(zkfl_ctx* ctx, const zkfl_circuit* c, const zkfl_zkey* z, int B);
 int zkfl_full_prove_fetch(zkfl_ctx* ctx, int B, uint8_t* proofs_out);
 
+/* ---- one large proof split across GPUs (BASELINE.json configs[4]): rank `part` of `nparts` runs the five
+ *      multi-scalar multiplications over ITS point range [part*m/nparts, (part+1)*m/nparts) and returns the partial
+ *      sums; the ranks all-gather the partials (NCCL / gloo: 384 B per proof per rank) and any rank finishes with
+ *      zkfl_groth16_finalize, which adds the partials (the group law is no NCCL reduction op) and applies the blinding.
+ *      partials layout per call: [A(64) x B | B1 x B | C x B | H x B | B2(128) x B], affine canonical. --------------- */
+int zkfl_groth16_msm_partials(zkfl_ctx* ctx, const zkfl_zkey* z, const uint8_t* wtns, int B, uint32_t part, uint32_t nparts,
+                              uint8_t* partials_out /* B x 384 */);
+int zkfl_groth16_finalize(zkfl_ctx* ctx, const zkfl_zkey* z, const uint8_t* partials /* nparts x B x 384 */, uint32_t nparts,
+                          const uint8_t* rs, int B, uint8_t* proofs_out /* B x 256 */);
+
+/* ---- verify: `snarkjs groth16 verify vkey.json public.json proof.json`
+ *      (tests/full_system_simulation.mjs:865-868,975-978,1116-1119). Host-side pairing check (SURVEY 2.4 row V1:
+ *      verification stays on the CPU). All points affine canonical little-endian as in vkey.json / proof.json:
+ *      alpha1 64 B, beta2/gamma2/delta2 128 B (x.c0,x.c1,y.c0,y.c1), ic (n_public+1) x 64 B, publics n_public x 32 B.
+ *      *ok = 1 iff e(A,B) = e(alpha,beta) e(vk_x,gamma) e(C,delta) and every public signal is < r. ---------------- */
+int zkfl_groth16_verify(const uint8_t* alpha1, const uint8_t* beta2, const uint8_t* gamma2, const uint8_t* delta2,
+                        const uint8_t* ic, const uint8_t* publics, uint32_t n_public, const uint8_t* proof, int* ok);
+
 /* ---- standalone multi-scalar multiplication (BASELINE.json: "G1 MSM pts/s at 2^20") ----------- */
 /* bases: n affine points, Montgomery little-endian (zkey point layout, 64 B G1 / 128 B G2);
  * scalars: n x 32 B canonical; out: affine canonical (64 / 128 B). */

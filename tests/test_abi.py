@@ -52,3 +52,23 @@ def test_product_does_not_import_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle_lib" not in src and "bn254_ref" not in src and "groth16_ref" not in src, f
+
+
+def test_host_verifier_in_the_real_library_without_a_gpu():
+    """`groth16 verify` is host code inside libzkfl.so (CPU): it must accept the golden proof made by the
+    pure-Python oracle and reject tampered inputs, with no CUDA device present."""
+    import __graft_entry__ as ge
+    ge.build_cuda()
+    import zkfl_b200  # noqa: F401
+    from zkfl_b200 import formats
+    from zkfl_b200 import snarkjs as sj
+    g = os.path.join(ROOT, "tests", "golden")
+    zk = open(os.path.join(g, "tiny.zkey"), "rb").read()
+    proof = formats.proof_bytes_to_json(open(os.path.join(g, "tiny.proof"), "rb").read())
+    vk = formats.export_verification_key(zk)
+    assert sj.groth16.verify(vk, ["228", "17"], proof)
+    assert not sj.groth16.verify(vk, ["229", "17"], proof)
+    assert not sj.groth16.verify(vk, ["228"], proof)
+    assert not sj.groth16.verify(vk, [str(2 ** 255), "17"], proof)
+    bad = dict(proof, pi_a=[proof["pi_a"][1], proof["pi_a"][0], "1"])
+    assert not sj.groth16.verify(vk, ["228", "17"], bad)

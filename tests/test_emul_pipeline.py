@@ -50,3 +50,48 @@ def test_bad_arguments_fail_loudly(emul_prover):
         emul_prover.load_zkey(b"zkey" + bytes(100))
     with pytest.raises(_lib.ZkflError):
         emul_prover.g1_mul_generator((2 ** 256 - 1).to_bytes(32, "little"))   # not reduced mod r
+
+
+def test_snarkjs_surface_and_cli_round_trip(tmp_path, monkeypatch):
+    """The file-based flow of the reference's tests (compile, setup, witness, prove, verify) through the snarkjs-named
+    API and the CLI shim, on the emulation library; the proof must match the oracle and verify in both verifiers."""
+    import json
+    import __graft_entry__ as ge
+    import groth16_ref as g16
+    import oracle_lib as ol
+    monkeypatch.setenv("ZKFL_LIBRARY_PATH", ge.build_emul())
+    from zkfl_b200 import snarkjs as sj
+    from zkfl_b200 import cli, formats
+    monkeypatch.setitem(sj._state, "prover", None)
+    monkeypatch.setitem(sj._state, "circuits", {})
+    monkeypatch.setitem(sj._state, "zkeys", {})
+    d = str(tmp_path)
+    assert cli.main(["circom", "secure_agg_client.circom", "--r1cs", "--wasm", "--sym", "-o", d]) == 0
+    assert cli.main(["snarkjs", "r1cs", "info", f"{d}/secure_agg_client.r1cs"]) == 0
+    assert cli.main(["snarkjs", "groth16", "setup", f"{d}/secure_agg_client.r1cs", f"{d}/pot12_final.ptau", f"{d}/c_0000.zkey"]) == 0
+    assert cli.main(["snarkjs", "zkey", "contribute", f"{d}/c_0000.zkey", f"{d}/c_final.zkey", "--name=t", "-e=x"]) == 0
+    assert cli.main(["snarkjs", "zkey", "export", "verificationkey", f"{d}/c_final.zkey", f"{d}/vkey.json"]) == 0
+    json.dump(I.secure_agg_client_input(), open(f"{d}/input.json", "w"))
+    wasm = f"{d}/secure_agg_client_js/secure_agg_client.wasm"
+    assert cli.main(["snarkjs", "wtns", "calculate", wasm, f"{d}/input.json", f"{d}/w.wtns"]) == 0
+    assert cli.main(["generate_witness", wasm, f"{d}/input.json", f"{d}/w2.wtns"]) == 0
+    assert open(f"{d}/w.wtns", "rb").read() == open(f"{d}/w2.wtns", "rb").read()
+    assert cli.main(["snarkjs", "groth16", "prove", f"{d}/c_final.zkey", f"{d}/w.wtns", f"{d}/proof.json", f"{d}/public.json"]) == 0
+    assert cli.main(["snarkjs", "groth16", "verify", f"{d}/vkey.json", f"{d}/public.json", f"{d}/proof.json"]) == 0
+    pub = json.load(open(f"{d}/public.json"))
+    bad = [str(int(pub[0]) + 1)] + pub[1:]
+    json.dump(bad, open(f"{d}/public_bad.json", "w"))
+    assert cli.main(["snarkjs", "groth16", "verify", f"{d}/vkey.json", f"{d}/public_bad.json", f"{d}/proof.json"]) == 1
+    bad_in = dict(I.secure_agg_client_input(), tau_squared="0", gradient=["3"] + ["0"] * 7)
+    json.dump(bad_in, open(f"{d}/bad_input.json", "w"))
+    assert cli.main(["snarkjs", "wtns", "calculate", wasm, f"{d}/bad_input.json", f"{d}/bad.wtns"]) == 1   # Assert Failed
+    # fixed blinding: API result equals the oracle's proof bytes; the oracle's pairing accepts it too
+    zk = open(f"{d}/c_final.zkey", "rb").read()
+    res = sj.groth16.fullProve(I.secure_agg_client_input(), wasm, f"{d}/c_final.zkey", rs=(5, 6))
+    w = formats.wtns_read(open(f"{d}/w.wtns", "rb").read())
+    ref_proof, ref_pub = ol.groth16_prove(zk, w, 5, 6)
+    assert formats.proof_json_to_bytes(res["proof"]) == ref_proof
+    assert res["publicSignals"] == [str(x) for x in ol.ints(ref_pub)]
+    vk = json.load(open(f"{d}/vkey.json"))
+    assert sj.groth16.verify(vk, res["publicSignals"], res["proof"])
+    assert g16.verify(g16.vkey_from_json(vk), ol.ints(ref_pub), g16.proof_from_json(res["proof"]))

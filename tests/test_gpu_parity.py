@@ -107,3 +107,67 @@ def test_random_blinding_still_verifies(gpu_prover):
     vk = g16.vkey_from_json(export_verification_key(zk))
     assert g16.verify(vk, ol.ints(pub1[0]), g16.proof_from_bytes(p1[0]))
     assert g16.verify(vk, ol.ints(pub1[0]), g16.proof_from_bytes(p2[0]))
+
+
+def test_product_verifier_agrees_with_oracle(gpu_prover):
+    import groth16_ref as g16
+    from zkfl_b200 import formats
+    from zkfl_b200 import snarkjs as sj
+    cc = build_circuit("secure_masked_update")
+    clients = I.simulation_clients(3)
+    for c in clients:
+        c.training_input([0] * 4)
+    ins = [c.secagg_input([j for j in (1, 2, 3) if j != c.id]) for c in clients]
+    zk, proofs, pubs = pc.case_prove(gpu_prover, cc, ins, [(1, 2), (3, 4), (5, 6)], python_verify=1)
+    vkj = formats.export_verification_key(zk)
+    for p, q in zip(proofs, pubs):
+        sig = formats.publics_bytes_to_json(q)
+        assert sj.groth16.verify(vkj, sig, formats.proof_bytes_to_json(p))
+        assert not sj.groth16.verify(vkj, [str(int(sig[0]) + 1)] + sig[1:], formats.proof_bytes_to_json(p))
+    swapped = formats.proof_bytes_to_json(proofs[0])
+    assert not sj.groth16.verify(vkj, formats.publics_bytes_to_json(pubs[1]), swapped)
+
+
+def test_split_msm_partials_single_gpu(gpu_prover):
+    """the multi-GPU split of one proof (point ranges + gather + add), with the ranks emulated one after another on one GPU"""
+    cc = build_circuit("sgd_verified")
+    circ = gpu_prover.load_circuit(cc)
+    zk = gpu_prover.new_zkey(cc, b"split")
+    Z = gpu_prover.load_zkey(zk)
+    ins = I.sgd_verified_batch(2, nonzero_weights=True)
+    ws = gpu_prover.calculate_witness(circ, ins)
+    rs = [(123, 456), (789, 1011)]
+    for nparts in (2, 3, 8):
+        parts = [gpu_prover.msm_partials(Z, ws, r, nparts) for r in range(nparts)]
+        got = gpu_prover.finalize(Z, parts, 2, rs)
+        assert got == [ol.groth16_prove(zk, w, *r)[0] for w, r in zip(ws, rs)], nparts
+    Z.close()
+    circ.close()
+
+
+def test_balance_unified_prod_2pow19(gpu_prover):
+    """BASELINE configs[0] at production size: BalanceProofUnified(128,7,16) over the seed-42 dataset whose Merkle root is
+    data/test_input_v5.json's root_D; 362k wires, domain 2^19; bit-exact against the oracle and pairing-verified."""
+    import json
+    import os
+    import groth16_ref as g16
+    from zkfl_b200 import formats
+    from zkfl_b200 import snarkjs as sj
+    inp = I.balance_prod_input()
+    golden = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "test_input_v5.json")))
+    assert inp["root"] == golden["root_D"]
+    cc = build_circuit("balance_unified_prod")
+    circ = gpu_prover.load_circuit(cc, check_constraints=False)
+    zk = gpu_prover.new_zkey(cc, b"prod")
+    Z = gpu_prover.load_zkey(zk)
+    assert Z.domain == 1 << 19
+    ws = gpu_prover.calculate_witness(circ, [inp])
+    assert ws[0] == ol.witness_batch(cc.program_bytes(), circ.pack_inputs([inp]), cc.n_inputs, cc.n_wires)
+    proofs, pubs = gpu_prover.prove(Z, ws, [(7, 9)])
+    ref_p, ref_pub = ol.groth16_prove(zk, ws[0], 7, 9)
+    assert proofs[0] == ref_p and pubs[0] == ref_pub
+    sig = formats.publics_bytes_to_json(pubs[0])
+    assert sig[1] == golden["root_D"] and sig[2] == "128"
+    assert sj.groth16.verify(formats.export_verification_key(zk), sig, formats.proof_bytes_to_json(proofs[0]))
+    Z.close()
+    circ.close()

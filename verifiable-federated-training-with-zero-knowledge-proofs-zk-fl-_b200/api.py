@@ -119,9 +119,10 @@ class Prover:
     def load_zkey(self, data: bytes) -> Zkey:
         return Zkey(self, data)
 
-    def new_zkey(self, r1cs_bytes: bytes, seed: bytes) -> bytes:
+    def new_zkey(self, r1cs, seed: bytes) -> bytes:
+        """r1cs: `.r1cs` bytes or a CompiledCircuit"""
         from .zkey_setup import new_zkey
-        return new_zkey(self, r1cs_bytes, seed)
+        return new_zkey(self, r1cs, seed)
 
     # ---------------------------------------------------------------- witness
     def calculate_witness(self, circuit: Circuit, inputs, check: bool = True) -> list[bytes]:
@@ -168,6 +169,19 @@ class Prover:
                                                           _lib.as_ptr(self._pack_rs(rs, B)), B, proofs, pubs))
         psz = 32 * zkey.n_public
         return ([proofs.raw[256 * b:256 * (b + 1)] for b in range(B)], [pubs.raw[psz * b:psz * (b + 1)] for b in range(B)])
+
+    def msm_partials(self, zkey: Zkey, wtns: list[bytes], part: int, nparts: int) -> bytes:
+        """the five MSM sums over this rank's point range (B x 384 bytes), see zkfl_groth16_msm_partials"""
+        B = len(wtns)
+        out = ctypes.create_string_buffer(384 * B)
+        self._check(self.lib.zkfl_groth16_msm_partials(self.ctx, zkey.handle, _lib.as_ptr(b"".join(wtns)), B, part, nparts, out))
+        return out.raw
+
+    def finalize(self, zkey: Zkey, partials: list[bytes], B: int, rs=None) -> list[bytes]:
+        proofs = ctypes.create_string_buffer(256 * B)
+        self._check(self.lib.zkfl_groth16_finalize(self.ctx, zkey.handle, _lib.as_ptr(b"".join(partials)), len(partials),
+                                                  _lib.as_ptr(self._pack_rs(rs, B)), B, proofs))
+        return [proofs.raw[256 * b:256 * (b + 1)] for b in range(B)]
 
     # ---------------------------------------------------------------- MSM / setup support
     def g1_msm(self, bases: bytes, scalars: bytes) -> bytes:

@@ -313,6 +313,9 @@ template <class F> ZK_HD Xyzz<F> xyzz_scalar_mul(const Xyzz<F>& p, const uint32_
   return r;
 }
 
+ZK_HD Fq to_mont_any(const Fq& x) { return x.to_mont(); }
+ZK_HD Fq2 to_mont_any(const Fq2& x) { Fq2 r; r.a = x.a.to_mont(); r.b = x.b.to_mont(); return r; }
+
 typedef Affine<Fq> G1Affine;
 typedef Affine<Fq2> G2Affine;
 typedef Xyzz<Fq> G1Xyzz;

@@ -533,6 +533,28 @@ ZK_GLOBAL void k_to_affine_canonical(const Xyzz<F>* __restrict__ in, size_t n, A
   a.y = a.y.from_mont();
   out[i] = a;
 }
+// affine canonical bytes -> XYZZ Montgomery, summing `nparts` partial results per output (multi-GPU split MSM:
+// every rank contributes one partial per MSM; the group law is not an NCCL reduction op, so "reduce" = gather + add)
+template <class F>
+ZK_GLOBAL void k_sum_partials(const Affine<F>* __restrict__ parts, uint32_t nparts, size_t part_stride, size_t elem_stride,
+                              size_t n, Xyzz<F>* __restrict__ out) {
+  size_t i = ZK_TID;
+  if (i >= n) return;
+  Xyzz<F> acc = Xyzz<F>::infinity();
+  for (uint32_t p = 0; p < nparts; p++) {
+    Affine<F> a = parts[p * part_stride + i * elem_stride];
+    if (!a.is_inf()) { a.x = to_mont_any(a.x); a.y = to_mont_any(a.y); }
+    xyzz_madd(acc, a, false);
+  }
+  out[i] = acc;
+}
+// marks the points outside [lo, hi) (and those already skipped) so a rank only sorts its own range
+ZK_GLOBAL void k_range_mask(const uint8_t* __restrict__ base_skip, uint32_t m, uint32_t lo, uint32_t hi, uint8_t* __restrict__ out) {
+  size_t i = ZK_TID;
+  if (i >= m) return;
+  out[i] = (i < lo || i >= hi || (base_skip && base_skip[i])) ? 1 : 0;
+}
+
 // integer-pipe microbenchmark: `iters` dependent Montgomery products per thread (roofline denominator)
 ZK_GLOBAL void k_bench_modmul(Fq* __restrict__ data, size_t n, uint32_t iters) {
   size_t i = ZK_TID;

@@ -1,6 +1,7 @@
 // libzkfl.so host side: artefact parsing (.zkey / .r1cs / .zkwp), HBM residency, kernel orchestration
 // on one CUDA stream per context, and the C ABI declared in include/zkfl.h.
 #include "kernels.cuh"
+#include "verify_host.h"
 
 #include <atomic>
 #include <cstdio>
@@ -90,7 +91,7 @@ struct zkfl_ctx {
   cudaStream_t side = nullptr;
   cudaEvent_t ev_acc[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}, ev_done = nullptr;
   DevBuf res_g1, res_g2, t_g1, t_g2, pis, var, proofs, pubs, bad;
-  DevBuf msm_sc, msm_out;
+  DevBuf msm_sc, msm_out, mask_w, mask_wb, mask_h, part_out, part_in;
   cudaEvent_t t0 = nullptr, t1 = nullptr;
 };
 
@@ -304,7 +305,11 @@ static int msm_run(zkfl_ctx* c, const Affine<F>* bases, const MsmShape& s, Xyzz<
 }
 
 // ------------------------------------------------------------------------------------ prove pipeline (witness in c->w)
-static int prove_from_device_witness(zkfl_ctx* c, const zkfl_zkey* z, const Fr* rs_dev, uint32_t B) {
+static int finalize_from_sums(zkfl_ctx* c, const zkfl_zkey* z, const Fr* rs_dev, uint32_t B);
+// part / nparts: this context handles the point range [part*m/nparts, (part+1)*m/nparts) of every MSM (nparts == 1: all).
+// finalize == false stops after the five MSM sums (res_g1 / res_g2).
+static int prove_from_device_witness(zkfl_ctx* c, const zkfl_zkey* z, const Fr* rs_dev, uint32_t B, uint32_t part = 0,
+                                     uint32_t nparts = 1, bool finalize = true) {
   const uint32_t n = z->domain, m = z->n_vars;
   Fr* w = c->w.as<Fr>();
   TRY(c->abc.reserve(3 * (size_t)n * B * sizeof(Fr)));
@@ -339,7 +344,17 @@ static int prove_from_device_witness(zkfl_ctx* c, const zkfl_zkey* z, const Fr* 
     for (int i = 0; i < 5; i++) CU(cudaEventCreate(&c->ev_acc[i]));
     CU(cudaEventCreate(&c->ev_done));
   }
-  { Stage st(c, "msm_sort_w"); TRY(msm_sort(c, w, nullptr, sw)); }
+  const uint8_t *skip_w = nullptr, *skip_wb = z->skipB.as<uint8_t>(), *skip_h = nullptr;
+  if (nparts > 1) {
+    TRY(c->mask_w.reserve(m)); TRY(c->mask_wb.reserve(m)); TRY(c->mask_h.reserve(n));
+    uint32_t lo = (uint32_t)((uint64_t)m * part / nparts), hi = (uint32_t)((uint64_t)m * (part + 1) / nparts);
+    uint32_t hlo = (uint32_t)((uint64_t)n * part / nparts), hhi = (uint32_t)((uint64_t)n * (part + 1) / nparts);
+    ZK_LAUNCH(k_range_mask, m, 256, c->stream, (const uint8_t*)nullptr, m, lo, hi, c->mask_w.as<uint8_t>());
+    ZK_LAUNCH(k_range_mask, m, 256, c->stream, z->skipB.as<uint8_t>(), m, lo, hi, c->mask_wb.as<uint8_t>());
+    ZK_LAUNCH(k_range_mask, n, 256, c->stream, (const uint8_t*)nullptr, n, hlo, hhi, c->mask_h.as<uint8_t>());
+    skip_w = c->mask_w.as<uint8_t>(); skip_wb = c->mask_wb.as<uint8_t>(); skip_h = c->mask_h.as<uint8_t>();
+  }
+  { Stage st(c, "msm_sort_w"); TRY(msm_sort(c, w, skip_w, sw)); }
   TRY(msm_accumulate<Fq>(c, z->pA.as<G1Affine>(), sw, 0, "msm_acc_g1"));
   CU(cudaEventRecord(c->ev_acc[0], c->stream));
   CU(cudaStreamWaitEvent(c->side, c->ev_acc[0], 0));
@@ -348,7 +363,7 @@ static int prove_from_device_witness(zkfl_ctx* c, const zkfl_zkey* z, const Fr* 
   CU(cudaEventRecord(c->ev_acc[1], c->stream));
   CU(cudaStreamWaitEvent(c->side, c->ev_acc[1], 0));
   TRY(msm_reduce<Fq>(c, sw, 1, r1 + 2 * (size_t)B, c->side, "msm_reduce_g1"));
-  { Stage st(c, "msm_sort_w"); TRY(msm_sort(c, w, z->skipB.as<uint8_t>(), sw)); }
+  { Stage st(c, "msm_sort_w"); TRY(msm_sort(c, w, skip_wb, sw)); }
   TRY(msm_accumulate<Fq>(c, z->pB1.as<G1Affine>(), sw, 2, "msm_acc_g1"));
   CU(cudaEventRecord(c->ev_acc[2], c->stream));
   CU(cudaStreamWaitEvent(c->side, c->ev_acc[2], 0));
@@ -357,13 +372,20 @@ static int prove_from_device_witness(zkfl_ctx* c, const zkfl_zkey* z, const Fr* 
   CU(cudaEventRecord(c->ev_acc[4], c->stream));
   CU(cudaStreamWaitEvent(c->side, c->ev_acc[4], 0));
   TRY(msm_reduce<Fq2>(c, sw, 4, r2, c->side, "msm_reduce_g2"));
-  { Stage st(c, "msm_sort_h"); TRY(msm_sort(c, c->hsc.as<Fr>(), nullptr, sh)); }
+  { Stage st(c, "msm_sort_h"); TRY(msm_sort(c, c->hsc.as<Fr>(), skip_h, sh)); }
   TRY(msm_accumulate<Fq>(c, z->pH.as<G1Affine>(), sh, 3, "msm_acc_g1"));
   CU(cudaEventRecord(c->ev_acc[3], c->stream));
   CU(cudaStreamWaitEvent(c->side, c->ev_acc[3], 0));
   TRY(msm_reduce<Fq>(c, sh, 3, r1 + 3 * (size_t)B, c->side, "msm_reduce_g1"));
   CU(cudaEventRecord(c->ev_done, c->side));
   CU(cudaStreamWaitEvent(c->stream, c->ev_done, 0));
+  if (!finalize) return 0;
+  return finalize_from_sums(c, z, rs_dev, B);
+}
+
+// blinding / assembly from the five MSM sums in res_g1 ([4][B]: A, B1, C, H) and res_g2 ([B]: B2)
+static int finalize_from_sums(zkfl_ctx* c, const zkfl_zkey* z, const Fr* rs_dev, uint32_t B) {
+  G1Xyzz* r1 = c->res_g1.as<G1Xyzz>();
   {
     Stage st(c, "finalize");
     TRY(c->t_g1.reserve(3 * (size_t)B * sizeof(G1Xyzz)));
@@ -832,6 +854,47 @@ int zkfl_full_prove_fetch(zkfl_ctx* c, int B, uint8_t* proofs_out) {
   return 0;
 }
 
+// ---- single large proof split over several GPUs: per-rank MSM partials, then gather + add + blind
+int zkfl_groth16_msm_partials(zkfl_ctx* c, const zkfl_zkey* z, const uint8_t* wtns, int B, uint32_t part, uint32_t nparts,
+                              uint8_t* partials_out) {
+  if (!c || !z || !wtns || !partials_out || B <= 0 || nparts == 0 || part >= nparts) return fail(ZKFL_ERR_ARG, "bad argument");
+  CU(cudaSetDevice(c->device));
+  size_t cnt = (size_t)z->n_vars * B;
+  TRY(c->aos.reserve(cnt * sizeof(Fr))); TRY(c->w.reserve(cnt * sizeof(Fr)));
+  CU(cudaMemcpyAsync(c->aos.p, wtns, cnt * sizeof(Fr), cudaMemcpyHostToDevice, c->stream));
+  ZK_LAUNCH(k_aos_to_soa, cnt, 256, c->stream, c->aos.as<Fr>(), c->w.as<Fr>(), z->n_vars, (uint32_t)B, 0u);
+  TRY(prove_from_device_witness(c, z, nullptr, (uint32_t)B, part, nparts, false));
+  // layout per proof b: A | B1 | C | H (64 B each, affine canonical) | B2 (128 B)  -> stored as [5 blocks][B]
+  TRY(c->part_out.reserve((size_t)B * 384));
+  uint8_t* o = c->part_out.as<uint8_t>();
+  ZK_LAUNCH(k_to_affine_canonical<Fq>, (size_t)4 * B, 64, c->stream, c->res_g1.as<G1Xyzz>(), (size_t)4 * B, (G1Affine*)o);
+  ZK_LAUNCH(k_to_affine_canonical<Fq2>, (size_t)B, 64, c->stream, c->res_g2.as<G2Xyzz>(), (size_t)B, (G2Affine*)(o + (size_t)B * 256));
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(partials_out, o, (size_t)B * 384, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+int zkfl_groth16_finalize(zkfl_ctx* c, const zkfl_zkey* z, const uint8_t* partials, uint32_t nparts, const uint8_t* rs, int B,
+                          uint8_t* proofs_out) {
+  if (!c || !z || !partials || !proofs_out || B <= 0 || nparts == 0) return fail(ZKFL_ERR_ARG, "bad argument");
+  CU(cudaSetDevice(c->device));
+  TRY(stage_rs(c, rs, B));
+  size_t per = (size_t)B * 384;
+  TRY(c->part_in.reserve(per * nparts));
+  TRY(c->res_g1.reserve(4 * (size_t)B * sizeof(G1Xyzz)));
+  TRY(c->res_g2.reserve((size_t)B * sizeof(G2Xyzz)));
+  CU(cudaMemcpyAsync(c->part_in.p, partials, per * nparts, cudaMemcpyHostToDevice, c->stream));
+  const uint8_t* in = c->part_in.as<uint8_t>();
+  ZK_LAUNCH(k_sum_partials<Fq>, (size_t)4 * B, 64, c->stream, (const G1Affine*)in, nparts, per / sizeof(G1Affine), (size_t)1, (size_t)4 * B,
+            c->res_g1.as<G1Xyzz>());
+  ZK_LAUNCH(k_sum_partials<Fq2>, (size_t)B, 64, c->stream, (const G2Affine*)(in + (size_t)B * 256), nparts, per / sizeof(G2Affine), (size_t)1,
+            (size_t)B, c->res_g2.as<G2Xyzz>());
+  TRY(finalize_from_sums(c, z, c->stage_rs.as<Fr>(), (uint32_t)B));
+  CU(cudaMemcpyAsync(proofs_out, c->proofs.p, (size_t)B * 256, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
 // ---- standalone MSM
 int zkfl_msm_bases_load(zkfl_ctx* c, const uint8_t* bases, size_t n, int group, void** handle) {
   if (!c || !bases || !handle || (group != 1 && group != 2) || n == 0 || n > 0x7FFFFFFFu) return fail(ZKFL_ERR_ARG, "bad argument");
@@ -909,6 +972,14 @@ int zkfl_g2_mul_generator(zkfl_ctx* c, const uint8_t* scalars, size_t n, uint8_t
   return gen_mul<Fq2>(c, g, scalars, n, out);
 }
 
+int zkfl_groth16_verify(const uint8_t* alpha1, const uint8_t* beta2, const uint8_t* gamma2, const uint8_t* delta2, const uint8_t* ic,
+                        const uint8_t* publics, uint32_t n_public, const uint8_t* proof, int* ok) {
+  if (!alpha1 || !beta2 || !gamma2 || !delta2 || !ic || (!publics && n_public) || !proof || !ok) return fail(ZKFL_ERR_ARG, "bad argument");
+  int r = zkv::groth16_verify(alpha1, beta2, gamma2, delta2, ic, publics, n_public, proof);
+  if (r < 0) return fail(ZKFL_ERR_FORMAT, "malformed verification input");
+  *ok = r;
+  return 0;
+}
 int zkfl_timer_begin(zkfl_ctx* c) {
   if (!c) return fail(ZKFL_ERR_ARG, "ctx is NULL");
   CU(cudaSetDevice(c->device));

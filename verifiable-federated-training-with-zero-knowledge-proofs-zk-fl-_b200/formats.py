@@ -107,3 +107,23 @@ def proof_json_to_bytes(j: dict) -> bytes:
 
 def publics_bytes_to_json(p: bytes) -> list:
     return [str(int.from_bytes(p[i:i + 32], "little")) for i in range(0, len(p), 32)]
+
+
+# ---------------------------------------------------------------- verification key <-> bytes
+def _g1_dec_to_bytes(p) -> bytes:
+    if p[2] == "0":
+        return bytes(64)
+    return int(p[0]).to_bytes(32, "little") + int(p[1]).to_bytes(32, "little")
+
+
+def _g2_dec_to_bytes(p) -> bytes:
+    if p[2][0] == "0" and p[2][1] == "0":
+        return bytes(128)
+    return b"".join(int(v).to_bytes(32, "little") for v in (p[0][0], p[0][1], p[1][0], p[1][1]))
+
+
+def vkey_json_to_bytes(vk: dict) -> dict:
+    """verification_key.json -> the byte fields zkfl_groth16_verify takes (affine canonical little-endian)."""
+    return {"alpha1": _g1_dec_to_bytes(vk["vk_alpha_1"]), "beta2": _g2_dec_to_bytes(vk["vk_beta_2"]),
+            "gamma2": _g2_dec_to_bytes(vk["vk_gamma_2"]), "delta2": _g2_dec_to_bytes(vk["vk_delta_2"]),
+            "ic": b"".join(_g1_dec_to_bytes(p) for p in vk["IC"]), "n_public": int(vk["nPublic"])}

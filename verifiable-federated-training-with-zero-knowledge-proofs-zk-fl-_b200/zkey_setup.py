@@ -89,9 +89,18 @@ def r1cs_info(data: bytes) -> dict:
             "nPubInputs": n_pub_in, "nOutputs": n_pub_out, "nLabels": n_labels}
 
 
-def new_zkey(prover, r1cs_bytes: bytes, seed: bytes) -> bytes:
-    """prover: zkfl_b200.api.Prover (its GPU does the scalar multiplications)."""
-    r = parse_r1cs(r1cs_bytes)
+def _terms_of(compiled) -> dict:
+    """the same dictionary parse_r1cs returns, straight from a CompiledCircuit (skips a 100s-of-MB round trip)"""
+    return {"n_wires": compiled.n_wires, "n_public": compiled.n_public, "n_constraints": compiled.n_constraints,
+            "A": zip(compiled.A.rows, compiled.A.wires, compiled.A.coefs),
+            "B": zip(compiled.B.rows, compiled.B.wires, compiled.B.coefs),
+            "C": zip(compiled.C.rows, compiled.C.wires, compiled.C.coefs)}
+
+
+def new_zkey(prover, r1cs, seed: bytes) -> bytes:
+    """prover: zkfl_b200.api.Prover (its GPU does the scalar multiplications). r1cs: `.r1cs` bytes or a CompiledCircuit."""
+    r = parse_r1cs(r1cs) if isinstance(r1cs, (bytes, bytearray)) else _terms_of(r1cs)
+    r = {k: (list(v) if k in "ABC" else v) for k, v in r.items()}
     m, l, nc = r["n_wires"], r["n_public"], r["n_constraints"]
     tau, alpha, beta, delta = toxic_from_seed(seed)
     lg = max((nc + l).bit_length(), 1)  # smallest 2^lg >= nc + l + 1
