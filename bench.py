@@ -42,6 +42,9 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="zkfl", choices=["zkfl", "reference"])
     ap.add_argument("--batch", type=int, default=int(os.environ.get("ZKFL_BENCH_BATCH", "256")))
+    ap.add_argument("--lanes", type=int, default=int(os.environ.get("ZKFL_BENCH_LANES", "2")),
+                    help="contexts (streams) per GPU; the batch of a step is split evenly over them and proved concurrently")
+    ap.add_argument("--no-msm", action="store_true", help="skip the standalone 2^20-point G1 MSM measurement")
     ap.add_argument("--distinct", type=int, default=16, help="distinct synthetic clients generated on the host (tiled to B)")
     return ap.parse_args()
 
@@ -98,6 +101,36 @@ def synth_inputs(circuit, batch: int, distinct: int, rank: int):
     ins = b"".join(packed[i % d] for i in range(batch))
     rs = b"".join(rnd.randrange(FR).to_bytes(32, "little") for _ in range(2 * batch))
     return ins, rs
+
+
+def bench_msm_2pow20(prover, torch, n: int = 1 << 20, reps: int = 5):
+    """BASELINE.json's second metric: one G1 MSM over 2^20 points (bases k_i*G made by the device generator kernel,
+    uniform 254-bit scalars, fixed seed). value: scalars resident; e2e: scalars copied from pinned host memory each run."""
+    import random
+    from zkfl_b200.formats import FR
+    rnd = random.Random(2020)
+    bases = prover.g1_mul_generator(b"".join(rnd.randrange(FR).to_bytes(32, "little") for _ in range(n)))
+    sc = b"".join(rnd.randrange(FR).to_bytes(32, "little") for _ in range(n))
+    pin = torch.empty(len(sc), dtype=torch.uint8).pin_memory()
+    pin.copy_(torch.frombuffer(bytearray(sc), dtype=torch.uint8))
+    out = torch.empty(64, dtype=torch.uint8).pin_memory()
+    h = prover.msm_load_bases(bases, 1)
+    for _ in range(3):
+        prover.msm_run(h, pin.data_ptr(), n, out.data_ptr())
+    first = bytes(out.numpy().tobytes())
+    prover.timer_begin()
+    for _ in range(reps):
+        prover.msm_run(h, None, n, None)
+    ms = prover.timer_end() / reps
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        prover.msm_run(h, pin.data_ptr(), n, out.data_ptr())
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / reps
+    assert bytes(out.numpy().tobytes()) == first
+    prover.msm_free_bases(h)
+    return {"metric": "g1_msm_points_per_s_2pow20", "value": n / (ms * 1e-3), "unit": "points/s", "ms": ms,
+            "e2e": {"value": n / (e2e_ms * 1e-3), "ms": e2e_ms, "h2d_bytes": len(sc), "d2h_bytes": 64}, "points": n,
+            "parity": "tests/test_gpu_parity.py::test_g1_msm_2pow20_against_oracle"}
 
 
 def cpu_arm(cc, zkey_bytes, circuit_pack, sample: int, nthreads: int):
@@ -164,7 +197,7 @@ def run_reference(args, rank, world):
         "config": {"workload": WORKLOAD, "sample_proofs_per_step": sample},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": ncores, "kind": "port",
                          "sample": f"{sample} proofs per step (witness + prove), one proof per thread, C++ oracle restating snarkjs "
-                                   f"(snarkjs itself cannot run: no Node.js on this image); witness {vals[-1][1]:.1f} ms, prove {vals[-1][2]:.0f} ms per proof-thread"},
+                                   f"(snarkjs itself cannot run: no Node.js on this image); amortised per proof: witness {vals[-1][1]:.1f} ms, prove {vals[-1][2]:.0f} ms"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -205,10 +238,16 @@ def main():
     barrier()
     if rank != 0:
         zk = make_zkey(cc, cache)
-    prover = Prover(local_rank)
-    circuit = prover.load_circuit(cc, check_constraints=False)
-    zkey = prover.load_zkey(zk)
+    lanes = max(1, min(args.lanes, B))
+    provers = [Prover(local_rank) for _ in range(lanes)]
+    prover = provers[0]
+    circuits = [p.load_circuit(cc, check_constraints=False) for p in provers]
+    zkeys = [p.load_zkey(zk) for p in provers]
+    circuit, zkey = circuits[0], zkeys[0]
     ins, rs = synth_inputs(circuit, B, args.distinct, rank)
+    # lane k proves proofs [lo_k, hi_k) of the step's batch
+    bounds = [(B * k // lanes, B * (k + 1) // lanes) for k in range(lanes)]
+    in_sz, l = 32 * circuit.n_inputs, zkey.n_public
 
     # pinned host buffers for the end-to-end arm
     pin_in = torch.empty(len(ins), dtype=torch.uint8).pin_memory()
@@ -216,15 +255,41 @@ def main():
     pin_rs = torch.empty(len(rs), dtype=torch.uint8).pin_memory()
     pin_rs.copy_(torch.frombuffer(bytearray(rs), dtype=torch.uint8))
     pin_proofs = torch.empty(256 * B, dtype=torch.uint8).pin_memory()
-    pin_pubs = torch.empty(32 * zkey.n_public * B, dtype=torch.uint8).pin_memory()
+    pin_pubs = torch.empty(32 * l * B, dtype=torch.uint8).pin_memory()
     l2_flush = torch.empty(192 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
+    def run_resident():
+        for k, p in enumerate(provers):
+            p.run_staged(circuits[k], zkeys[k], bounds[k][1] - bounds[k][0])
+
+    def fetch_all():
+        for k, p in enumerate(provers):
+            lo, hi = bounds[k]
+            p.fetch(hi - lo, pin_proofs.data_ptr() + 256 * lo)
+
+    def e2e_step():
+        def one(k):
+            lo, hi = bounds[k]
+            provers[k].full_prove_raw(circuits[k], zkeys[k], pin_in.data_ptr() + in_sz * lo, pin_rs.data_ptr() + 64 * lo, hi - lo,
+                                      pin_proofs.data_ptr() + 256 * lo, pin_pubs.data_ptr() + 32 * l * lo)
+        if lanes == 1:
+            one(0)
+            return
+        th = [threading.Thread(target=one, args=(k,)) for k in range(lanes)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+
     # ---- resident arm (value)
-    prover.stage(circuit, zkey, pin_in.data_ptr(), pin_rs.data_ptr(), B)
+    for k, p in enumerate(provers):
+        lo, hi = bounds[k]
+        p.stage(circuits[k], zkeys[k], pin_in.data_ptr() + in_sz * lo, pin_rs.data_ptr() + 64 * lo, hi - lo)
     for _ in range(W):
-        prover.run_staged(circuit, zkey, B)
-    prover.fetch(B, pin_proofs.data_ptr())
-    first = bytes(pin_proofs.numpy()[:256].tobytes())
+        run_resident()
+    fetch_all()
+    first_all = bytes(pin_proofs.numpy().tobytes())
+    first = first_all[:256]
     barrier()
     launches0 = prover.launch_count()
     with ClockSampler(local_rank) as clocks:
@@ -232,8 +297,12 @@ def main():
         for _ in range(K):
             l2_flush.zero_()
             torch.cuda.synchronize()
+            for p in provers[1:]:
+                p.fetch(1, None)              # drain the other lanes (synchronises their streams)
             prover.timer_begin()
-            prover.run_staged(circuit, zkey, B)
+            run_resident()
+            for p in provers[1:]:
+                prover.wait_other(p)          # lane 0's stream joins the others before the end timestamp
             step_ms.append(prover.timer_end())
     launches = prover.launch_count() - launches0
     barrier()
@@ -241,25 +310,29 @@ def main():
     if dist is not None:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
     total_ms = float(total_ms.item())
-    prover.fetch(B, pin_proofs.data_ptr())
-    assert bytes(pin_proofs.numpy()[:256].tobytes()) == first, "non-deterministic proof for fixed r, s"
+    fetch_all()
+    assert bytes(pin_proofs.numpy().tobytes()) == first_all, "non-deterministic proofs for fixed r, s"
 
     # ---- end-to-end arm (host buffers, H2D + D2H inside the timed region)
     for _ in range(min(W, 2)):
-        prover.full_prove_raw(circuit, zkey, pin_in.data_ptr(), pin_rs.data_ptr(), B, pin_proofs.data_ptr(), pin_pubs.data_ptr())
+        e2e_step()
     barrier()
     t0 = time.perf_counter()
     for _ in range(K):
-        prover.full_prove_raw(circuit, zkey, pin_in.data_ptr(), pin_rs.data_ptr(), B, pin_proofs.data_ptr(), pin_pubs.data_ptr())
+        e2e_step()
     e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_s = float(e2e_s.item())
-    assert bytes(pin_proofs.numpy()[:256].tobytes()) == first
+    assert bytes(pin_proofs.numpy().tobytes()) == first_all
 
     line = None
     if rank == 0:
         # ---- per-stage profile of one more step (CUDA events on the library's stream) + rooflines
+        # (a full batch on one context, so the stage times below are for B proofs without lane overlap)
+        prover.stage(circuit, zkey, pin_in.data_ptr(), pin_rs.data_ptr(), B)
+        prover.run_staged(circuit, zkey, B)
+        prover.fetch(1, None)
         prover.prof_enable(True)
         prover.run_staged(circuit, zkey, B)
         prof = prover.prof_read()
@@ -268,6 +341,7 @@ def main():
         g1_pts = B * (3 * m - l - 1 + n)
         acc_ms = prof["msm_acc_g1"]["ms"]
         imad_peak = prover.bench_imad(148 * 2048 * 4, 4096)
+        mac_peak = prover.bench_widemac(148 * 2048 * 4, 4096)
         modmul_rate = prover.bench_modmul(148 * 2048, 512)
         peaks = {}
         try:
@@ -292,11 +366,12 @@ def main():
         vk = groth16_ref.vkey_from_json(export_verification_key(zk))
         pubs0 = oracle_lib.ints(bytes(pin_pubs.numpy()[:32 * l].tobytes()))
         verified = groth16_ref.verify(vk, pubs0, groth16_ref.proof_from_bytes(first))
+        msm = bench_msm_2pow20(prover, torch) if not args.no_msm else None
         line = {
             "metric": METRIC, "value": world * B * K / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32x8 (254-bit modular integers)", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "batch_per_gpu": B, "n_vars": m, "domain": n, "n_public": l,
+            "config": {"workload": WORKLOAD, "batch_per_gpu": B, "lanes_per_gpu": lanes, "n_vars": m, "domain": n, "n_public": l,
                        "distinct_inputs": min(args.distinct, B), "l2": "flushed (192 MB write) between timed steps",
                        "sharding": "independent proofs, b -> rank, no collective", "proof_verified_by_oracle": bool(verified)},
             "e2e": {"value": world * B * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": len(ins) + len(rs),
@@ -304,16 +379,19 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks.summary(),
             "roofline": {"bound": "imad", "kernel": "k_msm_accumulate<Fq> (4 launches per step)", "achieved": achieved,
-                         "peak": imad_peak / 1e9, "unit": "GMAC/s", "frac": achieved / (imad_peak / 1e9), "traffic": None,
+                         "peak": mac_peak / 1e9, "unit": "GMAC/s", "frac": achieved / (mac_peak / 1e9), "traffic": None,
                          "share_of_step": acc_ms / prof_total,
-                         "note": "algorithmic MAC = G1 points x 16 windows x 1360 (SURVEY 8d normalisation); peak = live 32-bit IMAD-chain "
-                                 "microbenchmark (zkfl_bench_imad); measured Montgomery products/s = %.3e" % modmul_rate},
+                         "peak_imad32_gops": imad_peak / 1e9, "modmul_per_s": modmul_rate,
+                         "note": "MAC = 32x32->64 multiply-accumulate; algorithmic MAC = G1 points x 16 windows x 1360 (SURVEY 8d "
+                                 "normalisation); peak = live microbenchmark of fused wide MACs (zkfl_bench_widemac, IMAD.WIDE.U32.X); "
+                                 "peak_imad32_gops = live 32-bit IMAD rate for comparison"},
             "roofline_hbm": {"bound": "hbm", "kernel": "ntt stage (3 iNTT + coset + 3 NTT + join)", "achieved": ntt_bytes / (ntt_ms * 1e-3) / 1e9,
                              "peak": hbm_peak, "unit": "GB/s", "frac": ntt_bytes / (ntt_ms * 1e-3) / 1e9 / hbm_peak,
                              "traffic": None, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
             "stages_ms": {k: round(v["ms"], 3) for k, v in prof.items()},
+            "msm_g1_2pow20": msm,
             "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": ncores, "kind": "port",
-                             "sample": f"{sample} proofs (witness {cpu_w_ms:.1f} ms + prove {cpu_p_ms:.0f} ms per proof-thread), one proof per thread; "
+                             "sample": f"{sample} proofs, one proof per thread (amortised per proof: witness {cpu_w_ms:.1f} ms + prove {cpu_p_ms:.0f} ms); "
                                        "C++ oracle restating snarkjs (snarkjs cannot run: no Node.js on this image)"},
         }
     barrier()

@@ -130,6 +130,8 @@ uint64_t zkfl_launch_count(void);
  * table "stage ms launches\n..." into buf. */
 int zkfl_prof_enable(zkfl_ctx* ctx, int on);
 int zkfl_prof_read(zkfl_ctx* ctx, char* buf, size_t cap);
+/* two contexts on the same device (e.g. two half-batches in flight): make ctx's stream wait for other's queued work */
+int zkfl_ctx_wait_other(zkfl_ctx* ctx, zkfl_ctx* other);
 /* device timer on the context's stream: begin() synchronises and records, end() records, waits, returns ms */
 int zkfl_timer_begin(zkfl_ctx* ctx);
 int zkfl_timer_end(zkfl_ctx* ctx, float* ms_out);
@@ -138,6 +140,8 @@ int zkfl_timer_end(zkfl_ctx* ctx, float* ms_out);
  *   imad:   n threads x iters x 8 independent 32-bit multiply-adds */
 int zkfl_bench_modmul(zkfl_ctx* ctx, size_t n_threads, uint32_t iters, float* ms_out);
 int zkfl_bench_imad(zkfl_ctx* ctx, size_t n_threads, uint32_t iters, float* ms_out);
+/*   widemac: n threads x iters x 4 fused 32x32->64 multiply-accumulates (IMAD.WIDE.U32.X), the unit "MAC" of the rooflines */
+int zkfl_bench_widemac(zkfl_ctx* ctx, size_t n_threads, uint32_t iters, float* ms_out);
 
 #ifdef __cplusplus
 }

@@ -18,8 +18,8 @@ SYMBOLS = [
     "zkfl_groth16_prove_batch", "zkfl_groth16_full_prove_batch", "zkfl_full_prove_stage",
     "zkfl_full_prove_run", "zkfl_full_prove_fetch", "zkfl_g1_msm", "zkfl_g2_msm", "zkfl_msm_bases_load",
     "zkfl_msm_bases_free", "zkfl_msm_run", "zkfl_g1_mul_generator", "zkfl_g2_mul_generator",
-    "zkfl_launch_count", "zkfl_prof_enable", "zkfl_prof_read", "zkfl_bench_modmul", "zkfl_bench_imad",
-    "zkfl_timer_begin", "zkfl_timer_end", "zkfl_groth16_verify", "zkfl_groth16_msm_partials", "zkfl_groth16_finalize",
+    "zkfl_launch_count", "zkfl_prof_enable", "zkfl_prof_read", "zkfl_bench_modmul", "zkfl_bench_imad", "zkfl_bench_widemac",
+    "zkfl_timer_begin", "zkfl_timer_end", "zkfl_groth16_verify", "zkfl_groth16_msm_partials", "zkfl_groth16_finalize", "zkfl_ctx_wait_other",
 ]
 
 _libs = {}
@@ -72,9 +72,11 @@ def load(path: str | None = None):
         "zkfl_prof_enable": (i, [vp, i]), "zkfl_prof_read": (i, [vp, vp, sz]),
         "zkfl_bench_modmul": (i, [vp, sz, ctypes.c_uint32, ctypes.POINTER(ctypes.c_float)]),
         "zkfl_bench_imad": (i, [vp, sz, ctypes.c_uint32, ctypes.POINTER(ctypes.c_float)]),
+        "zkfl_bench_widemac": (i, [vp, sz, ctypes.c_uint32, ctypes.POINTER(ctypes.c_float)]),
         "zkfl_groth16_verify": (i, [vp, vp, vp, vp, vp, vp, ctypes.c_uint32, vp, ctypes.POINTER(ctypes.c_int)]),
         "zkfl_groth16_msm_partials": (i, [vp, vp, vp, i, ctypes.c_uint32, ctypes.c_uint32, vp]),
         "zkfl_groth16_finalize": (i, [vp, vp, vp, ctypes.c_uint32, vp, i, vp]),
+        "zkfl_ctx_wait_other": (i, [vp, vp]),
         "zkfl_timer_begin": (i, [vp]), "zkfl_timer_end": (i, [vp, ctypes.POINTER(ctypes.c_float)]),
     }
     for name, (res, args) in sig.items():

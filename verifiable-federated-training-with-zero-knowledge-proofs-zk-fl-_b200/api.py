@@ -221,6 +221,9 @@ class Prover:
             out[name] = {"ms": float(ms), "launches": int(launches), "calls": int(calls)}
         return out
 
+    def wait_other(self, other: "Prover"):
+        self._check(self.lib.zkfl_ctx_wait_other(self.ctx, other.ctx))
+
     def timer_begin(self):
         self._check(self.lib.zkfl_timer_begin(self.ctx))
 
@@ -234,6 +237,24 @@ class Prover:
         ms = ctypes.c_float()
         self._check(self.lib.zkfl_bench_imad(self.ctx, n_threads, iters, ctypes.byref(ms)))
         return n_threads * iters * 8 / (ms.value * 1e-3)
+
+    def bench_widemac(self, n_threads: int, iters: int) -> float:
+        """-> measured fused 32x32->64 multiply-accumulates per second"""
+        ms = ctypes.c_float()
+        self._check(self.lib.zkfl_bench_widemac(self.ctx, n_threads, iters, ctypes.byref(ms)))
+        return n_threads * iters * 4 / (ms.value * 1e-3)
+
+    def msm_load_bases(self, bases: bytes, group: int = 1):
+        h = ctypes.c_void_p()
+        self._check(self.lib.zkfl_msm_bases_load(self.ctx, _lib.as_ptr(bases), len(bases) // (64 if group == 1 else 128), group, ctypes.byref(h)))
+        return h
+
+    def msm_run(self, handle, scalars, n: int, out=None):
+        """scalars: host pointer/bytes (copied in) or None to reuse the scalars already staged in HBM; out None -> async"""
+        self._check(self.lib.zkfl_msm_run(self.ctx, handle, _lib.as_ptr(scalars), n, _lib.as_ptr(out)))
+
+    def msm_free_bases(self, handle):
+        self.lib.zkfl_msm_bases_free(handle)
 
     def bench_modmul(self, n_threads: int, iters: int) -> float:
         """-> measured Montgomery products per second"""

@@ -92,7 +92,7 @@ struct zkfl_ctx {
   cudaEvent_t ev_acc[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}, ev_done = nullptr;
   DevBuf res_g1, res_g2, t_g1, t_g2, pis, var, proofs, pubs, bad;
   DevBuf msm_sc, msm_out, mask_w, mask_wb, mask_h, part_out, part_in;
-  cudaEvent_t t0 = nullptr, t1 = nullptr;
+  cudaEvent_t t0 = nullptr, t1 = nullptr, ev_join = nullptr;
 };
 
 struct Stage {
@@ -507,6 +507,7 @@ void zkfl_ctx_free(zkfl_ctx* c) {
   cudaStreamSynchronize(c->stream);
   for (auto& r : c->pending) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
   if (c->t0) { cudaEventDestroy(c->t0); cudaEventDestroy(c->t1); }
+  if (c->ev_join) cudaEventDestroy(c->ev_join);
   if (c->side) {
     cudaStreamSynchronize(c->side);
     for (int i = 0; i < 5; i++) cudaEventDestroy(c->ev_acc[i]);
@@ -980,6 +981,16 @@ int zkfl_groth16_verify(const uint8_t* alpha1, const uint8_t* beta2, const uint8
   *ok = r;
   return 0;
 }
+// makes `c`'s stream wait for everything queued so far on `other`'s stream (two contexts on one GPU working on
+// half-batches concurrently: join before the end-of-step timestamp)
+int zkfl_ctx_wait_other(zkfl_ctx* c, zkfl_ctx* other) {
+  if (!c || !other || c->device != other->device) return fail(ZKFL_ERR_ARG, "bad argument");
+  CU(cudaSetDevice(c->device));
+  if (!other->ev_join) CU(cudaEventCreate(&other->ev_join));
+  CU(cudaEventRecord(other->ev_join, other->stream));
+  CU(cudaStreamWaitEvent(c->stream, other->ev_join, 0));
+  return 0;
+}
 int zkfl_timer_begin(zkfl_ctx* c) {
   if (!c) return fail(ZKFL_ERR_ARG, "ctx is NULL");
   CU(cudaSetDevice(c->device));
@@ -995,7 +1006,10 @@ int zkfl_timer_end(zkfl_ctx* c, float* ms_out) {
   CU(cudaEventElapsedTime(ms_out, c->t0, c->t1));
   return 0;
 }
-int zkfl_bench_imad(zkfl_ctx* c, size_t n_threads, uint32_t iters, float* ms_out) {
+static int bench_u32_kernel(zkfl_ctx* c, int which, size_t n_threads, uint32_t iters, float* ms_out);
+int zkfl_bench_imad(zkfl_ctx* c, size_t n_threads, uint32_t iters, float* ms_out) { return bench_u32_kernel(c, 0, n_threads, iters, ms_out); }
+int zkfl_bench_widemac(zkfl_ctx* c, size_t n_threads, uint32_t iters, float* ms_out) { return bench_u32_kernel(c, 1, n_threads, iters, ms_out); }
+static int bench_u32_kernel(zkfl_ctx* c, int which, size_t n_threads, uint32_t iters, float* ms_out) {
   if (!c || !ms_out || n_threads == 0) return fail(ZKFL_ERR_ARG, "bad argument");
   CU(cudaSetDevice(c->device));
   DevBuf d;
@@ -1003,9 +1017,11 @@ int zkfl_bench_imad(zkfl_ctx* c, size_t n_threads, uint32_t iters, float* ms_out
   CU(cudaMemsetAsync(d.p, 0x5a, n_threads * 4, c->stream));
   cudaEvent_t e0, e1;
   CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
-  ZK_LAUNCH(k_bench_imad, n_threads, 256, c->stream, d.as<uint32_t>(), n_threads, 16u);
+  if (which == 0) ZK_LAUNCH(k_bench_imad, n_threads, 256, c->stream, d.as<uint32_t>(), n_threads, 16u);
+  else ZK_LAUNCH(k_bench_widemac, n_threads, 256, c->stream, d.as<uint32_t>(), n_threads, 16u);
   CU(cudaEventRecord(e0, c->stream));
-  ZK_LAUNCH(k_bench_imad, n_threads, 256, c->stream, d.as<uint32_t>(), n_threads, iters);
+  if (which == 0) ZK_LAUNCH(k_bench_imad, n_threads, 256, c->stream, d.as<uint32_t>(), n_threads, iters);
+  else ZK_LAUNCH(k_bench_widemac, n_threads, 256, c->stream, d.as<uint32_t>(), n_threads, iters);
   CU(cudaEventRecord(e1, c->stream));
   CU(cudaEventSynchronize(e1));
   CU(cudaEventElapsedTime(ms_out, e0, e1));
