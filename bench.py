@@ -35,6 +35,10 @@ MAC_PER_G1_POINT = 16 * 1360
 MAC_PER_G2_POINT = 16 * 4080
 
 
+def log(msg):
+    print(f"[bench rank {os.environ.get('RANK', '0')}] {msg}", file=sys.stderr, flush=True)
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -281,6 +285,7 @@ def main():
         for t in th:
             t.join()
 
+    log(f"setup done: B={B} lanes={lanes} world={world}")
     # ---- resident arm (value)
     for k, p in enumerate(provers):
         lo, hi = bounds[k]
@@ -313,6 +318,7 @@ def main():
     fetch_all()
     assert bytes(pin_proofs.numpy().tobytes()) == first_all, "non-deterministic proofs for fixed r, s"
 
+    log(f"resident arm done: {total_ms / K:.1f} ms/step")
     # ---- end-to-end arm (host buffers, H2D + D2H inside the timed region)
     for _ in range(min(W, 2)):
         e2e_step()
@@ -326,6 +332,7 @@ def main():
     e2e_s = float(e2e_s.item())
     assert bytes(pin_proofs.numpy().tobytes()) == first_all
 
+    log(f"e2e arm done: {e2e_s * 1e3 / K:.1f} ms/step")
     line = None
     if rank == 0:
         # ---- per-stage profile of one more step (CUDA events on the library's stream) + rooflines
@@ -394,11 +401,12 @@ def main():
                              "sample": f"{sample} proofs, one proof per thread (amortised per proof: witness {cpu_w_ms:.1f} ms + prove {cpu_p_ms:.0f} ms); "
                                        "C++ oracle restating snarkjs (snarkjs cannot run: no Node.js on this image)"},
         }
+    if line is not None:
+        print(json.dumps(line), flush=True)
+        log("line printed")
     barrier()
     if dist is not None:
         dist.destroy_process_group()
-    if line is not None:
-        print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":
