@@ -45,8 +45,8 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="zkfl", choices=["zkfl", "reference"])
-    ap.add_argument("--batch", type=int, default=int(os.environ.get("ZKFL_BENCH_BATCH", "256")))
-    ap.add_argument("--lanes", type=int, default=int(os.environ.get("ZKFL_BENCH_LANES", "2")),
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("ZKFL_BENCH_BATCH", "1024")))
+    ap.add_argument("--lanes", type=int, default=int(os.environ.get("ZKFL_BENCH_LANES", "4")),
                     help="contexts (streams) per GPU; the batch of a step is split evenly over them and proved concurrently")
     ap.add_argument("--no-msm", action="store_true", help="skip the standalone 2^20-point G1 MSM measurement")
     ap.add_argument("--distinct", type=int, default=16, help="distinct synthetic clients generated on the host (tiled to B)")

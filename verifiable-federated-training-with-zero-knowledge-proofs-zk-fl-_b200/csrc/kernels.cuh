@@ -185,6 +185,62 @@ ZK_GLOBAL void k_ntt_stage(Fr* __restrict__ data, const Fr* __restrict__ tw, uin
     base[i1 * B + b] = u - v;
   }
 }
+// K fused radix-2 stages in registers (K = 1, 2, 3): a thread owns the 2^K elements that form a closed butterfly
+// network for those stages, so a pass over HBM does K stages instead of one (14 stages = 5 passes at n = 2^14).
+// dif = 1: stages with half = h, h/2, ... (h = `half`, the first stage's half); elements k + r*(h >> (K-1)).
+// dif = 0: stages with half = h, 2h, ...; elements k + r*h inside a block of size h << K.
+// scale (may be null, dif only): multiply element at position p by scale[p] on the way out (fuses k_scale_rows into
+// the last inverse pass).
+template <int K>
+ZK_GLOBAL void k_ntt_radix(Fr* __restrict__ data, const Fr* __restrict__ tw, const Fr* __restrict__ scale, uint32_t n, uint32_t B,
+                           uint32_t n_poly, uint32_t half, int dif) {
+  constexpr uint32_t R = 1u << K;
+  size_t tid = ZK_TID;
+  size_t per_poly = (size_t)(n >> K) * B;
+  if (tid >= per_poly * n_poly) return;
+  uint32_t poly = (uint32_t)(tid / per_poly);
+  size_t rem = tid % per_poly;
+  uint32_t g = (uint32_t)(rem / B), b = (uint32_t)(rem % B);
+  Fr* base = data + (size_t)poly * n * B;
+  Fr x[R];
+  if (dif) {
+    const uint32_t step = half >> (K - 1);          // distance between the thread's elements
+    const uint32_t blk = g / step, k = g % step;     // block of size 2*half
+    const size_t i0 = (size_t)blk * 2 * half + k;
+    ZK_UNROLL for (uint32_t r = 0; r < R; r++) x[r] = base[(i0 + (size_t)r * step) * B + b];
+    ZK_UNROLL for (int s = 0; s < K; s++) {
+      const uint32_t h = half >> s;                   // this stage's half, in elements
+      const uint32_t hr = R >> (s + 1);               // ... in units of `step`
+      ZK_UNROLL for (uint32_t r = 0; r < R; r++) {
+        if ((r / hr) & 1) continue;                   // r is the upper element of its pair
+        const uint32_t e = k + (r % hr) * step;       // exponent inside the stage's block of size 2h
+        Fr u = x[r], v = x[r + hr];
+        x[r] = u + v;
+        x[r + hr] = (u - v) * tw[(size_t)e * (n / 2 / h)];
+      }
+    }
+    ZK_UNROLL for (uint32_t r = 0; r < R; r++) {
+      size_t p = i0 + (size_t)r * step;
+      base[p * B + b] = scale ? x[r] * scale[p] : x[r];
+    }
+  } else {
+    const uint32_t blk = g / half, k = g % half;     // block of size half << K
+    const size_t i0 = (size_t)blk * ((size_t)half << K) + k;
+    ZK_UNROLL for (uint32_t r = 0; r < R; r++) x[r] = base[(i0 + (size_t)r * half) * B + b];
+    ZK_UNROLL for (int s = 0; s < K; s++) {
+      const uint32_t h = half << s;
+      const uint32_t hr = 1u << s;                    // pair distance in units of `half`
+      ZK_UNROLL for (uint32_t r = 0; r < R; r++) {
+        if ((r / hr) & 1) continue;
+        const uint32_t e = k + (r % hr) * half;
+        Fr u = x[r], v = x[r + hr] * tw[(size_t)e * (n / 2 / h)];
+        x[r] = u + v;
+        x[r + hr] = u - v;
+      }
+    }
+    ZK_UNROLL for (uint32_t r = 0; r < R; r++) base[(i0 + (size_t)r * half) * B + b] = x[r];
+  }
+}
 // after the DIF inverse transform position p holds coefficient bitrev(p): multiply by
 // tab[p] = n^-1 * inc^bitrev(p)  (inc = w_{2n}: the odd-coset shift snarkjs applies with batchApplyKey)
 ZK_GLOBAL void k_scale_rows(Fr* __restrict__ data, const Fr* __restrict__ tab, uint32_t n, uint32_t B, uint32_t n_poly) {

@@ -323,11 +323,25 @@ static int prove_from_device_witness(zkfl_ctx* c, const zkfl_zkey* z, const Fr* 
   }
   {
     Stage st(c, "ntt");
-    for (uint32_t h = n / 2; h >= 1; h >>= 1)
-      ZK_LAUNCH(k_ntt_stage, (size_t)3 * (n / 2) * B, 256, c->stream, abc, z->tw_inv.as<Fr>(), n, B, 3u, h, 1);
-    ZK_LAUNCH(k_scale_rows, (size_t)3 * n * B, 256, c->stream, abc, z->coset.as<Fr>(), n, B, 3u);
-    for (uint32_t h = 1; h <= n / 2; h <<= 1)
-      ZK_LAUNCH(k_ntt_stage, (size_t)3 * (n / 2) * B, 256, c->stream, abc, z->tw_fwd.as<Fr>(), n, B, 3u, h, 0);
+    // inverse transform (DIF, natural -> bit-reversed), 3 stages per pass; the last pass also applies n^-1 * w_2n^bitrev(p)
+    auto radix = [&](int K, uint32_t half, int dif, const Fr* twd, const Fr* scale) {
+      size_t threads = (size_t)3 * (n >> K) * B;
+      if (K == 3) ZK_LAUNCH(k_ntt_radix<3>, threads, 128, c->stream, abc, twd, scale, n, B, 3u, half, dif);
+      else if (K == 2) ZK_LAUNCH(k_ntt_radix<2>, threads, 128, c->stream, abc, twd, scale, n, B, 3u, half, dif);
+      else ZK_LAUNCH(k_ntt_radix<1>, threads, 256, c->stream, abc, twd, scale, n, B, 3u, half, dif);
+    };
+    const int lg = (int)z->log_n;
+    for (int done = 0; done < lg;) {   // DIF: stage t has half = n >> (t + 1)
+      int K = lg - done >= 3 ? 3 : lg - done;
+      bool last = done + K == lg;
+      radix(K, n >> (done + 1), 1, z->tw_inv.as<Fr>(), last ? z->coset.as<Fr>() : nullptr);
+      done += K;
+    }
+    for (int done = 0; done < lg;) {   // DIT: stage t has half = 1 << t
+      int K = lg - done >= 3 ? 3 : lg - done;
+      radix(K, 1u << done, 0, z->tw_fwd.as<Fr>(), nullptr);
+      done += K;
+    }
     ZK_LAUNCH(k_join_abc, (size_t)n * B, 256, c->stream, abc, c->hsc.as<Fr>(), n, B);
   }
   G1Xyzz* r1 = c->res_g1.as<G1Xyzz>();
