@@ -289,11 +289,13 @@ ZK_HD int32_t signed_digit(const uint32_t* k, uint32_t j, uint32_t c, uint32_t& 
 // (bases that are the point at infinity: wires absent from the B matrix, public wires of the C query).
 ZK_GLOBAL void k_msm_count(const Fr* __restrict__ scalars, const uint8_t* __restrict__ skip, MsmShape s,
                            uint32_t* __restrict__ counts) {
+  // proof-major thread order: a CTA works inside ONE proof's counters / list region (about 1 MB), which stays in L2;
+  // the scalar loads become 32-byte strided sectors (each scalar is exactly one sector, so no DRAM traffic is wasted).
   size_t tid = ZK_TID;
   if (tid >= (size_t)s.m * s.B) return;
-  uint32_t i = (uint32_t)(tid / s.B), b = (uint32_t)(tid % s.B);
+  uint32_t b = (uint32_t)(tid / s.m), i = (uint32_t)(tid % s.m);
   if (skip && skip[i]) return;
-  Fr k = scalars[tid];
+  Fr k = scalars[(size_t)i * s.B + b];
   if (k.is_zero()) return;
   uint32_t carry = 0;
   for (uint32_t j = 0; j < s.W; j++) {
@@ -340,9 +342,9 @@ ZK_GLOBAL void k_msm_scatter(const Fr* __restrict__ scalars, const uint8_t* __re
                              uint32_t* __restrict__ cursors, uint32_t* __restrict__ sorted, uint16_t* __restrict__ skey) {
   size_t tid = ZK_TID;
   if (tid >= (size_t)s.m * s.B) return;
-  uint32_t i = (uint32_t)(tid / s.B), b = (uint32_t)(tid % s.B);
+  uint32_t b = (uint32_t)(tid / s.m), i = (uint32_t)(tid % s.m);   // proof-major, see k_msm_count
   if (skip && skip[i]) return;
-  Fr k = scalars[tid];
+  Fr k = scalars[(size_t)i * s.B + b];
   if (k.is_zero()) return;
   uint32_t carry = 0;
   for (uint32_t j = 0; j < s.W; j++) {
