@@ -177,6 +177,7 @@ struct alignas(16) Fp {
 #else
   static ZK_HD Fp mul_hot(const Fp& a, const Fp& b) { return mul_call(a, b); }
 #endif
+  static ZK_HD Fp sqr_hot(const Fp& a) { return mul_hot(a, a); }
   ZK_HD Fp sqr() const { return *this * *this; }
   ZK_HD Fp to_mont() const { return *this * r2(); }
   ZK_HD Fp from_mont() const { Fp o = zero(); o.v[0] = 1; return *this * o; }
@@ -211,6 +212,10 @@ struct alignas(16) Fq2 {
     Fq2 r; r.a = aa - bb; r.b = s - aa - bb; return r;
   }
   ZK_HD Fq2 sqr() const { Fq t = a * b; Fq2 r; r.a = (a + b) * (a - b); r.b = t.dbl(); return r; }
+  static ZK_HD Fq2 sqr_hot(const Fq2& x) {   // (a + b)(a - b) + 2ab u: two products instead of three
+    Fq t = Fq::mul_hot(x.a, x.b);
+    Fq2 r; r.a = Fq::mul_hot(x.a + x.b, x.a - x.b); r.b = t.dbl(); return r;
+  }
   static ZK_HD Fq2 mul_hot(const Fq2& x, const Fq2& y) {
     Fq aa = Fq::mul_hot(x.a, y.a), bb = Fq::mul_hot(x.b, y.b), s = Fq::mul_hot(x.a + x.b, y.a + y.b);
     Fq2 r; r.a = aa - bb; r.b = s - aa - bb; return r;
@@ -268,8 +273,8 @@ template <class F> ZK_HD void xyzz_madd(Xyzz<F>& acc, const Affine<F>& q0, bool 
     if (Rr.is_zero()) acc = xyzz_dbl_affine(q); else acc = Xyzz<F>::infinity();
     return;
   }
-  F PP = F::mul_hot(Pp, Pp), PPP = F::mul_hot(Pp, PP), Qq = F::mul_hot(acc.X, PP);
-  F X3 = F::mul_hot(Rr, Rr) - PPP - Qq.dbl();
+  F PP = F::sqr_hot(Pp), PPP = F::mul_hot(Pp, PP), Qq = F::mul_hot(acc.X, PP);
+  F X3 = F::sqr_hot(Rr) - PPP - Qq.dbl();
   acc.Y = F::mul_hot(Rr, Qq - X3) - F::mul_hot(acc.Y, PPP);
   acc.X = X3;
   acc.ZZ = F::mul_hot(acc.ZZ, PP);
