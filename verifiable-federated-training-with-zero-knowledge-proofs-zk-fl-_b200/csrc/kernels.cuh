@@ -420,42 +420,48 @@ ZK_GLOBAL void k_msm_fixup(const uint32_t* __restrict__ offsets, const uint32_t*
   for (uint32_t ch = c0 + 1; ch <= c1; ch++) xyzz_add(acc, h[ch]);
   buckets[tid] = acc;
 }
-// pass 5a: running sums over chunks of L buckets: R = sum B_k, T = sum (k - k0) * B_k  (k0 = chunk*L, k from 1)
+// pass 5: bucket reduction S = sum_k (k+1) * X[k] over the nb buckets of a row, as a three-level tree so that the
+// serial depth is ~ 2*L1 + 2*L2 + 5*N2 additions instead of 2*sqrt(nb) + 3*sqrt(nb).
+// Level kernel: chunk t of L consecutive elements -> R_t = sum X, T_t = sum j * X[t*L + j] (zero-based local weights).
+// With Z(X) = sum_k k * X[k]:  Z(X) = sum_t T_t + L * Z(R)  and  S = Z(X) + sum(X) = Z(X) + sum(R).
 template <class F>
-ZK_GLOBAL void k_msm_reduce_chunks(const Xyzz<F>* __restrict__ buckets, MsmShape s, uint32_t L, Xyzz<F>* __restrict__ Rs,
-                                   Xyzz<F>* __restrict__ Ts) {
+ZK_GLOBAL void k_reduce_level(const Xyzz<F>* __restrict__ in, size_t rows, uint32_t N, uint32_t L, Xyzz<F>* __restrict__ R,
+                              Xyzz<F>* __restrict__ T) {
   size_t tid = ZK_TID;
-  uint32_t nchunk = s.nb / L;
-  if (tid >= (size_t)s.B * s.R * nchunk) return;
+  uint32_t nchunk = N / L;
+  if (tid >= rows * nchunk) return;
   size_t row = tid / nchunk;
   uint32_t ch = (uint32_t)(tid % nchunk);
-  const Xyzz<F>* bk = buckets + row * s.nb + (size_t)ch * L;
+  const Xyzz<F>* x = in + row * N + (size_t)ch * L;
   Xyzz<F> run = Xyzz<F>::infinity(), acc = Xyzz<F>::infinity();
-  for (int k = (int)L - 1; k >= 0; k--) {
-    xyzz_add(run, bk[k]);
+  for (int j = (int)L - 1; j >= 1; j--) {
+    xyzz_add(run, x[j]);
     xyzz_add(acc, run);
   }
-  Rs[tid] = run;
-  Ts[tid] = acc;
+  xyzz_add(run, x[0]);
+  R[tid] = run;
+  if (T) T[tid] = acc;
 }
-// pass 5b: window sum S = sum_t T_t + L * sum_t t * R_t, one thread per row
+// final: per row, from the level-2 outputs (N2 entries each): R2/T2 = level 2 of R1, RT = chunk sums of T1.
+//   Z(R1) = sum(T2) + L2 * Z(R2);  Z(X) = sum(T1) + L1 * Z(R1) = sum(RT) + L1 * Z(R1);  S = Z(X) + sum(R2)
 template <class F>
-ZK_GLOBAL void k_msm_reduce_rows(const Xyzz<F>* __restrict__ Rs, const Xyzz<F>* __restrict__ Ts, MsmShape s, uint32_t L,
-                                 Xyzz<F>* __restrict__ win) {
+ZK_GLOBAL void k_reduce_final(const Xyzz<F>* __restrict__ R2, const Xyzz<F>* __restrict__ T2, const Xyzz<F>* __restrict__ RT,
+                              size_t rows, uint32_t N2, uint32_t L1, uint32_t L2, Xyzz<F>* __restrict__ out) {
   size_t row = ZK_TID;
-  if (row >= (size_t)s.B * s.R) return;
-  uint32_t nchunk = s.nb / L;
-  const Xyzz<F>* R = Rs + row * nchunk;
-  const Xyzz<F>* T = Ts + row * nchunk;
-  Xyzz<F> run = Xyzz<F>::infinity(), acc = Xyzz<F>::infinity(), tsum = Xyzz<F>::infinity();
-  for (int t = (int)nchunk - 1; t >= 1; t--) {
-    xyzz_add(run, R[t]);
-    xyzz_add(acc, run);
-  }
-  for (uint32_t l = L; l > 1; l >>= 1) acc = xyzz_dbl(acc);
-  for (uint32_t t = 0; t < nchunk; t++) xyzz_add(tsum, T[t]);
-  xyzz_add(acc, tsum);
-  win[row] = acc;
+  if (row >= rows) return;
+  const Xyzz<F>* r2 = R2 + row * N2;
+  const Xyzz<F>* t2 = T2 + row * N2;
+  const Xyzz<F>* rt = RT + row * N2;
+  Xyzz<F> run = Xyzz<F>::infinity(), z = Xyzz<F>::infinity(), sum_r = Xyzz<F>::infinity(), sum_t2 = Xyzz<F>::infinity(),
+          sum_t1 = Xyzz<F>::infinity();
+  for (int t = (int)N2 - 1; t >= 1; t--) { xyzz_add(run, r2[t]); xyzz_add(z, run); }   // Z(R2)
+  for (uint32_t t = 0; t < N2; t++) { xyzz_add(sum_r, r2[t]); xyzz_add(sum_t2, t2[t]); xyzz_add(sum_t1, rt[t]); }
+  for (uint32_t l = L2; l > 1; l >>= 1) z = xyzz_dbl(z);
+  xyzz_add(z, sum_t2);                                                                    // Z(R1)
+  for (uint32_t l = L1; l > 1; l >>= 1) z = xyzz_dbl(z);
+  xyzz_add(z, sum_t1);                                                                    // Z(X)
+  xyzz_add(z, sum_r);                                                                     // + sum(X)
+  out[row] = z;
 }
 // pass 6: Horner over the windows, one thread per proof: out[b] = sum_j 2^(c*j) * win[b][j]
 template <class F>

@@ -87,7 +87,7 @@ struct zkfl_ctx {
   DevBuf counts, offsets, cursors, chunk_sums, sorted, skey, head, tail;
   // five MSMs per proof batch (A, C, B1, H on G1; B2 on G2): own bucket / reduction buffers each, so the
   // latency-bound bucket reduction of one MSM runs on `side` while the next MSM accumulates on `stream`
-  DevBuf buckets[5], Rs[5], Ts[5], win[5];
+  DevBuf buckets[5], Rs[5], Ts[5], lvl2[5], win[5];
   cudaStream_t side = nullptr;
   cudaEvent_t ev_acc[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}, ev_done = nullptr;
   DevBuf res_g1, res_g2, t_g1, t_g2, pis, var, proofs, pubs, bad;
@@ -230,13 +230,14 @@ static MsmShape msm_shape(uint32_t m, uint32_t B, bool shared, uint32_t force_c 
   s.cap = shared ? m * s.W : m;
   return s;
 }
-static uint32_t reduce_chunk(const MsmShape& s) {
-  uint32_t L = 1;
-  while (L * L < s.nb) L <<= 1;  // ~sqrt(nb)
-  if (L > s.nb) L = s.nb;
-  return L;
+// three-level reduction tree over nb = L1 * L2 * N2 buckets
+struct ReducePlan { uint32_t L1, L2, N1, N2; };
+static ReducePlan reduce_plan(const MsmShape& s) {
+  uint32_t lg = 0; while ((1u << lg) < s.nb) lg++;
+  uint32_t l1 = (lg + 2) / 3, l2 = (lg - l1 + 1) / 2;
+  ReducePlan p; p.L1 = 1u << l1; p.L2 = 1u << l2; p.N1 = s.nb >> l1; p.N2 = p.N1 >> l2;
+  return p;
 }
-
 static uint32_t accumulate_chunk() { uint32_t S = env_u32("ZKFL_MSM_CHUNK", 32); return S < 4 ? 4 : S; }
 
 static int msm_sort(zkfl_ctx* c, const Fr* scalars, const uint8_t* skip, const MsmShape& s) {
@@ -277,21 +278,28 @@ static int msm_accumulate(zkfl_ctx* c, const Affine<F>* bases, const MsmShape& s
 }
 static int msm_reserve_reduce(zkfl_ctx* c, const MsmShape& s, int slot, size_t elem) {
   size_t rows = (size_t)s.B * s.R;
-  uint32_t L = reduce_chunk(s), nchunk = s.nb / L;
-  TRY(c->Rs[slot].reserve(rows * nchunk * elem));
-  TRY(c->Ts[slot].reserve(rows * nchunk * elem));
+  ReducePlan p = reduce_plan(s);
+  TRY(c->Rs[slot].reserve(rows * p.N1 * elem));
+  TRY(c->Ts[slot].reserve(rows * p.N1 * elem));
+  TRY(c->lvl2[slot].reserve(3 * rows * p.N2 * elem));
   TRY(c->win[slot].reserve(rows * elem));
   return 0;
 }
-// bucket reduction sum_k k * B_k of one MSM on `stream` -> out[B]. Buffers must have been reserved (msm_reserve_reduce).
+// bucket reduction sum_k (k+1) * B_k of one MSM on `stream` -> out[B]. Buffers must have been reserved (msm_reserve_reduce).
 template <class F>
 static int msm_reduce(zkfl_ctx* c, const MsmShape& s, int slot, Xyzz<F>* out, cudaStream_t stream, const char* tag) {
   size_t rows = (size_t)s.B * s.R;
-  uint32_t L = reduce_chunk(s), nchunk = s.nb / L;
+  ReducePlan p = reduce_plan(s);
+  Xyzz<F>* R1 = c->Rs[slot].as<Xyzz<F>>();
+  Xyzz<F>* T1 = c->Ts[slot].as<Xyzz<F>>();
+  Xyzz<F>* R2 = c->lvl2[slot].as<Xyzz<F>>();
+  Xyzz<F>* T2 = R2 + rows * p.N2;
+  Xyzz<F>* RT = T2 + rows * p.N2;
   Stage st(c, tag, stream);
-  ZK_LAUNCH(k_msm_reduce_chunks<F>, rows * nchunk, 64, stream, c->buckets[slot].as<Xyzz<F>>(), s, L, c->Rs[slot].as<Xyzz<F>>(),
-            c->Ts[slot].as<Xyzz<F>>());
-  ZK_LAUNCH(k_msm_reduce_rows<F>, rows, 32, stream, c->Rs[slot].as<Xyzz<F>>(), c->Ts[slot].as<Xyzz<F>>(), s, L,
+  ZK_LAUNCH(k_reduce_level<F>, rows * p.N1, 64, stream, c->buckets[slot].as<Xyzz<F>>(), rows, s.nb, p.L1, R1, T1);
+  ZK_LAUNCH(k_reduce_level<F>, rows * p.N2, 64, stream, (const Xyzz<F>*)R1, rows, p.N1, p.L2, R2, T2);
+  ZK_LAUNCH(k_reduce_level<F>, rows * p.N2, 64, stream, (const Xyzz<F>*)T1, rows, p.N1, p.L2, RT, (Xyzz<F>*)nullptr);
+  ZK_LAUNCH(k_reduce_final<F>, rows, 32, stream, (const Xyzz<F>*)R2, (const Xyzz<F>*)T2, (const Xyzz<F>*)RT, rows, p.N2, p.L1, p.L2,
             c->win[slot].as<Xyzz<F>>());
   ZK_LAUNCH(k_msm_combine<F>, s.B, 32, stream, c->win[slot].as<Xyzz<F>>(), s, out);
   CU(cudaGetLastError());
