@@ -33,6 +33,7 @@ WORKLOAD = "sgd_verified TrainingStepVerified(8,4,3,1000): witness+prove, batch 
 # SURVEY 8(d) normalisation: 136 MAC per 8-limb Montgomery product, 1360 MAC per G1 mixed add, 16 windows (c = 16)
 MAC_PER_G1_POINT = 16 * 1360
 MAC_PER_G2_POINT = 16 * 4080
+PUBLISHED_PROOFS_PER_S = 0.147   # BASELINE.md section 1 (derived from Report.pdf Table 3, i7-10750H, snarkjs CLI)
 
 
 def log(msg):
@@ -376,7 +377,10 @@ def main():
         msm = bench_msm_2pow20(prover, torch) if not args.no_msm else None
         line = {
             "metric": METRIC, "value": world * B * K / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K,
-            "warmup": W, "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "warmup": W, "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": world * B * K / (total_ms * 1e-3) / PUBLISHED_PROOFS_PER_S,
+            "baseline_note": "BASELINE.md: 0.147 proofs/s = 1 / 6.8 s, snarkjs CLI `groth16 prove` of this circuit on an i7-10750H "
+                             "laptop (Report.pdf Table 3) -- the reference's only published figure; different hardware, CPU only",
             "dtype": "u32x8 (254-bit modular integers)", "data": "synthetic",
             "config": {"workload": WORKLOAD, "batch_per_gpu": B, "lanes_per_gpu": lanes, "n_vars": m, "domain": n, "n_public": l,
                        "distinct_inputs": min(args.distinct, B), "l2": "flushed (192 MB write) between timed steps",
