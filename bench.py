@@ -50,7 +50,8 @@ def parse_args():
     ap.add_argument("--lanes", type=int, default=int(os.environ.get("ZKFL_BENCH_LANES", "4")),
                     help="contexts (streams) per GPU; the batch of a step is split evenly over them and proved concurrently")
     ap.add_argument("--no-msm", action="store_true", help="skip the standalone 2^20-point G1 MSM measurement")
-    ap.add_argument("--distinct", type=int, default=16, help="distinct synthetic clients generated on the host (tiled to B)")
+    ap.add_argument("--distinct", type=int, default=int(os.environ.get("ZKFL_BENCH_DISTINCT", "0")),
+                    help="distinct synthetic clients generated on the host, tiled to B (0 = all B distinct)")
     return ap.parse_args()
 
 
@@ -99,13 +100,43 @@ def synth_inputs(circuit, batch: int, distinct: int, rank: int):
     from zkfl_b200 import inputs
     from zkfl_b200.formats import FR
     import random
-    d = max(1, min(distinct, batch))
-    objs = inputs.sgd_verified_batch(d, seed=12345 + rank, nonzero_weights=True)
-    packed = [circuit.pack_inputs([o]) for o in objs]
+    d = batch if distinct <= 0 else max(1, min(distinct, batch))
+    packed = _distinct_inputs(circuit, d, rank)
     rnd = random.Random(1000 + rank)
     ins = b"".join(packed[i % d] for i in range(batch))
     rs = b"".join(rnd.randrange(FR).to_bytes(32, "little") for _ in range(2 * batch))
     return ins, rs
+
+
+def _gen_chunk(args):
+    """worker: clients [lo, hi) of the seeded stream -> flattened input vectors (pure Python Poseidon is the slow part)"""
+    lo, hi, seed = args
+    import zkfl_b200  # noqa: F401
+    from zkfl_b200 import inputs
+    from zkfl_b200.circuits import build_circuit
+    cc = build_circuit("sgd_verified")
+    out = []
+    for cid in range(lo, hi):   # every client owns its own LCG stream so chunks are independent
+        lcg = inputs.JsLcg(seed + 7919 * cid)
+        cl = inputs.SimClient(cid + 1, lcg)
+        cl.TAU2 = 1 << 62
+        w = [lcg.random_int(-1000, 999) for _ in range(cl.DIM)]
+        out.append(b"".join(int(v).to_bytes(32, "little") for v in cc.flatten_input(cl.training_input(w))))
+    return out
+
+
+def _distinct_inputs(circuit, d: int, rank: int):
+    import multiprocessing as mp
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    nproc = max(1, min(len(os.sched_getaffinity(0)) // world, 32, d))
+    step = (d + nproc - 1) // nproc
+    jobs = [(lo, min(lo + step, d), 12345 + 1000003 * rank) for lo in range(0, d, step)]
+    if nproc == 1:
+        chunks = [_gen_chunk(j) for j in jobs]
+    else:
+        with mp.get_context("spawn").Pool(nproc) as pool:
+            chunks = pool.map(_gen_chunk, jobs)
+    return [x for ch in chunks for x in ch]
 
 
 def bench_msm_2pow20(prover, torch, n: int = 1 << 20, reps: int = 5):
@@ -383,7 +414,7 @@ def main():
                              "laptop (Report.pdf Table 3) -- the reference's only published figure; different hardware, CPU only",
             "dtype": "u32x8 (254-bit modular integers)", "data": "synthetic",
             "config": {"workload": WORKLOAD, "batch_per_gpu": B, "lanes_per_gpu": lanes, "n_vars": m, "domain": n, "n_public": l,
-                       "distinct_inputs": min(args.distinct, B), "l2": "flushed (192 MB write) between timed steps",
+                       "distinct_inputs": B if args.distinct <= 0 else min(args.distinct, B), "l2": "flushed (192 MB write) between timed steps",
                        "sharding": "independent proofs, b -> rank, no collective", "proof_verified_by_oracle": bool(verified)},
             "e2e": {"value": world * B * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": len(ins) + len(rs),
                     "d2h_bytes_per_step": 256 * B + 32 * l * B},

@@ -171,3 +171,17 @@ def test_balance_unified_prod_2pow19(gpu_prover):
     assert sj.groth16.verify(formats.export_verification_key(zk), sig, formats.proof_bytes_to_json(proofs[0]))
     Z.close()
     circ.close()
+
+
+def test_full_round_like_the_reference_simulation(gpu_prover):
+    """tests/full_system_simulation.mjs flow (3 clients, 9 proofs, 9 verifications, masked aggregation) on the GPU backend,
+    then a 24-client round (72 proofs, BASELINE configs[3] shape) without re-running setup."""
+    from zkfl_b200 import simulation
+    cache = {}
+    rep = simulation.run_round(gpu_prover, 3, cache=cache)
+    assert rep["verified"] == {"balance": 3, "training": 3, "secagg": 3}
+    assert rep["aggregated_gradient"] == rep["expected_gradient"]           # the pairwise masks cancel
+    assert rep["new_model"] == [-0.01 * g for g in rep["aggregated_gradient"]]
+    rep = simulation.run_round(gpu_prover, 24, cache=cache)
+    assert rep["verified"] == {"balance": 24, "training": 24, "secagg": 24}
+    assert rep["aggregated_gradient"] == rep["expected_gradient"]
