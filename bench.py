@@ -421,7 +421,10 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks.summary(),
             "roofline": {"bound": "imad", "kernel": "k_msm_accumulate<Fq> (4 launches per step)", "achieved": achieved,
-                         "peak": mac_peak / 1e9, "unit": "GMAC/s", "frac": achieved / (mac_peak / 1e9), "traffic": None,
+                         "peak": mac_peak / 1e9, "unit": "GMAC/s", "frac": achieved / (mac_peak / 1e9),
+                         # DRAM bytes per launch from the committed ncu capture (taken at 256 proofs per launch)
+                         "traffic": 613.6e6 if B // lanes == 256 else None,
+                         "traffic_source": "profiles/r01_ncu_full_k_msm_accumulate_chunks_v2.csv (dram read + write per launch, 256 proofs)",
                          "share_of_step": acc_ms / prof_total,
                          "peak_imad32_gops": imad_peak / 1e9, "modmul_per_s": modmul_rate,
                          "note": "MAC = 32x32->64 multiply-accumulate; algorithmic MAC = G1 points x 16 windows x 1360 (SURVEY 8d "
