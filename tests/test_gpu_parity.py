@@ -185,3 +185,41 @@ def test_full_round_like_the_reference_simulation(gpu_prover):
     rep = simulation.run_round(gpu_prover, 24, cache=cache)
     assert rep["verified"] == {"balance": 24, "training": 24, "secagg": 24}
     assert rep["aggregated_gradient"] == rep["expected_gradient"]
+
+
+@pytest.mark.skipif(not __import__("os").environ.get("ZKFL_SLOW"), reason="several minutes; set ZKFL_SLOW=1")
+def test_scaled_training_circuit_2pow20_single_proof_and_split(gpu_prover):
+    """BASELINE configs[4]: TrainingStepVerified(256, 32, 8, 1000) -- 976k wires, 966k constraints, domain 2^20 -- as ONE
+    proof: whole on one context, and with every MSM split into 8 point ranges (the 8-GPU exchange, ranks emulated one after
+    another on this GPU); both bit-exact against the oracle and verified."""
+    import time
+    from zkfl_b200 import formats
+    from zkfl_b200 import snarkjs as sj
+    from zkfl_b200.circuits.library import training_step_verified
+    t = time.time()
+    cc = training_step_verified(256, 32, 8, 1000, "sgd_scaled_2pow20")
+    inp = I.scaled_training_input(256, 32, 8)
+    circ = gpu_prover.load_circuit(cc, check_constraints=False)
+    zk = gpu_prover.new_zkey(cc, b"scaled")
+    Z = gpu_prover.load_zkey(zk)
+    assert Z.domain == 1 << 20
+    print(f"build + setup {time.time() - t:.0f} s, zkey {len(zk) / 1e6:.0f} MB")
+    t = time.time()
+    ws = gpu_prover.calculate_witness(circ, [inp], check=False)
+    proofs, pubs = gpu_prover.prove(Z, ws, [(3, 4)])
+    print(f"witness + prove (first call, buffers allocated) {time.time() - t:.2f} s")
+    t = time.time()
+    proofs2, _ = gpu_prover.prove(Z, ws, [(3, 4)])
+    print(f"prove, second call {time.time() - t:.3f} s")
+    assert proofs2 == proofs
+    t = time.time()
+    ref_p, ref_pub = ol.groth16_prove(zk, ws[0], 3, 4)
+    print(f"oracle prove {time.time() - t:.1f} s on {ol.ncores()} threads")
+    assert ws[0] == ol.witness_batch(cc.program_bytes(), circ.pack_inputs([inp]), cc.n_inputs, cc.n_wires)
+    assert proofs[0] == ref_p and pubs[0] == ref_pub
+    parts = [gpu_prover.msm_partials(Z, ws, r, 8) for r in range(8)]
+    assert gpu_prover.finalize(Z, parts, 1, [(3, 4)]) == [ref_p]
+    sig = formats.publics_bytes_to_json(pubs[0])
+    assert sj.groth16.verify(formats.export_verification_key(zk), sig, formats.proof_bytes_to_json(proofs[0]))
+    Z.close()
+    circ.close()

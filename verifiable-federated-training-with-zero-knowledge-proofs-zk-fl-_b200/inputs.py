@@ -87,8 +87,10 @@ class SimClient:
     """One client of full_system_simulation.mjs (N=8, MODEL_DIM=4, DEPTH=3, tau^2=1e8, round 1)."""
     N, DIM, DEPTH, TAU2, PRECISION, ROUND = 8, 4, 3, 100000000, 1000, 1
 
-    def __init__(self, client_id: int, lcg: JsLcg):
+    def __init__(self, client_id: int, lcg: JsLcg, n: int | None = None, dim: int | None = None, depth: int | None = None):
         self.id = client_id
+        if n is not None:          # scaled configurations (BASELINE configs[4]); defaults are the reference's (8, 4, 3)
+            self.N, self.DIM, self.DEPTH = n, dim, depth
         self.features, self.labels = [], []
         for i in range(self.N):                                           # :282-295
             self.features.append([lcg.random_int(0, 100, client_id * 1000 + i * 10 + j) for j in range(self.DIM)])
@@ -158,6 +160,16 @@ def sgd_verified_batch(n: int, seed: int = 12345, nonzero_weights: bool = False)
             cl.TAU2 = 1 << 62  # test_verified_gradient.mjs uses a large bound; stay below LessThan(64)'s range
         out.append(cl.training_input(w))
     return out
+
+
+def scaled_training_input(batch: int, dim: int, depth: int, seed: int = 2024) -> dict:
+    """TrainingStepVerified(batch, dim, depth, 1000) input for the scaled synthetic circuit:
+    features in [0, 100], |weights| <= 1000 so every LessThan(64) operand stays below 2^64."""
+    assert batch <= 1 << depth
+    lcg = JsLcg(seed)
+    cl = SimClient(1, lcg, n=batch, dim=dim, depth=depth)
+    cl.TAU2 = 1 << 62
+    return cl.training_input([lcg.random_int(-1000, 999) for _ in range(dim)])
 
 
 def secure_agg_client_input() -> dict:

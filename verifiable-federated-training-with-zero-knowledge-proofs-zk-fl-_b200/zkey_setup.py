@@ -89,19 +89,32 @@ def r1cs_info(data: bytes) -> dict:
             "nPubInputs": n_pub_in, "nOutputs": n_pub_out, "nLabels": n_labels}
 
 
-def _terms_of(compiled) -> dict:
-    """the same dictionary parse_r1cs returns, straight from a CompiledCircuit (skips a 100s-of-MB round trip)"""
-    return {"n_wires": compiled.n_wires, "n_public": compiled.n_public, "n_constraints": compiled.n_constraints,
-            "A": zip(compiled.A.rows, compiled.A.wires, compiled.A.coefs),
-            "B": zip(compiled.B.rows, compiled.B.wires, compiled.B.coefs),
-            "C": zip(compiled.C.rows, compiled.C.wires, compiled.C.coefs)}
+class _Terms:
+    """(row, wire, coef) triples of the three matrices, re-iterable without materialising tuples (the scaled circuits
+    have tens of millions of non-zeros). Built from `.r1cs` bytes or straight from a CompiledCircuit."""
+
+    def __init__(self, r1cs):
+        if isinstance(r1cs, (bytes, bytearray)):
+            d = parse_r1cs(r1cs)
+            self.n_wires, self.n_public, self.n_constraints = d["n_wires"], d["n_public"], d["n_constraints"]
+            self._m = {k: tuple(zip(*d[k])) if d[k] else ((), (), ()) for k in "ABC"}
+        else:
+            self.n_wires, self.n_public, self.n_constraints = r1cs.n_wires, r1cs.n_public, r1cs.n_constraints
+            self._m = {"A": (r1cs.A.rows, r1cs.A.wires, r1cs.A.coefs), "B": (r1cs.B.rows, r1cs.B.wires, r1cs.B.coefs),
+                       "C": (r1cs.C.rows, r1cs.C.wires, r1cs.C.coefs)}
+
+    def __getitem__(self, key):
+        return zip(*self._m[key])
+
+    def count(self, key):
+        return len(self._m[key][0])
 
 
 def new_zkey(prover, r1cs, seed: bytes) -> bytes:
     """prover: zkfl_b200.api.Prover (its GPU does the scalar multiplications). r1cs: `.r1cs` bytes or a CompiledCircuit."""
-    r = parse_r1cs(r1cs) if isinstance(r1cs, (bytes, bytearray)) else _terms_of(r1cs)
-    r = {k: (list(v) if k in "ABC" else v) for k, v in r.items()}
-    m, l, nc = r["n_wires"], r["n_public"], r["n_constraints"]
+    r = _Terms(r1cs)
+    r_info = {"n_wires": r.n_wires, "n_public": r.n_public, "n_constraints": r.n_constraints}
+    m, l, nc = r_info["n_wires"], r_info["n_public"], r_info["n_constraints"]
     tau, alpha, beta, delta = toxic_from_seed(seed)
     lg = max((nc + l).bit_length(), 1)  # smallest 2^lg >= nc + l + 1
     n = 1 << lg
@@ -135,16 +148,16 @@ def new_zkey(prover, r1cs, seed: bytes) -> bytes:
     beta2, gamma2, delta2, pb2 = g2[:128], g2[128:256], g2[256:384], g2[384:]
     hdr = (struct.pack("<I", 32) + FQ.to_bytes(32, "little") + struct.pack("<I", 32) + FR.to_bytes(32, "little")
            + struct.pack("<III", m, l, n) + alpha1 + beta1 + beta2 + gamma2 + delta1 + delta2)
-    coeffs = bytearray()
+    parts = []
     n_coef = 0
+    pack = struct.Struct("<III").pack
     for mtx, key in ((0, "A"), (1, "B")):
-        for row, wire, k in r[key]:
-            coeffs += struct.pack("<III", mtx, row, wire) + (k * _R2 % FR).to_bytes(32, "little")
-            n_coef += 1
-    for s in range(l + 1):
-        coeffs += struct.pack("<III", 0, nc + s, s) + (_R2 % FR).to_bytes(32, "little")
-        n_coef += 1
+        parts.append(b"".join(pack(mtx, row, wire) + (k * _R2 % FR).to_bytes(32, "little") for row, wire, k in r[key]))
+        n_coef += r.count(key)
+    parts.append(b"".join(pack(0, nc + s, s) + (_R2 % FR).to_bytes(32, "little") for s in range(l + 1)))
+    n_coef += l + 1
+    coeffs = b"".join(parts)
     # snarkjs writes A and B interleaved in constraint order; the prover does not depend on the order
-    sections = [(1, struct.pack("<I", 1)), (2, hdr), (3, ic), (4, struct.pack("<I", n_coef) + bytes(coeffs)),
+    sections = [(1, struct.pack("<I", 1)), (2, hdr), (3, ic), (4, struct.pack("<I", n_coef) + coeffs),
                 (5, pa), (6, pb1), (7, pb2), (8, pc), (9, ph), (10, bytes(64) + struct.pack("<I", 0))]
     return write_container(b"zkey", 1, sections)
