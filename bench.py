@@ -212,12 +212,12 @@ def run_reference(args, rank, world):
     from zkfl_b200 import inputs
     from zkfl_b200.circuits import build_circuit
     cc = build_circuit("sgd_verified")
-    cache = os.path.join(ROOT, "gpurun_out", "bench_cache")
-    zkey_path = os.path.join(cache, "sgd_verified.zkey")
-    if os.path.exists(zkey_path):
-        zk = open(zkey_path, "rb").read()
-    else:
-        zk = make_zkey(cc, cache)   # needs the GPU once (setup is not part of the timed path)
+    # proving key made by the ORACLE alone (C++ scalar multiplications): nothing of the CUDA library is on this arm
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import groth16_ref
+    import witness_ref
+    from zkfl_b200.zkey_setup import toxic_from_seed
+    zk = groth16_ref.setup_fast(witness_ref.R1cs(cc.r1cs_bytes()), *toxic_from_seed(b"zkfl-bench"))
     ncores = len(os.sched_getaffinity(0))
     objs = inputs.sgd_verified_batch(4, seed=12345, nonzero_weights=True)
     packs = [b"".join(int(v).to_bytes(32, "little") for v in cc.flatten_input(o)) for o in objs]

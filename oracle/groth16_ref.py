@@ -309,3 +309,74 @@ def verify(vkey, publics, proof) -> bool:
         vk_x = ec_add(vk_x, ec_mul(ic, int(x)))
     return bn.pairing_product_is_one([
         (ec_neg(a), b), (vkey["alpha1"], vkey["beta2"]), (vk_x, vkey["gamma2"]), (c, vkey["delta2"])])
+
+
+# --------------------------------------------------------------------------- fast setup (C++ oracle scalar muls)
+def setup_fast(r1cs: R1cs, tau: int, alpha: int, beta: int, delta: int, nthreads: int = 0):
+    """Same key as `setup()` (same formulas, same section layout) with the k*G multiplications done by the C++ oracle
+    (oracle_lib.g1_mul_gen / g2_mul_gen) instead of pure Python -- usable at the real circuit sizes. Returns zkey bytes."""
+    import oracle_lib as ol
+    m, l, nc = r1cs.n_wires, r1cs.n_public, r1cs.n_constraints
+    lg = max((nc + l).bit_length(), 1)
+    n = 1 << lg
+
+    def lagrange(lg_):
+        nn = 1 << lg_
+        w = fr_root_of_unity(lg_)
+        pw, x = [], 1
+        for _ in range(nn):
+            pw.append(x)
+            x = x * w % R
+        zt = (pow(tau, nn, R) - 1) * bn.inv_mod(nn, R) % R
+        den = [(tau - p) % R for p in pw]
+        pref, acc = [], 1
+        for v in den:
+            pref.append(acc)
+            acc = acc * v % R
+        inv = bn.inv_mod(acc, R)
+        out = [0] * nn
+        for i in range(nn - 1, -1, -1):
+            out[i] = zt * pw[i] % R * (inv * pref[i] % R) % R
+            inv = inv * den[i] % R
+        return out
+
+    L = lagrange(lg)
+    At, Bt, Ct = [0] * m, [0] * m, [0] * m
+    coeffs = []
+    for c, (a, b, cc) in enumerate(r1cs.constraints):
+        for wire, k in a:
+            At[wire] = (At[wire] + k * L[c]) % R
+            coeffs.append((0, c, wire, k))
+        for wire, k in b:
+            Bt[wire] = (Bt[wire] + k * L[c]) % R
+            coeffs.append((1, c, wire, k))
+        for wire, k in cc:
+            Ct[wire] = (Ct[wire] + k * L[c]) % R
+    for s in range(l + 1):
+        At[s] = (At[s] + L[nc + s]) % R
+        coeffs.append((0, nc + s, s, 1))
+    dinv = bn.inv_mod(delta, R)
+    comb = [(beta * a + alpha * b + c) % R for a, b, c in zip(At, Bt, Ct)]
+    L2 = lagrange(lg + 1)
+    g1s = [alpha, beta, delta] + comb[:l + 1] + At + Bt + [c * dinv % R for c in comb[l + 1:]] + [L2[2 * i + 1] * dinv % R for i in range(n)]
+    g1 = ol.g1_mul_gen(ol.fes(g1s), nthreads)
+    g2 = ol.g2_mul_gen(ol.fes([beta, 1, delta] + Bt), nthreads)
+    pos = [0]
+
+    def take(cnt):
+        out = g1[64 * pos[0]:64 * (pos[0] + cnt)]
+        pos[0] += cnt
+        return out
+
+    alpha1, beta1, delta1 = take(1), take(1), take(1)
+    ic, pa, pb1, pc, ph = take(l + 1), take(m), take(m), take(m - l - 1), take(n)
+    hdr2 = (struct.pack("<I", 32) + Q.to_bytes(32, "little") + struct.pack("<I", 32) + R.to_bytes(32, "little")
+            + struct.pack("<III", m, l, n) + alpha1 + beta1 + g2[:128] + g2[128:256] + delta1 + g2[256:384])
+    sec4 = struct.pack("<I", len(coeffs)) + b"".join(
+        struct.pack("<III", mtx, c, wire) + (k * RR % R * RR % R).to_bytes(32, "little") for mtx, c, wire, k in coeffs)
+    sections = [(1, struct.pack("<I", 1)), (2, hdr2), (3, ic), (4, sec4), (5, pa), (6, pb1), (7, g2[384:]), (8, pc), (9, ph),
+                (10, bytes(64) + struct.pack("<I", 0))]
+    out = [b"zkey", struct.pack("<II", 1, len(sections))]
+    for sid, payload in sections:
+        out += [struct.pack("<IQ", sid, len(payload)), payload]
+    return b"".join(out)

@@ -95,3 +95,25 @@ def test_snarkjs_surface_and_cli_round_trip(tmp_path, monkeypatch):
     vk = json.load(open(f"{d}/vkey.json"))
     assert sj.groth16.verify(vk, res["publicSignals"], res["proof"])
     assert g16.verify(g16.vkey_from_json(vk), ol.ints(ref_pub), g16.proof_from_json(res["proof"]))
+
+
+def test_product_setup_matches_the_oracle_setup(emul_prover, oracle):
+    """`groth16 setup` replacement (host scalar arithmetic + device generator multiplications) against the oracle's own
+    setup from the same toxic waste: every point section and the header byte-identical, coefficient sections equal as sets
+    (snarkjs interleaves A/B per constraint, we write A then B: the prover does not depend on the order)."""
+    import struct
+    import groth16_ref as g16
+    import witness_ref as wr
+    from zkfl_b200.zkey_setup import toxic_from_seed
+    cc = build_circuit("secure_agg_client")
+    mine = emul_prover.new_zkey(cc, b"parity-seed")
+    ref = g16.setup_fast(wr.R1cs(cc.r1cs_bytes()), *toxic_from_seed(b"parity-seed"))
+    _, a = wr.read_sections(mine, b"zkey")
+    _, b = wr.read_sections(ref, b"zkey")
+    for sid in (1, 2, 3, 5, 6, 7, 8, 9):
+        assert a[sid] == b[sid], f"section {sid} differs"
+
+    def coeff_set(sec):
+        n = struct.unpack_from("<I", sec, 0)[0]
+        return {sec[4 + 44 * i:48 + 44 * i] for i in range(n)}
+    assert coeff_set(a[4]) == coeff_set(b[4]) and len(a[4]) == len(b[4])
