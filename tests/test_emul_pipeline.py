@@ -1,6 +1,8 @@
 """CPU suite for the kernel logic: the CUDA sources compiled as a host emulation (tests/_emul, a test
 double that the product never loads) must agree with the oracle bit for bit. The GPU suite
 (tests/test_gpu_parity.py) repeats these cases on the real sm_100a library at full sizes."""
+import os
+
 import pytest
 
 import parity_cases as pc
@@ -117,3 +119,31 @@ def test_product_setup_matches_the_oracle_setup(emul_prover, oracle):
         n = struct.unpack_from("<I", sec, 0)[0]
         return {sec[4 + 44 * i:48 + 44 * i] for i in range(n)}
     assert coeff_set(a[4]) == coeff_set(b[4]) and len(a[4]) == len(b[4])
+
+
+def test_c_abi_argument_and_format_errors(emul_prover):
+    """errors come back as codes + messages, never as crashes: mismatched artefacts, truncated files, unreduced values"""
+    import ctypes
+    from zkfl_b200.api import Circuit
+    lib, ctx = emul_prover.lib, emul_prover.ctx
+    cc = pc.tiny_circuit()
+    circ = emul_prover.load_circuit(cc)
+    other = emul_prover.load_circuit(build_circuit("secure_agg_client"), check_constraints=False)
+    zk = open(os.path.join(os.path.dirname(__file__), "golden", "tiny.zkey"), "rb").read()
+    Z = emul_prover.load_zkey(zk)
+    with pytest.raises(_lib.ZkflError, match="do not match"):
+        emul_prover.full_prove(other, Z, [I.secure_agg_client_input()], [(1, 2)])
+    with pytest.raises(_lib.ZkflError, match="not reduced"):
+        emul_prover.full_prove(circ, Z, pc.tiny_inputs()[:1], [(2 ** 255, 1)])
+    with pytest.raises(_lib.ZkflError):
+        emul_prover.load_zkey(zk[:len(zk) // 2])
+    with pytest.raises(_lib.ZkflError):
+        emul_prover.load_zkey(b"wtns" + zk[4:])
+    bad = bytearray(cc.program_bytes())
+    bad[12 + 12 + 12] ^= 0xFF   # n_ops in the header no longer matches the op section
+    with pytest.raises(_lib.ZkflError):
+        Circuit(emul_prover, bytes(bad))
+    h = ctypes.c_void_p()
+    assert lib.zkfl_zkey_load(ctx, None, 0, ctypes.byref(h)) != 0 and lib.zkfl_last_error()
+    assert lib.zkfl_groth16_prove_batch(ctx, Z.handle, None, None, 1, None, None) != 0
+    circ.close(); other.close(); Z.close()

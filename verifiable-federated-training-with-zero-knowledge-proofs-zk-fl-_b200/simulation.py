@@ -45,14 +45,15 @@ def run_round(prover, n_clients: int = 3, seed: int = 12345, weights=None, verif
         timing[name + "_s"] = time.perf_counter() - t
         return vk, [formats.proof_bytes_to_json(p) for p in proofs], [formats.publics_bytes_to_json(q) for q in pubs]
 
-    def check(vk, sig, proof):
-        return (not verify) or sj.groth16.verify(vk, sig, proof)
+    def verify_all(vk, sigs, proofs):
+        return [True] * len(sigs) if not verify else sj.groth16.verifyBatch(vk, list(zip(sigs, proofs)))
 
     # phase 3: balance proofs; Server.verifyBalanceProof (:848-880)
     vk, proofs, sigs = prove_phase("balance_unified", [c.balance_input() for c in clients])
     balance_root = {}
-    for c, p, s in zip(clients, proofs, sigs):
-        ok = s[1] == str(c.root_d) and s[2] == str(c.N) and int(s[3]) + int(s[4]) == c.N and check(vk, s, p)
+    valid = verify_all(vk, sigs, proofs)
+    for c, p, s, v in zip(clients, proofs, sigs, valid):
+        ok = s[1] == str(c.root_d) and s[2] == str(c.N) and int(s[3]) + int(s[4]) == c.N and v
         if ok:
             balance_root[c.id] = s[1]
             report["verified"]["balance"] += 1
@@ -60,12 +61,13 @@ def run_round(prover, n_clients: int = 3, seed: int = 12345, weights=None, verif
     # phase 4: verified-gradient proofs; Server.verifyTrainingProof (:886-990)
     vk, proofs, sigs = prove_phase("sgd_verified", [c.training_input(model) for c in clients])
     trained = set()
-    for c, p, s in zip(clients, proofs, sigs):
+    valid = verify_all(vk, sigs, proofs)
+    for c, p, s, v in zip(clients, proofs, sigs, valid):
         ok = (balance_root.get(c.id) == str(c.root_d)                                           # binding to the balance proof
               and s[1] == str(c.ROUND) and s[2] == str(c.root_d) and s[3] == str(c.root_g) and s[4] == str(c.root_w)
               and s[5] == str(c.TAU2)
               and inputs.gradient_commitment(c.gradient, c.id, c.ROUND) == c.root_g            # recomputed from the clear gradient
-              and check(vk, s, p))
+              and v)
         if ok:
             trained.add(c.id)
             report["verified"]["training"] += 1
@@ -77,10 +79,11 @@ def run_round(prover, n_clients: int = 3, seed: int = 12345, weights=None, verif
 
     vk, proofs, sigs = prove_phase("secure_masked_update", [c.secagg_input(peers_of(c)) for c in clients])
     accepted = []
-    for c, p, s in zip(clients, proofs, sigs):
+    valid = verify_all(vk, sigs, proofs)
+    for c, p, s, v in zip(clients, proofs, sigs, valid):
         ok = (c.id in trained and s[0] == str(c.id) and s[1] == str(c.ROUND) and s[2] == str(c.root_d) and s[3] == str(c.root_g)
               and s[4] == str(c.root_w) and s[6] == str(c.TAU2) and s[7:11] == [str(x) for x in c.masked_update]
-              and s[11:13] == [str(j) for j in peers_of(c)] and check(vk, s, p))
+              and s[11:13] == [str(j) for j in peers_of(c)] and v)
         if ok:
             accepted.append(c)
             report["verified"]["secagg"] += 1

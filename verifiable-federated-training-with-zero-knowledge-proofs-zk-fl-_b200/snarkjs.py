@@ -165,6 +165,15 @@ class groth16:
         return _result(proofs[0], pubs[0])
 
     @staticmethod
+    def verifyBatch(vkey: dict, items, threads: int = 0) -> list:
+        """items: [(publicSignals, proof), ...] -> [bool, ...]. The pairing check is host code that releases the GIL, so the
+        proofs of a round are checked on all host cores (the reference runs one `snarkjs groth16 verify` process per proof)."""
+        from concurrent.futures import ThreadPoolExecutor
+        n = threads or len(os.sched_getaffinity(0))
+        with ThreadPoolExecutor(max_workers=max(1, min(n, len(items) or 1))) as ex:
+            return list(ex.map(lambda it: groth16.verify(vkey, it[0], it[1]), items))
+
+    @staticmethod
     def verify(vkey: dict, publicSignals, proof: dict) -> bool:
         """`snarkjs groth16 verify vkey public proof` (tests/full_system_simulation.mjs:865-868)."""
         if isinstance(vkey, str):
