@@ -109,9 +109,10 @@ struct alignas(16) Fp {
       uint32_t* Y = (i & 1) ? ev : od;   // plays "odd"
       const uint32_t bi = b.v[i];
       if (i == 0) {
-        ZK_UNROLL for (int j = 0; j < 8; j += 2) {
-          Y[j] = a.v[j + 1] * bi; Y[j + 1] = __umulhi(a.v[j + 1], bi);
-          X[j] = a.v[j] * bi;     X[j + 1] = __umulhi(a.v[j], bi);
+        ZK_UNROLL for (int j = 0; j < 8; j += 2) {   // 64-bit products: one IMAD.WIDE each instead of IMAD + half-rate IMAD.HI
+          const uint64_t py = (uint64_t)a.v[j + 1] * bi, px = (uint64_t)a.v[j] * bi;
+          Y[j] = (uint32_t)py; Y[j + 1] = (uint32_t)(py >> 32);
+          X[j] = (uint32_t)px; X[j + 1] = (uint32_t)(px >> 32);
         }
       } else {
         // previous total / 2^32: Y[0] is zero, Y[1] joins X[0], Y shifts down two words while taking the odd products
@@ -178,6 +179,140 @@ struct alignas(16) Fp {
   static ZK_HD Fp mul_hot(const Fp& a, const Fp& b) { return mul_call(a, b); }
 #endif
   static ZK_HD Fp sqr_hot(const Fp& a) { return mul_hot(a, a); }
+
+  // ------------------------------------------------------------------ lazy reduction building blocks
+  // 512-bit unreduced product and a separate Montgomery reduction (limb-exact model: tests/dev/wide_model.py).
+  // For sharing ONE reduction between several products: Fq2 Karatsuba (3 wide products + 2 reductions = 336 wide MACs instead
+  // of 408) and Y3 = R*(Q - X3) - Y1*PPP in the G1 mixed add (200 instead of 272).  MEASURED SLOWER on B200 (G2 bucket
+  // accumulation 92 -> 113 ms at 1024 proofs): the 512-bit add/sub glue and the explicit shifts of a separate reduction cost
+  // more issue slots than the 72 wide MACs saved, so it is opt-in (-DZKFL_LAZY_REDUCTION) and off by default.
+  struct Wide { uint32_t v[16]; };
+
+  // a + b without reduction (inputs < p, result < 2p < 2^255)
+  static ZK_HD Fp add_noreduce(const Fp& a, const Fp& b) {
+    Fp r; uint64_t c = 0;
+    ZK_UNROLL for (int i = 0; i < 8; i++) { c += (uint64_t)a.v[i] + b.v[i]; r.v[i] = (uint32_t)c; c >>= 32; }
+    return r;
+  }
+  static ZK_HD Wide wide_add(const Wide& x, const Wide& y) {   // no overflow by the callers' bounds
+    Wide r; uint64_t c = 0;
+    ZK_UNROLL for (int i = 0; i < 16; i++) { c += (uint64_t)x.v[i] + y.v[i]; r.v[i] = (uint32_t)c; c >>= 32; }
+    return r;
+  }
+  static ZK_HD Wide wide_sub(const Wide& x, const Wide& y) {   // x >= y by the callers' bounds
+    Wide r; uint64_t bw = 0;
+    ZK_UNROLL for (int i = 0; i < 16; i++) { uint64_t d = (uint64_t)x.v[i] - y.v[i] - bw; r.v[i] = (uint32_t)d; bw = (d >> 32) & 1; }
+    return r;
+  }
+  static ZK_HD Wide wide_add_pR(const Wide& x) {               // x + p * 2^256
+    Wide r = x; uint64_t c = 0;
+    ZK_UNROLL for (int i = 0; i < 8; i++) { c += (uint64_t)x.v[8 + i] + P::mod(i); r.v[8 + i] = (uint32_t)c; c >>= 32; }
+    return r;
+  }
+
+  static ZK_HD Wide mul_wide(const Fp& a, const Fp& b) {
+    Wide r;
+#ifdef ZKFL_PTX_MUL
+    // even/odd paired chains as in mul_inline, without the reduction rows. E word k has weight 2^(32k), O word k has
+    // weight 2^(32(k+1)); each chain's carry lands in a word that so far only holds carries.
+    uint32_t E[17], O[17];
+    ZK_UNROLL for (int k = 0; k < 17; k++) { E[k] = 0; O[k] = 0; }
+    ZK_UNROLL for (int i = 0; i < 8; i++) {
+      const uint32_t bi = b.v[i];
+      const int pe = i & 1;            // parity of the a-limbs whose products are word-aligned with E in this row
+      const int e0 = i + pe;           // first E word of the row
+      E[e0] = ptx::mad_lo_cc(a.v[pe], bi, E[e0]); E[e0 + 1] = ptx::madc_hi_cc(a.v[pe], bi, E[e0 + 1]);
+      ZK_UNROLL for (int t = 1; t < 4; t++) {
+        E[e0 + 2 * t] = ptx::madc_lo_cc(a.v[pe + 2 * t], bi, E[e0 + 2 * t]);
+        E[e0 + 2 * t + 1] = ptx::madc_hi_cc(a.v[pe + 2 * t], bi, E[e0 + 2 * t + 1]);
+      }
+      E[e0 + 8] = ptx::addc(E[e0 + 8], 0);
+      const int po = 1 - pe;           // the other parity goes to O
+      const int o0 = i + po - 1;       // first O word of the row (O is offset by one word)
+      O[o0] = ptx::mad_lo_cc(a.v[po], bi, O[o0]); O[o0 + 1] = ptx::madc_hi_cc(a.v[po], bi, O[o0 + 1]);
+      ZK_UNROLL for (int t = 1; t < 4; t++) {
+        O[o0 + 2 * t] = ptx::madc_lo_cc(a.v[po + 2 * t], bi, O[o0 + 2 * t]);
+        O[o0 + 2 * t + 1] = ptx::madc_hi_cc(a.v[po + 2 * t], bi, O[o0 + 2 * t + 1]);
+      }
+      O[o0 + 8] = ptx::addc(O[o0 + 8], 0);
+    }
+    r.v[0] = E[0];
+    r.v[1] = ptx::add_cc(E[1], O[0]);
+    ZK_UNROLL for (int k = 2; k < 15; k++) r.v[k] = ptx::addc_cc(E[k], O[k - 1]);
+    r.v[15] = ptx::addc(E[15], O[14]);
+#else
+    uint32_t t[16];
+    ZK_UNROLL for (int i = 0; i < 16; i++) t[i] = 0;
+    ZK_UNROLL for (int i = 0; i < 8; i++) {
+      uint64_t c = 0;
+      ZK_UNROLL for (int j = 0; j < 8; j++) { c += (uint64_t)a.v[j] * b.v[i] + t[i + j]; t[i + j] = (uint32_t)c; c >>= 32; }
+      t[i + 8] = (uint32_t)c;
+    }
+    ZK_UNROLL for (int i = 0; i < 16; i++) r.v[i] = t[i];
+#endif
+    return r;
+  }
+
+  // t * 2^-256 mod p for t < 2 * p * 2^256
+  static ZK_HD Fp redc(const Wide& t) {
+    uint32_t r[9];
+#ifdef ZKFL_PTX_MUL
+    uint32_t X[8], Y[8];
+    ZK_UNROLL for (int k = 0; k < 8; k++) { X[k] = t.v[k]; Y[k] = 0; }
+    ZK_UNROLL for (int i = 0; i < 8; i++) {
+      const uint32_t m = X[0] * P::inv();
+      Y[0] = ptx::mad_lo_cc(m, P::mod(1), Y[0]); Y[1] = ptx::madc_hi_cc(m, P::mod(1), Y[1]);
+      ZK_UNROLL for (int j = 2; j < 8; j += 2) { Y[j] = ptx::madc_lo_cc(m, P::mod(j + 1), Y[j]); Y[j + 1] = ptx::madc_hi_cc(m, P::mod(j + 1), Y[j + 1]); }
+      X[0] = ptx::mad_lo_cc(m, P::mod(0), X[0]); X[1] = ptx::madc_hi_cc(m, P::mod(0), X[1]);
+      ZK_UNROLL for (int j = 2; j < 8; j += 2) { X[j] = ptx::madc_lo_cc(m, P::mod(j), X[j]); X[j + 1] = ptx::madc_hi_cc(m, P::mod(j), X[j + 1]); }
+      Y[7] = ptx::addc(Y[7], 0);
+      // divide by 2^32 (X[0] is zero): X' = Y with X'[0] += X[1]; Y' = X[2..7], carry rippling; then bring in t[8 + i]
+      uint32_t nx[8], ny[8];
+      nx[0] = ptx::add_cc(Y[0], X[1]);
+      ZK_UNROLL for (int k = 0; k < 6; k++) ny[k] = ptx::addc_cc(X[k + 2], 0);
+      ny[6] = ptx::addc(0, 0);
+      ZK_UNROLL for (int k = 1; k < 7; k++) nx[k] = Y[k];
+      nx[7] = ptx::add_cc(Y[7], t.v[8 + i]);
+      ny[7] = ptx::addc(0, 0);
+      ZK_UNROLL for (int k = 0; k < 8; k++) { X[k] = nx[k]; Y[k] = ny[k]; }
+    }
+    r[0] = X[0];
+    r[1] = ptx::add_cc(X[1], Y[0]);
+    ZK_UNROLL for (int k = 2; k < 8; k++) r[k] = ptx::addc_cc(X[k], Y[k - 1]);
+    r[8] = ptx::addc(0, Y[7]);
+#else
+    uint32_t w[17];
+    ZK_UNROLL for (int i = 0; i < 16; i++) w[i] = t.v[i];
+    w[16] = 0;
+    ZK_UNROLL for (int i = 0; i < 8; i++) {
+      const uint32_t m = w[i] * P::inv();
+      uint64_t c = 0;
+      ZK_UNROLL for (int j = 0; j < 8; j++) { c += (uint64_t)m * P::mod(j) + w[i + j]; w[i + j] = (uint32_t)c; c >>= 32; }
+      for (int k = i + 8; k < 17 && c; k++) { c += w[k]; w[k] = (uint32_t)c; c >>= 32; }
+    }
+    ZK_UNROLL for (int i = 0; i < 9; i++) r[i] = w[8 + i];
+#endif
+    // value < 3p: at most two subtractions
+    ZK_UNROLL for (int round = 0; round < 2; round++) {
+      uint32_t d[9]; uint64_t bw = 0;
+      ZK_UNROLL for (int i = 0; i < 9; i++) { uint64_t q = (uint64_t)r[i] - (i < 8 ? P::mod(i) : 0u) - bw; d[i] = (uint32_t)q; bw = (q >> 32) & 1; }
+      const uint32_t keep = (uint32_t)0 - (uint32_t)bw;   // all ones when r < p
+      ZK_UNROLL for (int i = 0; i < 9; i++) r[i] = (r[i] & keep) | (d[i] & ~keep);
+    }
+    Fp o; ZK_UNROLL for (int i = 0; i < 8; i++) o.v[i] = r[i];
+    return o;
+  }
+  // (a*b - c*d) / R mod p with one reduction
+  static ZK_HD_NOINLINE Fp diff_of_products_call(Fp a, Fp b, Fp c, Fp d) {
+    return redc(wide_sub(wide_add_pR(mul_wide(a, b)), mul_wide(c, d)));
+  }
+  static ZK_HD Fp diff_of_products(const Fp& a, const Fp& b, const Fp& c, const Fp& d) {
+#ifndef ZKFL_LAZY_REDUCTION
+    return mul_hot(a, b) - mul_hot(c, d);
+#else
+    return diff_of_products_call(a, b, c, d);
+#endif
+  }
   ZK_HD Fp sqr() const { return *this * *this; }
   ZK_HD Fp to_mont() const { return *this * r2(); }
   ZK_HD Fp from_mont() const { Fp o = zero(); o.v[0] = 1; return *this * o; }
@@ -216,10 +351,24 @@ struct alignas(16) Fq2 {
     Fq t = Fq::mul_hot(x.a, x.b);
     Fq2 r; r.a = Fq::mul_hot(x.a + x.b, x.a - x.b); r.b = t.dbl(); return r;
   }
+  // Karatsuba with lazy reduction: three 512-bit products, two Montgomery reductions
+  static ZK_HD_NOINLINE Fq2 mul_lazy_call(Fq2 x, Fq2 y) {
+    Fq::Wide aa = Fq::mul_wide(x.a, y.a), bb = Fq::mul_wide(x.b, y.b);
+    Fq::Wide ss = Fq::mul_wide(Fq::add_noreduce(x.a, x.b), Fq::add_noreduce(y.a, y.b));
+    Fq2 r;
+    r.a = Fq::redc(Fq::wide_sub(Fq::wide_add_pR(aa), bb));
+    r.b = Fq::redc(Fq::wide_sub(Fq::wide_sub(ss, aa), bb));
+    return r;
+  }
   static ZK_HD Fq2 mul_hot(const Fq2& x, const Fq2& y) {
+#ifndef ZKFL_LAZY_REDUCTION
     Fq aa = Fq::mul_hot(x.a, y.a), bb = Fq::mul_hot(x.b, y.b), s = Fq::mul_hot(x.a + x.b, y.a + y.b);
     Fq2 r; r.a = aa - bb; r.b = s - aa - bb; return r;
+#else
+    return mul_lazy_call(x, y);
+#endif
   }
+  static ZK_HD Fq2 diff_of_products(const Fq2& a, const Fq2& b, const Fq2& c, const Fq2& d) { return mul_hot(a, b) - mul_hot(c, d); }
   ZK_HD Fq2 inv() const { Fq d = (a.sqr() + b.sqr()).inv(); Fq2 r; r.a = a * d; r.b = (b * d).neg(); return r; }
   ZK_HD Fq2 from_mont() const { Fq2 r; r.a = a.from_mont(); r.b = b.from_mont(); return r; }
 };
@@ -275,7 +424,7 @@ template <class F> ZK_HD void xyzz_madd(Xyzz<F>& acc, const Affine<F>& q0, bool 
   }
   F PP = F::sqr_hot(Pp), PPP = F::mul_hot(Pp, PP), Qq = F::mul_hot(acc.X, PP);
   F X3 = F::sqr_hot(Rr) - PPP - Qq.dbl();
-  acc.Y = F::mul_hot(Rr, Qq - X3) - F::mul_hot(acc.Y, PPP);
+  acc.Y = F::diff_of_products(Rr, Qq - X3, acc.Y, PPP);
   acc.X = X3;
   acc.ZZ = F::mul_hot(acc.ZZ, PP);
   acc.ZZZ = F::mul_hot(acc.ZZZ, PPP);
