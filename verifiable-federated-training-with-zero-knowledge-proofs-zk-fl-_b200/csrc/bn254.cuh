@@ -351,6 +351,7 @@ struct alignas(16) Fq2 {
     Fq t = Fq::mul_hot(x.a, x.b);
     Fq2 r; r.a = Fq::mul_hot(x.a + x.b, x.a - x.b); r.b = t.dbl(); return r;
   }
+#ifdef ZKFL_LAZY_REDUCTION
   // Karatsuba with lazy reduction: three 512-bit products, two Montgomery reductions
   static ZK_HD_NOINLINE Fq2 mul_lazy_call(Fq2 x, Fq2 y) {
     Fq::Wide aa = Fq::mul_wide(x.a, y.a), bb = Fq::mul_wide(x.b, y.b);
@@ -360,6 +361,7 @@ struct alignas(16) Fq2 {
     r.b = Fq::redc(Fq::wide_sub(Fq::wide_sub(ss, aa), bb));
     return r;
   }
+#endif
   static ZK_HD Fq2 mul_hot(const Fq2& x, const Fq2& y) {
 #ifndef ZKFL_LAZY_REDUCTION
     Fq aa = Fq::mul_hot(x.a, y.a), bb = Fq::mul_hot(x.b, y.b), s = Fq::mul_hot(x.a + x.b, y.a + y.b);
