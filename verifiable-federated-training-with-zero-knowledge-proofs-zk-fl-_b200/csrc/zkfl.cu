@@ -88,8 +88,8 @@ struct zkfl_ctx {
   // five MSMs per proof batch (A, C, B1, H on G1; B2 on G2): own bucket / reduction buffers each, so the
   // latency-bound bucket reduction of one MSM runs on `side` while the next MSM accumulates on `stream`
   DevBuf buckets[5], Rs[5], Ts[5], lvl2[5], win[5];
-  cudaStream_t side = nullptr;
-  cudaEvent_t ev_acc[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}, ev_done = nullptr;
+  cudaStream_t side[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // one per MSM slot: the reductions are latency-bound and run concurrently
+  cudaEvent_t ev_acc[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}, ev_red[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   DevBuf res_g1, res_g2, t_g1, t_g2, pis, var, proofs, pubs, bad;
   DevBuf msm_sc, msm_out, mask_w, mask_wb, mask_h, part_out, part_in;
   cudaEvent_t t0 = nullptr, t1 = nullptr, ev_join = nullptr;
@@ -361,10 +361,12 @@ static int prove_from_device_witness(zkfl_ctx* c, const zkfl_zkey* z, const Fr* 
   for (int slot = 0; slot < 3; slot++) TRY(msm_reserve_reduce(c, sw, slot, sizeof(G1Xyzz)));
   TRY(msm_reserve_reduce(c, sh, 3, sizeof(G1Xyzz)));
   TRY(msm_reserve_reduce(c, sw, 4, sizeof(G2Xyzz)));
-  if (!c->side) {
-    CU(cudaStreamCreate(&c->side));
-    for (int i = 0; i < 5; i++) CU(cudaEventCreate(&c->ev_acc[i]));
-    CU(cudaEventCreate(&c->ev_done));
+  if (!c->side[0]) {
+    for (int i = 0; i < 5; i++) {
+      CU(cudaStreamCreate(&c->side[i]));
+      CU(cudaEventCreate(&c->ev_acc[i]));
+      CU(cudaEventCreate(&c->ev_red[i]));
+    }
   }
   const uint8_t *skip_w = nullptr, *skip_wb = z->skipB.as<uint8_t>(), *skip_h = nullptr;
   if (nparts > 1) {
@@ -379,28 +381,32 @@ static int prove_from_device_witness(zkfl_ctx* c, const zkfl_zkey* z, const Fr* 
   { Stage st(c, "msm_sort_w"); TRY(msm_sort(c, w, skip_w, sw)); }
   TRY(msm_accumulate<Fq>(c, z->pA.as<G1Affine>(), sw, 0, "msm_acc_g1"));
   CU(cudaEventRecord(c->ev_acc[0], c->stream));
-  CU(cudaStreamWaitEvent(c->side, c->ev_acc[0], 0));
-  TRY(msm_reduce<Fq>(c, sw, 0, r1, c->side, "msm_reduce_g1"));
+  CU(cudaStreamWaitEvent(c->side[0], c->ev_acc[0], 0));
+  TRY(msm_reduce<Fq>(c, sw, 0, r1, c->side[0], "msm_reduce_g1"));
+  CU(cudaEventRecord(c->ev_red[0], c->side[0]));
   TRY(msm_accumulate<Fq>(c, z->pC.as<G1Affine>(), sw, 1, "msm_acc_g1"));
   CU(cudaEventRecord(c->ev_acc[1], c->stream));
-  CU(cudaStreamWaitEvent(c->side, c->ev_acc[1], 0));
-  TRY(msm_reduce<Fq>(c, sw, 1, r1 + 2 * (size_t)B, c->side, "msm_reduce_g1"));
+  CU(cudaStreamWaitEvent(c->side[1], c->ev_acc[1], 0));
+  TRY(msm_reduce<Fq>(c, sw, 1, r1 + 2 * (size_t)B, c->side[1], "msm_reduce_g1"));
+  CU(cudaEventRecord(c->ev_red[1], c->side[1]));
   { Stage st(c, "msm_sort_w"); TRY(msm_sort(c, w, skip_wb, sw)); }
   TRY(msm_accumulate<Fq>(c, z->pB1.as<G1Affine>(), sw, 2, "msm_acc_g1"));
   CU(cudaEventRecord(c->ev_acc[2], c->stream));
-  CU(cudaStreamWaitEvent(c->side, c->ev_acc[2], 0));
-  TRY(msm_reduce<Fq>(c, sw, 2, r1 + B, c->side, "msm_reduce_g1"));
+  CU(cudaStreamWaitEvent(c->side[2], c->ev_acc[2], 0));
+  TRY(msm_reduce<Fq>(c, sw, 2, r1 + B, c->side[2], "msm_reduce_g1"));
+  CU(cudaEventRecord(c->ev_red[2], c->side[2]));
   TRY(msm_accumulate<Fq2>(c, z->pB2.as<G2Affine>(), sw, 4, "msm_acc_g2"));
   CU(cudaEventRecord(c->ev_acc[4], c->stream));
-  CU(cudaStreamWaitEvent(c->side, c->ev_acc[4], 0));
-  TRY(msm_reduce<Fq2>(c, sw, 4, r2, c->side, "msm_reduce_g2"));
+  CU(cudaStreamWaitEvent(c->side[4], c->ev_acc[4], 0));
+  TRY(msm_reduce<Fq2>(c, sw, 4, r2, c->side[4], "msm_reduce_g2"));
+  CU(cudaEventRecord(c->ev_red[4], c->side[4]));
   { Stage st(c, "msm_sort_h"); TRY(msm_sort(c, c->hsc.as<Fr>(), skip_h, sh)); }
   TRY(msm_accumulate<Fq>(c, z->pH.as<G1Affine>(), sh, 3, "msm_acc_g1"));
   CU(cudaEventRecord(c->ev_acc[3], c->stream));
-  CU(cudaStreamWaitEvent(c->side, c->ev_acc[3], 0));
-  TRY(msm_reduce<Fq>(c, sh, 3, r1 + 3 * (size_t)B, c->side, "msm_reduce_g1"));
-  CU(cudaEventRecord(c->ev_done, c->side));
-  CU(cudaStreamWaitEvent(c->stream, c->ev_done, 0));
+  CU(cudaStreamWaitEvent(c->side[3], c->ev_acc[3], 0));
+  TRY(msm_reduce<Fq>(c, sh, 3, r1 + 3 * (size_t)B, c->side[3], "msm_reduce_g1"));
+  CU(cudaEventRecord(c->ev_red[3], c->side[3]));
+  for (int i = 0; i < 5; i++) CU(cudaStreamWaitEvent(c->stream, c->ev_red[i], 0));
   if (!finalize) return 0;
   return finalize_from_sums(c, z, rs_dev, B);
 }
@@ -530,11 +536,12 @@ void zkfl_ctx_free(zkfl_ctx* c) {
   for (auto& r : c->pending) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
   if (c->t0) { cudaEventDestroy(c->t0); cudaEventDestroy(c->t1); }
   if (c->ev_join) cudaEventDestroy(c->ev_join);
-  if (c->side) {
-    cudaStreamSynchronize(c->side);
-    for (int i = 0; i < 5; i++) cudaEventDestroy(c->ev_acc[i]);
-    cudaEventDestroy(c->ev_done);
-    cudaStreamDestroy(c->side);
+  for (int i = 0; i < 5; i++) {
+    if (!c->side[i]) continue;
+    cudaStreamSynchronize(c->side[i]);
+    cudaEventDestroy(c->ev_acc[i]);
+    cudaEventDestroy(c->ev_red[i]);
+    cudaStreamDestroy(c->side[i]);
   }
   cudaStreamDestroy(c->stream);
   delete c;
