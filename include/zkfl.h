@@ -72,6 +72,12 @@ void zkfl_r1cs_free(zkfl_r1cs* r);
 int zkfl_wtns_calculate_batch(zkfl_ctx* ctx, const zkfl_circuit* c, const zkfl_r1cs* r1cs, const uint8_t* inputs,
                               int B, uint8_t* wtns_out, uint32_t* first_bad);
 int zkfl_r1cs_check_batch(zkfl_ctx* ctx, const zkfl_r1cs* r1cs, const uint8_t* wtns, int B, uint32_t* first_bad);
+/* Runs a witness program for B instances and returns only `n_sel` selected wires (out: B x n_sel field elements).
+ * This is how the OFF-circuit commitment pipeline of the reference (vectorHash / buildMerkleTree / derivePairwiseMask,
+ * tests/full_system_simulation.mjs:139-238, computed there with circomlibjs on the CPU) runs on the GPU: the commitments
+ * of all clients are the wires of a "commitment program" compiled by the same front-end (zkfl_b200/commitments.py). */
+int zkfl_wtns_eval_wires(zkfl_ctx* ctx, const zkfl_circuit* c, const uint8_t* inputs, int B, const uint32_t* wires,
+                         uint32_t n_sel, uint8_t* out);
 
 /* ---- prove: `snarkjs groth16 prove zkey wtns proof.json public.json`
  *      (tests/full_system_simulation.mjs:773-775 and five more call sites), batched ---- */

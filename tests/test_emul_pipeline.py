@@ -147,3 +147,27 @@ def test_c_abi_argument_and_format_errors(emul_prover):
     assert lib.zkfl_zkey_load(ctx, None, 0, ctypes.byref(h)) != 0 and lib.zkfl_last_error()
     assert lib.zkfl_groth16_prove_batch(ctx, Z.handle, None, None, 1, None, None) != 0
     circ.close(); other.close(); Z.close()
+
+
+def test_commitment_pipeline_matches_the_reference_helpers(emul_prover):
+    """the off-circuit commitments (Merkle tree, root_D/root_W/root_G/root_K, PRF masks) computed by the batched evaluator
+    equal the oracle's restatement of the reference's JavaScript helpers for the simulation's clients"""
+    import bn254_ref as bn
+    from zkfl_b200 import commitments
+    clients = I.simulation_clients(3)
+    req = []
+    for c in clients:
+        c.training_input([3, -2, 0, 7])
+        peers = [j for j in (1, 2, 3) if j != c.id]
+        req.append({"features": c.features, "labels": c.labels, "weights": c.weights, "gradient": c.gradient, "client_id": c.id,
+                    "round": c.ROUND, "master_key": bn.poseidon([c.id, 12345]), "peer_ids": peers,
+                    "shared_keys": [bn.poseidon([min(c.id, j), max(c.id, j), 12345]) for j in peers]})
+    got = commitments.compute(emul_prover, req, 8, 4, 3)
+    for c, r, g in zip(clients, req, got):
+        tree = bn.build_merkle_tree([bn.vector_hash(f + [l]) for f, l in zip(c.features, c.labels)], 3)
+        assert g["tree"] == tree and g["root_D"] == c.root_d
+        assert g["root_W"] == bn.weight_commitment(c.weights) == c.root_w
+        assert g["root_G"] == bn.gradient_commitment([x % bn.R for x in c.gradient], c.id, c.ROUND) == c.root_g
+        assert g["root_K"] == bn.key_material_commitment(r["master_key"], r["shared_keys"])
+        for j, key, mask in zip(r["peer_ids"], r["shared_keys"], g["masks"]):
+            assert mask == bn.derive_pairwise_mask(key, c.ROUND, c.id, j, 4)

@@ -232,3 +232,31 @@ def test_scaled_training_circuit_2pow20_single_proof_and_split(gpu_prover):
     assert sj.groth16.verify(formats.export_verification_key(zk), sig, formats.proof_bytes_to_json(proofs[0]))
     Z.close()
     circ.close()
+
+
+def test_commitment_pipeline_on_gpu_for_1024_clients(gpu_prover):
+    """dataset Merkle trees, commitments and PRF masks of 1024 clients in one batched run; a sample of the
+    clients is compared with the oracle's restatement of the reference's JavaScript helpers."""
+    import time
+    from zkfl_b200 import commitments
+    lcg = I.JsLcg(777)
+    req = []
+    for cid in range(1, 1025):
+        feats = [[lcg.random_int(0, 100) for _ in range(4)] for _ in range(8)]
+        labels = [(i + cid) % 2 for i in range(8)]
+        base = 3 * ((cid - 1) // 3)
+        peers = [base + k for k in (1, 2, 3) if base + k != cid]
+        req.append({"features": feats, "labels": labels, "weights": [lcg.random_int(-1000, 999) for _ in range(4)],
+                    "gradient": [lcg.random_int(-50, 49) for _ in range(4)], "client_id": cid, "round": 1,
+                    "master_key": 1000 + 111 * cid, "peer_ids": peers, "shared_keys": [cid * 7 + j for j in peers]})
+    t = time.time()
+    got = commitments.compute(gpu_prover, req, 8, 4, 3)
+    print(f"commitments of 1024 clients: {time.time() - t:.2f} s (host packing included)")
+    for idx in (0, 1, 511, 1023):
+        r, g = req[idx], got[idx]
+        tree = bn.build_merkle_tree([bn.vector_hash(f + [l]) for f, l in zip(r["features"], r["labels"])], 3)
+        assert g["tree"] == tree
+        assert g["root_W"] == bn.weight_commitment(r["weights"])
+        assert g["root_G"] == bn.gradient_commitment([x % bn.R for x in r["gradient"]], r["client_id"], 1)
+        assert g["root_K"] == bn.key_material_commitment(r["master_key"], r["shared_keys"])
+        assert g["masks"][1] == bn.derive_pairwise_mask(r["shared_keys"][1], 1, r["client_id"], r["peer_ids"][1], 4)

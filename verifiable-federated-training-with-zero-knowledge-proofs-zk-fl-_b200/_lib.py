@@ -14,7 +14,7 @@ DEFAULT_PATH = os.path.join(_HERE, "libzkfl.so")
 SYMBOLS = [
     "zkfl_last_error", "zkfl_version", "zkfl_ctx_create", "zkfl_ctx_free", "zkfl_circuit_load",
     "zkfl_circuit_free", "zkfl_circuit_info", "zkfl_zkey_load", "zkfl_zkey_free", "zkfl_zkey_info",
-    "zkfl_r1cs_load", "zkfl_r1cs_free", "zkfl_wtns_calculate_batch", "zkfl_r1cs_check_batch",
+    "zkfl_r1cs_load", "zkfl_r1cs_free", "zkfl_wtns_calculate_batch", "zkfl_r1cs_check_batch", "zkfl_wtns_eval_wires",
     "zkfl_groth16_prove_batch", "zkfl_groth16_full_prove_batch", "zkfl_full_prove_stage",
     "zkfl_full_prove_run", "zkfl_full_prove_fetch", "zkfl_g1_msm", "zkfl_g2_msm", "zkfl_msm_bases_load",
     "zkfl_msm_bases_free", "zkfl_msm_run", "zkfl_g1_mul_generator", "zkfl_g2_mul_generator",
@@ -59,6 +59,7 @@ def load(path: str | None = None):
         "zkfl_r1cs_load": (i, [vp, vp, sz, pp]), "zkfl_r1cs_free": (None, [vp]),
         "zkfl_wtns_calculate_batch": (i, [vp, vp, vp, vp, i, vp, vp]),
         "zkfl_r1cs_check_batch": (i, [vp, vp, vp, i, vp]),
+        "zkfl_wtns_eval_wires": (i, [vp, vp, vp, i, vp, ctypes.c_uint32, vp]),
         "zkfl_groth16_prove_batch": (i, [vp, vp, vp, vp, i, vp, vp]),
         "zkfl_groth16_full_prove_batch": (i, [vp, vp, vp, vp, vp, i, vp, vp]),
         "zkfl_full_prove_stage": (i, [vp, vp, vp, vp, vp, i]),

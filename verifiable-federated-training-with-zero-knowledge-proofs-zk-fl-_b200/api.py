@@ -136,6 +136,15 @@ class Prover:
         sz = 32 * circuit.n_wires
         return [out.raw[b * sz:(b + 1) * sz] for b in range(B)]
 
+    def eval_wires(self, circuit: Circuit, packed_inputs: bytes, wires: list[int]) -> list[list[int]]:
+        """runs the program for every instance and returns the selected wires as Python ints, one list per instance"""
+        B = len(packed_inputs) // (32 * circuit.n_inputs)
+        sel = (ctypes.c_uint32 * len(wires))(*wires)
+        out = ctypes.create_string_buffer(32 * len(wires) * B)
+        self._check(self.lib.zkfl_wtns_eval_wires(self.ctx, circuit.handle, _lib.as_ptr(packed_inputs), B, sel, len(wires), out))
+        raw, n = out.raw, len(wires)
+        return [[int.from_bytes(raw[32 * (b * n + k):32 * (b * n + k + 1)], "little") for k in range(n)] for b in range(B)]
+
     def check_witness(self, circuit: Circuit, wtns: list[bytes]):
         B = len(wtns)
         bad = (ctypes.c_uint32 * B)()

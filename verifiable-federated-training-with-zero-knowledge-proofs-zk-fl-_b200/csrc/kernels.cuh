@@ -42,6 +42,15 @@ ZK_GLOBAL void k_soa_to_aos(const Fr* __restrict__ src, Fr* __restrict__ dst, ui
   dst[(size_t)b * n_elem + e] = src[(size_t)e * B + b];
 }
 
+// selected wires of the device witness [n_wires][B] -> host layout [b][k] (used to read commitments out of a program run)
+ZK_GLOBAL void k_gather_wires(const Fr* __restrict__ w, const uint32_t* __restrict__ wires, uint32_t n_sel, uint32_t B,
+                              Fr* __restrict__ out) {
+  size_t tid = ZK_TID;
+  if (tid >= (size_t)n_sel * B) return;
+  uint32_t k = (uint32_t)(tid / B), b = (uint32_t)(tid % B);
+  out[(size_t)b * n_sel + k] = w[(size_t)ZK_LDG(wires + k) * B + b];
+}
+
 // ================================================================================ W1: batched witness evaluator
 struct PoseidonDev {
   uint32_t rounds, rp;

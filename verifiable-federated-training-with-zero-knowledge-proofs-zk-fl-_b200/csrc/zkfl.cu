@@ -817,6 +817,24 @@ int zkfl_wtns_calculate_batch(zkfl_ctx* c, const zkfl_circuit* k, const zkfl_r1c
   CU(cudaStreamSynchronize(c->stream));
   return rc;
 }
+// runs the program and returns only the selected wires (B x n_sel field elements); the witness stays in HBM
+int zkfl_wtns_eval_wires(zkfl_ctx* c, const zkfl_circuit* k, const uint8_t* inputs, int B, const uint32_t* wires, uint32_t n_sel,
+                         uint8_t* out) {
+  if (!c || !k || !inputs || !wires || !out || B <= 0 || n_sel == 0) return fail(ZKFL_ERR_ARG, "bad argument");
+  for (uint32_t i = 0; i < n_sel; i++) if (wires[i] >= k->n_wires) return fail(ZKFL_ERR_ARG, "wire index out of range");
+  for (size_t i = 0; i < (size_t)B * k->n_inputs; i++)
+    if (!fr_bytes_lt_mod(inputs + 32 * i)) return fail(ZKFL_ERR_ARG, "input not reduced mod r");
+  CU(cudaSetDevice(c->device));
+  TRY(run_witness(c, k, inputs, (uint32_t)B));
+  TRY(c->bad.reserve((size_t)n_sel * 4));
+  TRY(c->aos.reserve((size_t)n_sel * B * sizeof(Fr)));
+  CU(cudaMemcpyAsync(c->bad.p, wires, (size_t)n_sel * 4, cudaMemcpyHostToDevice, c->stream));
+  ZK_LAUNCH(k_gather_wires, (size_t)n_sel * B, 256, c->stream, c->w.as<Fr>(), c->bad.as<uint32_t>(), n_sel, (uint32_t)B, c->aos.as<Fr>());
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(out, c->aos.p, (size_t)n_sel * B * sizeof(Fr), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
 int zkfl_r1cs_check_batch(zkfl_ctx* c, const zkfl_r1cs* r, const uint8_t* wtns, int B, uint32_t* first_bad) {
   if (!c || !r || !wtns || B <= 0) return fail(ZKFL_ERR_ARG, "bad argument");
   CU(cudaSetDevice(c->device));
