@@ -7,8 +7,10 @@ across GPUs with no data-path collective (weak scaling: B proofs per rank).
 
   value : proofs/s with inputs already resident in HBM (device-event timed)
   e2e   : proofs/s through the C ABI full-prove call with pinned HOST buffers (H2D/D2H inside the timed region)
-  roofline : the dominant kernel (bucket accumulation of the five MSMs) against the measured IMAD rate;
-             roofline_hbm: the NTT stage against the measured HBM copy bandwidth
+  roofline : the dominant kernel (G1 bucket accumulation) against the live-measured rate of fused 32x32->64
+             multiply-accumulates (the integer pipe is the bound; no dense contraction exists on this path);
+             roofline_hbm: the NTT stage against the measured HBM copy bandwidth (MEASURED_PEAKS.json)
+  msm_g1_2pow20 : BASELINE.json's second metric, one 2^20-point G1 MSM
   cpu_baseline : the C++ oracle (restatement of snarkjs' algorithm) on the box's host cores, bounded sample
 
 `--impl reference` times the CPU arm alone: snarkjs itself cannot run here (no Node.js on the image), so it is

@@ -8,9 +8,11 @@
 // are warp-uniform broadcast loads.  Bases (zkey points) are shared by all proofs of a batch and
 // stay L2-resident (a few MB per circuit).
 //
-// All kernels are sync-free one-thread-per-item kernels: the bound is the integer pipe (IMAD) for
-// the group law / Montgomery products and HBM for the NTT passes; tensor cores do not apply
-// (no dense contraction anywhere on the path).
+// All kernels are sync-free one-thread-per-item kernels (which is also what lets the CPU test-suite run the same
+// sources as a host emulation): the bound is the integer pipe (fused IMAD.WIDE multiply-accumulates) for the group
+// law, the Montgomery products and -- at the batch sizes used -- even the NTT passes; tensor cores do not apply
+// (no dense contraction anywhere on the path). Balance comes from the work decomposition (fixed-size chunks of the
+// bucket-sorted lists, dependency levels of the witness program), not from intra-CTA cooperation.
 #pragma once
 #include "bn254.cuh"
 
