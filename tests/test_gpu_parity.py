@@ -260,3 +260,74 @@ def test_commitment_pipeline_on_gpu_for_1024_clients(gpu_prover):
         assert g["root_G"] == bn.gradient_commitment([x % bn.R for x in r["gradient"]], r["client_id"], 1)
         assert g["root_K"] == bn.key_material_commitment(r["master_key"], r["shared_keys"])
         assert g["masks"][1] == bn.derive_pairwise_mask(r["shared_keys"][1], 1, r["client_id"], r["peer_ids"][1], 4)
+
+
+def test_odd_batch_sizes_partial_warps(gpu_prover):
+    """B = 1, 33, 65: batch-minor layout with partially filled warps; every proof against the oracle"""
+    cc = build_circuit("sgd_step_quick")
+    circ = gpu_prover.load_circuit(cc)
+    zk = gpu_prover.new_zkey(cc, b"odd")
+    Z = gpu_prover.load_zkey(zk)
+    clients = I.simulation_clients(3)
+    base = []
+    for c in clients:
+        t = c.training_input([0] * 4)
+        base.append({k: v for k, v in t.items() if k not in ("weights", "expectedSummedGrad", "remainder", "root_W")})
+    rnd = random.Random(33)
+    for B in (1, 33, 65):
+        ins = [base[i % 3] for i in range(B)]
+        rs = [(rnd.randrange(bn.R), rnd.randrange(bn.R)) for _ in range(B)]
+        proofs, pubs = gpu_prover.full_prove(circ, Z, ins, rs)
+        ws = gpu_prover.calculate_witness(circ, base)
+        for b in (0, B // 2, B - 1):
+            ref_p, ref_pub = ol.groth16_prove(zk, ws[b % 3], *rs[b])
+            assert proofs[b] == ref_p and pubs[b] == ref_pub, (B, b)
+    Z.close()
+    circ.close()
+
+
+def test_secure_aggregation_batch_of_256(gpu_prover):
+    """BASELINE configs[2]: 256 SecureMaskedUpdate(4,2) client proofs in one batch (federations of three, seeded gradients in
+    [-50, 49] as tests/test_secure_aggregation.mjs:151); all verified, a sample bit-exact against the oracle, masks cancel."""
+    import time
+    from zkfl_b200 import commitments, formats
+    from zkfl_b200 import snarkjs as sj
+    n = 255   # 85 federations of three
+    lcg = I.JsLcg(4242)
+    req = []
+    for cid in range(1, n + 1):
+        base = 3 * ((cid - 1) // 3)
+        peers = [base + k for k in (1, 2, 3) if base + k != cid]
+        req.append({"features": [[0] * 4] * 8, "labels": [0] * 8, "weights": [0] * 4, "gradient": [lcg.random_int(-50, 49) for _ in range(4)],
+                    "client_id": cid, "round": 1, "master_key": 1000 + 111 * cid, "peer_ids": peers,
+                    "shared_keys": [bn.poseidon([min(cid, j), max(cid, j), 12345]) for j in peers]})
+    com = commitments.compute(gpu_prover, req, 8, 4, 3)      # root_G, root_K and the PRF masks of all clients on the GPU
+    root_d, root_w = bn.poseidon([12345]), bn.poseidon([67890])  # test_secure_aggregation.mjs:275-276
+    ins = []
+    for r, c in zip(req, com):
+        masked = [g % bn.R for g in r["gradient"]]
+        for j, mask in zip(r["peer_ids"], c["masks"]):
+            masked = [(m + x) % bn.R if r["client_id"] < j else (m - x) % bn.R for m, x in zip(masked, mask)]
+        r["masked"] = masked
+        ins.append({"client_id": r["client_id"], "round": 1, "root_D": root_d, "root_G": c["root_G"], "root_W": root_w, "root_K": c["root_K"],
+                    "tauSquared": 100000000, "masked_update": masked, "peer_ids": r["peer_ids"], "gradient": r["gradient"],
+                    "master_key": r["master_key"], "shared_keys": r["shared_keys"]})
+    for f in range(0, n, 3):   # the pairwise masks cancel inside every federation (test_secure_aggregation.mjs:215-238)
+        for k in range(4):
+            assert sum(req[f + i]["masked"][k] for i in range(3)) % bn.R == sum(req[f + i]["gradient"][k] for i in range(3)) % bn.R
+    cc = build_circuit("secure_masked_update")
+    circ = gpu_prover.load_circuit(cc)
+    zk = gpu_prover.new_zkey(cc, b"secagg256")
+    Z = gpu_prover.load_zkey(zk)
+    ws = gpu_prover.calculate_witness(circ, ins)            # every === holds for all 255 clients
+    rs = [(i + 1, 1000 + i) for i in range(n)]
+    t = time.time()
+    proofs, pubs = gpu_prover.full_prove(circ, Z, ins, rs)
+    print(f"{n} secure_masked_update proofs: {time.time() - t:.3f} s")
+    for b in (0, 100, n - 1):
+        assert (proofs[b], pubs[b]) == ol.groth16_prove(zk, ws[b], *rs[b])
+    vk = formats.export_verification_key(zk)
+    ok = sj.groth16.verifyBatch(vk, [(formats.publics_bytes_to_json(q), formats.proof_bytes_to_json(p)) for p, q in zip(proofs, pubs)])
+    assert all(ok) and len(ok) == n
+    Z.close()
+    circ.close()
