@@ -293,9 +293,11 @@ def main():
     lanes = max(1, min(args.lanes, B))
     provers = [Prover(local_rank) for _ in range(lanes)]
     prover = provers[0]
-    circuits = [p.load_circuit(cc, check_constraints=False) for p in provers]
-    zkeys = [p.load_zkey(zk) for p in provers]
-    circuit, zkey = circuits[0], zkeys[0]
+    # the compiled program and the proving key (coefficients, window-shifted base tables: ~100 MB) are read-only device
+    # data: ONE resident copy is shared by all contexts of this GPU, so the tables stay L2-resident
+    circuit = prover.load_circuit(cc, check_constraints=False)
+    zkey = prover.load_zkey(zk)
+    circuits, zkeys = [circuit] * lanes, [zkey] * lanes
     ins, rs = synth_inputs(circuit, B, args.distinct, rank)
     n_distinct = len({ins[i * 32 * circuit.n_inputs:(i + 1) * 32 * circuit.n_inputs] for i in range(B)})
     # lane k proves proofs [lo_k, hi_k) of the step's batch

@@ -8,8 +8,9 @@
  * Conventions: plain pointers and sizes only; every function returns 0 on success and a negative
  * code on failure (message: zkfl_last_error()); no exception crosses the ABI; the caller owns all
  * buffers; handles are opaque and released by the matching *_free.  A zkfl_ctx is bound to one CUDA
- * device and is NOT thread-safe (one ctx per GPU per host thread).  There is no CPU fallback: without
- * a usable CUDA device zkfl_ctx_create fails.
+ * device and is NOT thread-safe (one ctx per GPU per host thread); zkfl_circuit / zkfl_zkey handles are read-only
+ * after loading and may be used by several contexts of the same device concurrently (one resident copy of the key
+ * tables).  There is no CPU fallback: without a usable CUDA device zkfl_ctx_create fails.
  *
  * Encodings: field elements are 32-byte little-endian canonical integers (the `.wtns` encoding);
  * a proof is 256 bytes: pi_a (x,y) | pi_b (x.c0,x.c1,y.c0,y.c1) | pi_c (x,y), affine canonical
