@@ -49,7 +49,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="zkfl", choices=["zkfl", "reference"])
     ap.add_argument("--batch", type=int, default=int(os.environ.get("ZKFL_BENCH_BATCH", "1024")))
-    ap.add_argument("--lanes", type=int, default=int(os.environ.get("ZKFL_BENCH_LANES", "4")),
+    ap.add_argument("--lanes", type=int, default=int(os.environ.get("ZKFL_BENCH_LANES", "2")),
                     help="contexts (streams) per GPU; the batch of a step is split evenly over them and proved concurrently")
     ap.add_argument("--no-msm", action="store_true", help="skip the standalone 2^20-point G1 MSM measurement")
     ap.add_argument("--distinct", type=int, default=int(os.environ.get("ZKFL_BENCH_DISTINCT", "0")),
@@ -441,9 +441,11 @@ def main():
             "clocks": clocks.summary(),
             "roofline": {"bound": "imad", "kernel": "k_msm_accumulate<Fq> (4 launches per step)", "achieved": achieved,
                          "peak": mac_peak / 1e9, "unit": "GMAC/s", "frac": achieved / (mac_peak / 1e9),
-                         # DRAM bytes per launch from the committed ncu capture (taken at 256 proofs per launch)
-                         "traffic": 613.6e6 if B // lanes == 256 else None,
-                         "traffic_source": "profiles/r01_ncu_full_k_msm_accumulate_chunks_v2.csv (dram read + write per launch, 256 proofs)",
+                         # DRAM bytes per launch from the committed ncu capture (taken at 256 proofs per launch; the traffic
+                         # -- sorted references, keys, bucket writes -- is proportional to the proofs per launch)
+                         "traffic": 613.6e6 * (B // lanes) / 256,
+                         "traffic_source": "profiles/r01_ncu_full_k_msm_accumulate_chunks_v2.csv (dram read + write per launch at 256 "
+                                           "proofs, scaled to the proofs per launch of this run)",
                          "share_of_step": acc_ms / prof_total,
                          "peak_imad32_gops": imad_peak / 1e9, "modmul_per_s": modmul_rate,
                          "note": "MAC = 32x32->64 multiply-accumulate; algorithmic MAC = G1 points x 16 windows x 1360 (SURVEY 8d "
