@@ -32,6 +32,21 @@ def test_tiny_circuit_witness_prove_verify(emul_prover):
     pc.case_prove(emul_prover, cc, pc.tiny_inputs(), [(11, 22), (33, 44), (0, 0)])
 
 
+def test_batch_affine_accumulation(emul_prover, monkeypatch):
+    """The batch-affine bucket accumulation (large-batch path) forced on small cases: degenerate buckets (doubling,
+    P + (-P), infinity bases, runs cut by chunk borders) and a whole proof batch, bit-exact against the oracle."""
+    monkeypatch.setenv("ZKFL_MSM_AFFINE", "1")
+    for chunk, slots in (("4", "3"), ("8", "64")):
+        monkeypatch.setenv("ZKFL_MSM_CHUNK", chunk)
+        monkeypatch.setenv("ZKFL_MSM_AFFINE_K", slots)
+        pc.case_g1_msm_degenerate(emul_prover)
+        for n in (1, 33, 300):
+            pc.case_g1_msm(emul_prover, n)
+        pc.case_g2_msm(emul_prover, 40)
+    cc = pc.tiny_circuit()
+    pc.case_prove(emul_prover, cc, pc.tiny_inputs(), [(11, 22), (33, 44), (0, 0)])
+
+
 def test_failed_constraint_raises_assert(emul_prover):
     cc = pc.tiny_circuit()
     circ = emul_prover.load_circuit(cc)

@@ -83,6 +83,47 @@ def test_prove_sgd_verified_batch(gpu_prover):
     pc.case_prove(gpu_prover, build_circuit("sgd_verified"), ins, rs, python_verify=2)
 
 
+def test_batch_affine_accumulation_forced(gpu_prover, monkeypatch):
+    """The large-batch bucket accumulation (batch-affine, warp-shared inversion) forced on at test sizes: degenerate buckets,
+    G1/G2 MSMs against the oracle, and sgd_verified proofs bit-exact with fixed (r, s) for several chunk/slot shapes."""
+    monkeypatch.setenv("ZKFL_MSM_AFFINE", "1")
+    cc = build_circuit("sgd_verified")
+    ins = I.sgd_verified_batch(4) + I.sgd_verified_batch(1, nonzero_weights=True)
+    rnd = random.Random(10)
+    rs = [(rnd.randrange(bn.R), rnd.randrange(bn.R)) for _ in range(5)]
+    for chunk, slots in (("32", "64"), ("8", "5"), ("16", "32")):
+        monkeypatch.setenv("ZKFL_MSM_CHUNK", chunk)
+        monkeypatch.setenv("ZKFL_MSM_AFFINE_K", slots)
+        pc.case_g1_msm_degenerate(gpu_prover)
+        for n in (1, 33, 1000, 1 << 14):
+            pc.case_g1_msm(gpu_prover, n)
+        pc.case_g2_msm(gpu_prover, 300)
+        pc.case_prove(gpu_prover, cc, ins, rs, python_verify=1 if slots == "64" else 0)
+
+
+def test_large_batch_batch_affine_matches_chunk_kernel(gpu_prover, monkeypatch):
+    """B = 1024 sgd_verified proofs (the bench shape) through the opt-in batch-affine kernel: its proofs equal the default
+    XYZZ chunk kernel's byte for byte, and a sample equals the oracle's."""
+    monkeypatch.setenv("ZKFL_MSM_AFFINE", "1")
+    cc = build_circuit("sgd_verified")
+    circ = gpu_prover.load_circuit(cc)
+    zk = gpu_prover.new_zkey(cc, b"affine-1024")
+    Z = gpu_prover.load_zkey(zk)
+    base = I.sgd_verified_batch(7) + I.sgd_verified_batch(1, nonzero_weights=True)
+    B = 1024
+    ins = [base[i % 8] for i in range(B)]
+    rs = [(i + 1, 7 * i + 3) for i in range(B)]
+    p_aff, pub_aff = gpu_prover.full_prove(circ, Z, ins, rs)
+    monkeypatch.setenv("ZKFL_MSM_AFFINE", "0")
+    p_xyzz, pub_xyzz = gpu_prover.full_prove(circ, Z, ins, rs)
+    assert p_aff == p_xyzz and pub_aff == pub_xyzz
+    ws = gpu_prover.calculate_witness(circ, base)
+    for b in (0, 511, 1023):
+        assert (p_aff[b], pub_aff[b]) == ol.groth16_prove(zk, ws[b % 8], *rs[b])
+    Z.close()
+    circ.close()
+
+
 def test_prove_other_circuits(gpu_prover):
     clients = I.simulation_clients(3)
     for c in clients:

@@ -78,16 +78,42 @@ struct alignas(16) Fp {
     return r;
   }
   friend ZK_HD Fp operator+(const Fp& a, const Fp& b) {
+#ifdef ZKFL_PTX_MUL
+    // carry chains in PTX: 8 adds, 9 subtracts, 8 selects (the portable form below costs about twice the instructions)
+    uint32_t t[8], u[8];
+    t[0] = ptx::add_cc(a.v[0], b.v[0]);
+    ZK_UNROLL for (int i = 1; i < 7; i++) t[i] = ptx::addc_cc(a.v[i], b.v[i]);
+    t[7] = ptx::addc(a.v[7], b.v[7]);                       // a + b < 2^255: no carry out
+    u[0] = ptx::sub_cc(t[0], P::mod(0));
+    ZK_UNROLL for (int i = 1; i < 8; i++) u[i] = ptx::subc_cc(t[i], P::mod(i));
+    const uint32_t borrow = ptx::subc(0, 0);                // all ones when t < p
+    Fp r;
+    ZK_UNROLL for (int i = 0; i < 8; i++) r.v[i] = borrow ? t[i] : u[i];
+    return r;
+#else
     uint32_t t[8]; uint64_t c = 0;
     ZK_UNROLL for (int i = 0; i < 8; i++) { c += (uint64_t)a.v[i] + b.v[i]; t[i] = (uint32_t)c; c >>= 32; }
     return reduce_once(t);  // a + b < 2^255: no carry out
+#endif
   }
   friend ZK_HD Fp operator-(const Fp& a, const Fp& b) {
+#ifdef ZKFL_PTX_MUL
+    uint32_t t[8];
+    t[0] = ptx::sub_cc(a.v[0], b.v[0]);
+    ZK_UNROLL for (int i = 1; i < 8; i++) t[i] = ptx::subc_cc(a.v[i], b.v[i]);
+    const uint32_t borrow = ptx::subc(0, 0);                // all ones when a < b: add p back
+    Fp r;
+    r.v[0] = ptx::add_cc(t[0], P::mod(0) & borrow);
+    ZK_UNROLL for (int i = 1; i < 7; i++) r.v[i] = ptx::addc_cc(t[i], P::mod(i) & borrow);
+    r.v[7] = ptx::addc(t[7], P::mod(7) & borrow);
+    return r;
+#else
     uint32_t t[8]; uint64_t bw = 0;
     ZK_UNROLL for (int i = 0; i < 8; i++) { uint64_t d = (uint64_t)a.v[i] - b.v[i] - bw; t[i] = (uint32_t)d; bw = (d >> 32) & 1; }
     uint32_t msk = (uint32_t)0 - (uint32_t)bw; uint64_t c = 0; Fp r;
     ZK_UNROLL for (int i = 0; i < 8; i++) { c += (uint64_t)t[i] + (P::mod(i) & msk); r.v[i] = (uint32_t)c; c >>= 32; }
     return r;
+#endif
   }
   ZK_HD Fp neg() const { return zero() - *this; }
   ZK_HD Fp dbl() const { return *this + *this; }
@@ -316,6 +342,50 @@ struct alignas(16) Fp {
   ZK_HD Fp to_mont() const { return *this * r2(); }
   ZK_HD Fp from_mont() const { Fp o = zero(); o.v[0] = 1; return *this * o; }
 
+  // Binary extended Euclid (HAC 14.61): ~380 halvings + ~180 subtractions of 256-bit integers, about a fifth of the issue
+  // slots of the Fermat ladder below.  Used for the ONE shared inversion of a batch-affine round (k_msm_accumulate_affine),
+  // where every lane of the warp inverts the same value, so the data-dependent branches are warp-uniform.
+  // Input a*R (Montgomery), output a^-1 * R; 0 -> 0.
+  ZK_HD Fp inv_gcd() const {
+    if (is_zero()) return *this;
+    uint32_t u[8], w[8], x1[8], x2[8];
+    ZK_UNROLL for (int i = 0; i < 8; i++) { u[i] = v[i]; w[i] = P::mod(i); x1[i] = 0; x2[i] = 0; }
+    x1[0] = 1;
+    // invariant: x1 * (aR) = u, x2 * (aR) = w  (mod p); all four stay below p
+    auto is_one = [](const uint32_t* a) { uint32_t o = a[0] ^ 1u; ZK_UNROLL for (int i = 1; i < 8; i++) o |= a[i]; return o == 0; };
+    auto shr1 = [](uint32_t* a, uint32_t top) {
+      ZK_UNROLL for (int i = 0; i < 7; i++) a[i] = (a[i] >> 1) | (a[i + 1] << 31);
+      a[7] = (a[7] >> 1) | (top << 31);
+    };
+    auto halve_mod = [&](uint32_t* a) {   // a / 2 mod p
+      uint32_t msk = (uint32_t)0 - (a[0] & 1u); uint64_t c = 0;
+      ZK_UNROLL for (int i = 0; i < 8; i++) { c += (uint64_t)a[i] + (P::mod(i) & msk); a[i] = (uint32_t)c; c >>= 32; }
+      shr1(a, (uint32_t)c);
+    };
+    auto sub_to = [](uint32_t* a, const uint32_t* b) -> uint32_t {   // a -= b, returns the borrow
+      uint64_t bw = 0;
+      ZK_UNROLL for (int i = 0; i < 8; i++) { uint64_t d = (uint64_t)a[i] - b[i] - bw; a[i] = (uint32_t)d; bw = (d >> 32) & 1; }
+      return (uint32_t)bw;
+    };
+    auto sub_mod = [&](uint32_t* a, const uint32_t* b) {              // a = a - b mod p
+      uint32_t msk = (uint32_t)0 - sub_to(a, b); uint64_t c = 0;
+      ZK_UNROLL for (int i = 0; i < 8; i++) { c += (uint64_t)a[i] + (P::mod(i) & msk); a[i] = (uint32_t)c; c >>= 32; }
+    };
+    auto geq = [](const uint32_t* a, const uint32_t* b) {
+      uint64_t bw = 0;
+      ZK_UNROLL for (int i = 0; i < 8; i++) { uint64_t d = (uint64_t)a[i] - b[i] - bw; bw = (d >> 32) & 1; }
+      return bw == 0;
+    };
+    ZK_NOUNROLL while (!is_one(u) && !is_one(w)) {
+      ZK_NOUNROLL while (!(u[0] & 1u)) { shr1(u, 0); halve_mod(x1); }
+      ZK_NOUNROLL while (!(w[0] & 1u)) { shr1(w, 0); halve_mod(x2); }
+      if (geq(u, w)) { sub_to(u, w); sub_mod(x1, x2); } else { sub_to(w, u); sub_mod(x2, x1); }
+    }
+    Fp r; const bool from_u = is_one(u);
+    ZK_UNROLL for (int i = 0; i < 8; i++) r.v[i] = from_u ? x1[i] : x2[i];
+    // r = (aR)^-1; wanted a^-1 * R = r * R^2 = montmul(r, R^3)
+    return r * (r2() * r2());
+  }
   ZK_HD Fp inv() const {  // Fermat, exponent p - 2 (setup / affine conversion only)
     Fp r = one();
     ZK_NOUNROLL for (int i = 253; i >= 0; i--) {
@@ -371,6 +441,7 @@ struct alignas(16) Fq2 {
   }
   static ZK_HD Fq2 diff_of_products(const Fq2& a, const Fq2& b, const Fq2& c, const Fq2& d) { return mul_hot(a, b) - mul_hot(c, d); }
   ZK_HD Fq2 inv() const { Fq d = (a.sqr() + b.sqr()).inv(); Fq2 r; r.a = a * d; r.b = (b * d).neg(); return r; }
+  ZK_HD Fq2 inv_gcd() const { Fq d = (a.sqr() + b.sqr()).inv_gcd(); Fq2 r; r.a = a * d; r.b = (b * d).neg(); return r; }
   ZK_HD Fq2 from_mont() const { Fq2 r; r.a = a.from_mont(); r.b = b.from_mont(); return r; }
 };
 
@@ -470,6 +541,21 @@ template <class F> ZK_HD Xyzz<F> xyzz_scalar_mul(const Xyzz<F>& p, const uint32_
 
 ZK_HD Fq to_mont_any(const Fq& x) { return x.to_mont(); }
 ZK_HD Fq2 to_mont_any(const Fq2& x) { Fq2 r; r.a = x.a.to_mont(); r.b = x.b.to_mont(); return r; }
+
+// ------------------------------------------------------------------------------ warp exchange of field elements (device)
+#if !defined(ZKFL_EMUL)
+enum { ZK_SHFL_UP = 0, ZK_SHFL_DOWN = 1, ZK_SHFL_IDX = 2 };
+template <int MODE> __device__ __forceinline__ Fq warp_shfl(const Fq& x, uint32_t arg) {
+  Fq r;
+  ZK_UNROLL for (int i = 0; i < 8; i++)
+    r.v[i] = MODE == ZK_SHFL_UP ? __shfl_up_sync(0xffffffffu, x.v[i], arg)
+           : MODE == ZK_SHFL_DOWN ? __shfl_down_sync(0xffffffffu, x.v[i], arg) : __shfl_sync(0xffffffffu, x.v[i], (int)arg);
+  return r;
+}
+template <int MODE> __device__ __forceinline__ Fq2 warp_shfl(const Fq2& x, uint32_t arg) {
+  Fq2 r; r.a = warp_shfl<MODE>(x.a, arg); r.b = warp_shfl<MODE>(x.b, arg); return r;
+}
+#endif
 
 typedef Affine<Fq> G1Affine;
 typedef Affine<Fq2> G2Affine;

@@ -28,6 +28,13 @@ static inline void zk_atomic_min_u32(uint32_t* p, uint32_t v) {
 #define ZK_ATOMIC_MIN(p, v) zk_atomic_min_u32((p), (v))
 #endif
 
+// software prefetch of a line that a later iteration gathers (no register cost; a no-op in the host emulation)
+#if defined(__CUDA_ARCH__)
+#define ZK_PREFETCH(ptr) asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr))
+#else
+#define ZK_PREFETCH(ptr) ((void)(ptr))
+#endif
+
 // ================================================================================ layout helpers
 // host layout [b][e] (what .wtns / the C ABI use)  ->  device layout [e][b]
 ZK_GLOBAL void k_aos_to_soa(const Fr* __restrict__ src, Fr* __restrict__ dst, uint32_t n_elem, uint32_t B,
@@ -280,7 +287,16 @@ struct MsmShape {
   uint32_t R;    // bucket sets ("rows") per proof: W (one per window) or 1 (all windows share one set: the bases
                  // table then holds 2^(c*j) * P_i at index j*m + i, so no doublings are needed after the reduction)
   uint32_t cap;  // entries reserved per row in the sorted index list (m, or m*W when R == 1)
+  uint32_t lsS;  // 0: the sorted list of a row is linear. Otherwise it is stored CHUNK-TRANSPOSED for the batch-affine
+                 // accumulation (chunks of S = 1 << lsS entries, cap a multiple of 32*S): entry r of chunk c sits at
+                 // (c/32)*32*S + r*32 + c%32, so the 32 lanes of a warp (32 consecutive chunks) read consecutive words.
 };
+// address of sorted position `pos` inside a row's list region
+ZK_HD uint32_t msm_list_index(const MsmShape& s, uint32_t pos) {
+  if (s.lsS == 0) return pos;
+  const uint32_t S = 1u << s.lsS, chunk = pos >> s.lsS, r = pos & (S - 1);
+  return ((chunk >> 5) << (5 + s.lsS)) + (r << 5) + (chunk & 31u);
+}
 ZK_HD uint32_t scalar_bits(const uint32_t* k, uint32_t pos, uint32_t c) {
   uint32_t word = pos >> 5, off = pos & 31;
   if (word >= 8) return 0;
@@ -365,8 +381,9 @@ ZK_GLOBAL void k_msm_scatter(const Fr* __restrict__ scalars, const uint8_t* __re
     size_t row = s.R == 1 ? (size_t)b : (size_t)b * s.W + j;
     uint32_t pos = ZK_ATOMIC_ADD(cursors + row * s.nb + (mag - 1), 1u);
     uint32_t ref = s.R == 1 ? j * s.m + i : i;
-    sorted[(size_t)row * s.cap + pos] = ref | (d < 0 ? 0x80000000u : 0u);
-    skey[row * s.cap + pos] = (uint16_t)(mag - 1);
+    const size_t at = (size_t)row * s.cap + msm_list_index(s, pos);
+    sorted[at] = ref | (d < 0 ? 0x80000000u : 0u);
+    skey[at] = (uint16_t)(mag - 1);
   }
 }
 // pass 4: BALANCED bucket accumulation. One thread per (row, chunk of S consecutive sorted entries): every thread
@@ -391,11 +408,20 @@ ZK_GLOBAL void k_msm_accumulate_chunks(const Affine<F>* __restrict__ bases, cons
   uint32_t pos1 = pos0 + S < total ? pos0 + S : total;
   const uint32_t* list = sorted + row * s.cap;
   const uint16_t* keys = skey + row * s.cap;
-  uint32_t cur = keys[pos0];
+  uint32_t cur = keys[msm_list_index(s, pos0)];
   bool first = true;
   Xyzz<F> acc = Xyzz<F>::infinity();
+  // one entry of lookahead: the next key / list word are loaded, and the next base prefetched, while this entry's mixed add runs
+  uint32_t k_next = cur, e_next = list[msm_list_index(s, pos0)], e_next2 = 0;
+  if (pos0 + 1 < pos1) e_next2 = list[msm_list_index(s, pos0 + 1)];
   for (uint32_t pos = pos0; pos < pos1; pos++) {
-    uint32_t k = keys[pos];
+    const uint32_t k = k_next, e = e_next;
+    e_next = e_next2;
+    if (pos + 1 < pos1) {
+      ZK_PREFETCH(bases + (e_next & 0x7FFFFFFFu));
+      k_next = keys[msm_list_index(s, pos + 1)];
+      if (pos + 2 < pos1) e_next2 = list[msm_list_index(s, pos + 2)];
+    }
     if (k != cur) {
       // the run of bucket `cur` ends inside this chunk; it is whole unless it began in an earlier chunk
       if (first && off[cur] < pos0) head[tid] = acc; else buckets[row * s.nb + cur] = acc;
@@ -403,7 +429,6 @@ ZK_GLOBAL void k_msm_accumulate_chunks(const Affine<F>* __restrict__ bases, cons
       cur = k;
       first = false;
     }
-    uint32_t e = list[pos];
     xyzz_madd(acc, bases[e & 0x7FFFFFFFu], (e >> 31) != 0);
   }
   bool starts_here = !(first && off[cur] < pos0);
@@ -412,6 +437,177 @@ ZK_GLOBAL void k_msm_accumulate_chunks(const Affine<F>* __restrict__ bases, cons
   else if (first) head[tid] = acc;   // run covers the chunk's first entry (possibly the whole chunk)
   else tail[tid] = acc;              // run started here and continues in the next chunk
 }
+// pass 4, BATCH-AFFINE variant (large batches).  Same decomposition into chunks of S sorted entries and the same outputs
+// (whole buckets written directly, head/tail partials for pass 4b), but the running sums stay AFFINE, and the S additions
+// of a chunk are interleaved with those of the K-1 other chunks of the same thread and of the 32*K chunks of the warp, so
+// that ONE field inversion serves 32*K additions (Montgomery's trick, shared across the warp).
+//   sweep r = 0..S-1 over the thread's K slots (direction alternates):
+//     finish addition r of the slot: 1/d from the prefix product stored by the previous sweep, lambda = (y_P - y_acc)/d,
+//       x3 = lambda^2 - x_acc - x_P, y3 = lambda (x_acc - x3) - y_acc;
+//     prepare addition r+1: d' = x_P' - x3, exclusive prefix product of the d' to scratch;
+//   between sweeps: one inversion of the warp's total product (coop_inverse: warp scans + binary Euclid, warp-uniform).
+// 6 products per addition plus the shared inversion and 12 scan products per K additions, instead of the 10 of the XYZZ
+// mixed add; the price is ~200 B of coalesced scratch traffic per addition (HBM streams, prefetched one slot ahead).
+// Doublings / cancellations / infinities are handled exactly (denominator substituted, never zero).
+// Geometry: a row's list holds cpr = cap/S chunks = cpr32 groups of 32 chunks (one per lane); cpr32 is a multiple of K and a
+// warp owns K consecutive groups of ONE row; slot (group G, lane) of the scratch arrays is G*32 + lane.
+template <class F> ZK_D F coop_inverse(const F& total, uint32_t lane) {
+#ifdef ZKFL_EMUL
+  (void)lane;
+  return total.inv_gcd();   // the emulation runs lanes one after the other: same value, no sharing
+#else
+  F incl = total, suf = total;
+  ZK_UNROLL for (uint32_t off = 1; off < 32; off <<= 1) {
+    F t = warp_shfl<ZK_SHFL_UP>(incl, off), u = warp_shfl<ZK_SHFL_DOWN>(suf, off);
+    F mi = incl * t, ms = suf * u;
+    if (lane >= off) incl = mi;
+    if (lane + off < 32) suf = ms;
+  }
+  F all_inv = warp_shfl<ZK_SHFL_IDX>(incl, 31).inv_gcd();   // same value in every lane: uniform control flow
+  F ep = warp_shfl<ZK_SHFL_UP>(incl, 1), es = warp_shfl<ZK_SHFL_DOWN>(suf, 1);
+  if (lane > 0) all_inv = all_inv * ep;
+  if (lane < 31) all_inv = all_inv * es;
+  return all_inv;
+#endif
+}
+enum { ZK_AFF_KEEP = 0, ZK_AFF_START = 1, ZK_AFF_ADD = 2, ZK_AFF_DBL = 3, ZK_AFF_CANCEL = 4 };
+// what the slot's next addition is, and its (never zero) denominator
+template <class F> ZK_D uint32_t aff_classify(bool newrun, const Affine<F>& p, const Affine<F>& a, F& d) {
+  d = F::one();
+  if (newrun) return ZK_AFF_START;
+  if (p.is_inf()) return ZK_AFF_KEEP;
+  if (a.is_inf()) return ZK_AFF_START;
+  F dx = p.x - a.x;
+  if (!dx.is_zero()) { d = dx; return ZK_AFF_ADD; }
+  if (p.y == a.y) { F y2 = p.y.dbl(); if (!y2.is_zero()) { d = y2; return ZK_AFF_DBL; } }
+  return ZK_AFF_CANCEL;
+}
+template <class F> ZK_D Xyzz<F> aff_to_xyzz(const Affine<F>& a) { return Xyzz<F>::from_affine(a); }
+
+template <class F>
+ZK_GLOBAL void k_msm_accumulate_affine(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ sorted,
+                                       const uint16_t* __restrict__ skey, const uint32_t* __restrict__ offsets,
+                                       const uint32_t* __restrict__ counts, MsmShape s, uint32_t K, uint32_t n_rows,
+                                       Affine<F>* __restrict__ acc, F* __restrict__ pre, Xyzz<F>* __restrict__ buckets,
+                                       Xyzz<F>* __restrict__ head, Xyzz<F>* __restrict__ tail) {
+  const size_t tid = ZK_TID;
+  const uint32_t lane = (uint32_t)(tid & 31);
+  const uint32_t S = 1u << s.lsS, cpr = s.cap >> s.lsS, cpr32 = cpr >> 5, wpr = cpr32 / K;   // warps per row
+  const size_t warp = tid >> 5;
+  const bool live = warp < (size_t)n_rows * wpr;
+  const uint32_t row = live ? (uint32_t)(warp / wpr) : 0u;
+  const uint32_t grp0 = live ? (uint32_t)(warp - (size_t)row * wpr) * K : 0u;
+  const uint32_t* off = offsets + (size_t)row * s.nb;
+  const uint32_t* cnt = counts + (size_t)row * s.nb;
+  const uint32_t total = live ? ZK_LDG(off + s.nb - 1) + ZK_LDG(cnt + s.nb - 1) : 0u;
+  const uint32_t gstride = 32u << s.lsS;                           // list entries per group
+  // groups of this warp that still have an entry r: a prefix [0, n_r) of its K groups
+  auto groups_with = [&](uint32_t r) -> uint32_t {
+    if (r >= S || total <= r) return 0u;
+    const uint32_t g = (total - r + gstride - 1) / gstride;        // groups of the row with base position + r < total
+    return g <= grp0 ? 0u : (g - grp0 < K ? g - grp0 : K);
+  };
+  const uint32_t* row_list = sorted + (size_t)row * s.cap;
+  const uint16_t* row_keys = skey + (size_t)row * s.cap;
+  const size_t slot0 = ((size_t)row * cpr32 + grp0) * 32 + lane;
+  F inv = F::one();
+  ZK_NOUNROLL for (uint32_t r = 0; r < S; r++) {
+    const uint32_t n_r = groups_with(r), n_next = groups_with(r + 1);
+    if (n_r == 0) break;
+    const bool up = !(r & 1u);
+    F prod = F::one();
+    // list word of the NEXT slot of the sweep, loaded one iteration early so that its base can be prefetched a full
+    // iteration before it is needed (lanes without an entry there prefetch nothing)
+    uint32_t e_ahead = 0;
+    if (n_r > 1) e_ahead = row_list[(grp0 + (up ? 1u : n_r - 2)) * gstride + (r << 5) + lane];
+    ZK_NOUNROLL for (uint32_t j = 0; j < n_r; j++) {
+      const uint32_t k = up ? j : n_r - 1 - j;
+      const uint32_t at = (grp0 + k) * gstride + (r << 5) + lane;  // chunk-transposed list address of entry r
+      const size_t slot = slot0 + (size_t)k * 32;
+      const uint32_t chunk = ((grp0 + k) << 5) + lane, pos0 = chunk << s.lsS, pos = pos0 + r;
+      const bool active = pos < total;
+      const bool next_grp = k < n_next;                            // warp-uniform: this group also takes part in sweep r+1
+      const bool next_lane = next_grp && pos + 1 < total;
+      // ---- prefetch for the following slot of this sweep
+      if (j + 1 < n_r) {
+        const size_t slot_n = up ? slot + 32 : slot - 32;
+        const uint32_t pos_n = up ? pos + (gstride << 0) : pos - gstride;   // same lane and r, next group: S*32 positions away
+        if (pos_n < total) ZK_PREFETCH(bases + (e_ahead & 0x7FFFFFFFu));
+        if (j + 2 < n_r) e_ahead = row_list[up ? at + 2 * gstride : at - 2 * gstride];
+        if (r) { ZK_PREFETCH(acc + slot_n); ZK_PREFETCH(pre + slot_n); }
+      }
+      // ---- loads of this slot
+      uint32_t key = 0, prevkey = 0, key2 = 0, e = 0, e2 = 0;
+      if (active) {
+        key = row_keys[at];
+        prevkey = r ? row_keys[at - 32] : key;
+        e = row_list[at];
+        if (next_lane) { key2 = row_keys[at + 32]; e2 = row_list[at + 32]; }
+      }
+      const bool newrun = r == 0 || key != prevkey;
+      const bool next_same = next_lane && key2 == key;             // entry r+1 continues this run: a real addition
+      F d = F::one();
+      uint32_t mode = ZK_AFF_KEEP;
+      Affine<F> p, a;
+      if (active) {
+        p = bases[e & 0x7FFFFFFFu];
+        if (next_same) ZK_PREFETCH(bases + (e2 & 0x7FFFFFFFu));
+        if (e >> 31) p.y = p.y.neg();
+        if (r) a = acc[slot];
+        mode = aff_classify(newrun, p, a, d);
+      }
+      // ---- finish addition r
+      F dinv = inv;
+      if (r) {                                                     // sweep 0 only starts sums: nothing to invert
+        dinv = F::mul_hot(inv, pre[slot]);
+        inv = F::mul_hot(inv, d);
+      }
+      if (active) {
+        const size_t hidx = (size_t)row * cpr + chunk;
+        if (newrun && r) {   // the run of `prevkey` ended with the previous entry: whole iff it began inside this chunk
+          if (off[prevkey] < pos0) head[hidx] = aff_to_xyzz(a); else buckets[(size_t)row * s.nb + prevkey] = aff_to_xyzz(a);
+        }
+        if (mode == ZK_AFF_START) a = p;
+        else if (mode == ZK_AFF_CANCEL) { a.x = F::zero(); a.y = F::zero(); }
+        else if (mode == ZK_AFF_ADD) {
+          const F lam = F::mul_hot(p.y - a.y, dinv);
+          const F x3 = F::sqr_hot(lam) - a.x - p.x;
+          a.y = F::mul_hot(lam, a.x - x3) - a.y;
+          a.x = x3;
+        } else if (mode == ZK_AFF_DBL) {
+          F xx = a.x.sqr();
+          const F lam = (xx.dbl() + xx) * dinv;
+          const F x3 = lam.sqr() - a.x.dbl();
+          a.y = lam * (a.x - x3) - a.y;
+          a.x = x3;
+        }
+        const uint32_t pos1 = pos0 + S < total ? pos0 + S : total;
+        if (pos + 1 == pos1) {   // last entry of the chunk: flush the run it belongs to
+          const uint32_t st = off[key];
+          if (st >= pos0 && st + cnt[key] <= pos1) buckets[(size_t)row * s.nb + key] = aff_to_xyzz(a);
+          else if (st <= pos0) head[hidx] = aff_to_xyzz(a);   // the run covering the chunk's first entry
+          else tail[hidx] = aff_to_xyzz(a);                    // began inside this chunk, continues in the next
+        } else if (mode != ZK_AFF_KEEP) {
+          acc[slot] = a;
+        }
+      }
+      // ---- prepare addition r + 1: its denominator joins the prefix products of the next sweep (opposite direction)
+      if (next_grp) {
+        F d2 = F::one();
+        if (next_same) {
+          Affine<F> p2 = bases[e2 & 0x7FFFFFFFu];
+          if (e2 >> 31) p2.y = p2.y.neg();
+          aff_classify(false, p2, a, d2);
+        }
+        pre[slot] = prod;
+        prod = F::mul_hot(prod, d2);
+      }
+    }
+    if (n_next == 0) break;
+    inv = coop_inverse(prod, lane);
+  }
+}
+
 // pass 4b: one thread per (row, bucket): empty buckets become infinity, buckets spread over several chunks are
 // summed from the partials those chunks left.
 template <class F>

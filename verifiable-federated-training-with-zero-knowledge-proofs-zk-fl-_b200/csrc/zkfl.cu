@@ -23,7 +23,12 @@ using namespace zk;
 static thread_local std::string g_err;
 static std::atomic<uint64_t> g_launches(0);
 namespace zkrt {
-void note_launch(const char*) { g_launches.fetch_add(1, std::memory_order_relaxed); }
+void note_launch(const char* name) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  static int trace = -1;   // ZKFL_TRACE_LAUNCHES=1: kernel names on stderr (tests use it to see which path ran)
+  if (trace < 0) { const char* v = getenv("ZKFL_TRACE_LAUNCHES"); trace = (v && *v && *v != '0') ? 1 : 0; }
+  if (trace == 1) fprintf(stderr, "[zkfl launch] %s\n", name);
+}
 bool debug_sync() {
   static int on = -1;
   if (on < 0) { const char* v = getenv("ZKFL_DEBUG_SYNC"); on = (v && *v && *v != '0') ? 1 : 0; }
@@ -85,6 +90,7 @@ struct zkfl_ctx {
   // workspace (grow-only)
   DevBuf w, abc, hsc, stage_in, stage_rs, aos;
   DevBuf counts, offsets, cursors, chunk_sums, sorted, skey, head, tail;
+  DevBuf aff_acc, aff_pre;   // batch-affine accumulation: running affine sums and prefix products, [slot group][lane]
   // five MSMs per proof batch (A, C, B1, H on G1; B2 on G2): own bucket / reduction buffers each, so the
   // latency-bound bucket reduction of one MSM runs on `side` while the next MSM accumulates on `stream`
   DevBuf buckets[5], Rs[5], Ts[5], lvl2[5], win[5];
@@ -214,6 +220,8 @@ static uint32_t env_u32(const char* name, uint32_t dflt) {
   const char* v = getenv(name);
   return v && *v ? (uint32_t)strtoul(v, nullptr, 10) : dflt;
 }
+static uint32_t accumulate_chunk() { uint32_t S = env_u32("ZKFL_MSM_CHUNK", 32); return S < 4 ? 4 : S; }
+static uint32_t affine_slots() { uint32_t K = env_u32("ZKFL_MSM_AFFINE_K", 64); return K < 1 ? 1 : (K > 4096 ? 4096 : K); }   // chunks per thread
 // shared = all windows of a proof accumulate into ONE bucket set (bases table precomputed with the window shifts)
 static MsmShape msm_shape(uint32_t m, uint32_t B, bool shared, uint32_t force_c = 0) {
   uint32_t best_c = 4; double best = 1e300;
@@ -228,6 +236,21 @@ static MsmShape msm_shape(uint32_t m, uint32_t B, bool shared, uint32_t force_c 
   MsmShape s; s.m = m; s.B = B; s.c = c; s.W = 254 / c + 1; s.nb = 1u << (c - 1);
   s.R = shared ? 1 : s.W;
   s.cap = shared ? m * s.W : m;
+  s.lsS = 0;
+  // Batch-affine accumulation (k_msm_accumulate_affine): OPT-IN.  Measured on B200 at 1024 sgd_verified proofs it executes
+  // fewer instructions per addition than the XYZZ chunk kernel (2390 vs ~2600) but runs at 22 % FMA-pipe utilisation
+  // against 46 %: 130 registers, long-running warps (tail effect) and the serial latency of the shared inversion leave two
+  // warps per scheduler on average (profiles/r01_ncu_full_k_msm_accumulate_affine.csv), so the XYZZ kernel stays the default.
+  // ZKFL_MSM_AFFINE = 0 / unset: never, 1: always, 2: by size (needs K*S sorted entries per thread to fill the GPU).
+  const uint32_t mode = env_u32("ZKFL_MSM_AFFINE", 0);
+  uint32_t S = accumulate_chunk(), ls = 0;
+  while ((1u << ls) < S) ls++;
+  const double threads = (double)B * s.R * s.cap / ((double)(1u << ls) * affine_slots());
+  if (mode == 1 || (mode != 0 && shared && threads >= 148.0 * 512.0)) {
+    s.lsS = ls;
+    const uint32_t unit = (32u << ls) * affine_slots();   // a warp owns K groups of 32 chunks of ONE row
+    s.cap = (s.cap + unit - 1) / unit * unit;
+  }
   return s;
 }
 // three-level reduction tree over nb = L1 * L2 * N2 buckets
@@ -238,7 +261,6 @@ static ReducePlan reduce_plan(const MsmShape& s) {
   ReducePlan p; p.L1 = 1u << l1; p.L2 = 1u << l2; p.N1 = s.nb >> l1; p.N2 = p.N1 >> l2;
   return p;
 }
-static uint32_t accumulate_chunk() { uint32_t S = env_u32("ZKFL_MSM_CHUNK", 32); return S < 4 ? 4 : S; }
 
 static int msm_sort(zkfl_ctx* c, const Fr* scalars, const uint8_t* skip, const MsmShape& s) {
   size_t rows = (size_t)s.B * s.R;
@@ -264,9 +286,25 @@ template <class F>
 static int msm_accumulate(zkfl_ctx* c, const Affine<F>* bases, const MsmShape& s, int slot, const char* tag) {
   size_t rows = (size_t)s.B * s.R;
   TRY(c->buckets[slot].reserve(rows * s.nb * sizeof(Xyzz<F>)));
-  const uint32_t S = accumulate_chunk(), cpr = (s.cap + S - 1) / S;
+  const uint32_t S = s.lsS ? (1u << s.lsS) : accumulate_chunk(), cpr = (s.cap + S - 1) / S;
   TRY(c->head.reserve(rows * cpr * sizeof(Xyzz<F>)));
   TRY(c->tail.reserve(rows * cpr * sizeof(Xyzz<F>)));
+  if (s.lsS) {
+    const uint32_t K = affine_slots();
+    const size_t n_groups = rows * (cpr >> 5);
+    if ((cpr >> 5) % K != 0 || rows >= 0xFFFFFFFFull) return fail(ZKFL_ERR_ARG, "batch-affine accumulation: bad list geometry");
+    TRY(c->aff_acc.reserve(n_groups * 32 * sizeof(Affine<F>)));
+    TRY(c->aff_pre.reserve(n_groups * 32 * sizeof(F)));
+    Stage st(c, tag);
+    ZK_LAUNCH(k_msm_accumulate_affine<F>, n_groups / K * 32, 128, c->stream, bases, c->sorted.as<uint32_t>(),
+              c->skey.as<uint16_t>(), c->offsets.as<uint32_t>(), c->counts.as<uint32_t>(), s, K, (uint32_t)rows,
+              c->aff_acc.as<Affine<F>>(), c->aff_pre.as<F>(), c->buckets[slot].as<Xyzz<F>>(), c->head.as<Xyzz<F>>(),
+              c->tail.as<Xyzz<F>>());
+    ZK_LAUNCH(k_msm_fixup<F>, rows * s.nb, 128, c->stream, c->offsets.as<uint32_t>(), c->counts.as<uint32_t>(), s, S, cpr,
+              c->head.as<Xyzz<F>>(), c->tail.as<Xyzz<F>>(), c->buckets[slot].as<Xyzz<F>>());
+    CU(cudaGetLastError());
+    return 0;
+  }
   Stage st(c, tag);
   ZK_LAUNCH(k_msm_accumulate_chunks<F>, rows * cpr, 128, c->stream, bases, c->sorted.as<uint32_t>(), c->skey.as<uint16_t>(),
             c->offsets.as<uint32_t>(), c->counts.as<uint32_t>(), s, S, cpr, c->buckets[slot].as<Xyzz<F>>(), c->head.as<Xyzz<F>>(),
