@@ -114,6 +114,18 @@ int zkfl_groth16_finalize(zkfl_ctx* ctx, const zkfl_zkey* z, const uint8_t* part
 int zkfl_groth16_verify(const uint8_t* alpha1, const uint8_t* beta2, const uint8_t* gamma2, const uint8_t* delta2,
                         const uint8_t* ic, const uint8_t* publics, uint32_t n_public, const uint8_t* proof, int* ok);
 
+/* ---- batch verify on the GPU (Server.verifyBalanceProof / verifyTrainingProof /
+ *      verifySecureAggregationProof, tests/full_system_simulation.mjs:848-1131 -- one `snarkjs groth16 verify` child process
+ *      per proof there).  B proofs under ONE verification key, same encodings as zkfl_groth16_verify;
+ *      publics: B x n_public x 32 B, proofs: B x 256 B, ok: B x int32 (1 = valid, 0 = invalid or malformed proof).
+ *      Per proof: vk_x, three Miller loops, and the final exponentiation, spread over threads (csrc/pairing.cuh). ------- */
+int zkfl_groth16_verify_batch(zkfl_ctx* ctx, const uint8_t* alpha1, const uint8_t* beta2, const uint8_t* gamma2,
+                              const uint8_t* delta2, const uint8_t* ic, uint32_t n_public, const uint8_t* publics,
+                              const uint8_t* proofs, int B, int32_t* ok);
+
+/* dev / test hook: intermediate buffers of the last zkfl_groth16_verify_batch ("v_t", "v_g1", "v_g2", "v_flags", "v_f", "v_halves") */
+int zkfl_debug_read(zkfl_ctx* ctx, const char* name, void* out, size_t bytes);
+
 /* ---- standalone multi-scalar multiplication (BASELINE.json: "G1 MSM pts/s at 2^20") ----------- */
 /* bases: n affine points, Montgomery little-endian (zkey point layout, 64 B G1 / 128 B G2);
  * scalars: n x 32 B canonical; out: affine canonical (64 / 128 B). */

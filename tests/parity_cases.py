@@ -118,3 +118,44 @@ def case_prove(P, cc, ins, rs, seed=b"zkfl-test", python_verify=1):
     Z.close()
     circ.close()
     return zk, proofs, pubs
+
+
+def case_verify_batch(P, zk: bytes, proofs, pubs):
+    """GPU (or emulated) batch verifier against the oracle's pairing check and the single-proof host verifier: the valid
+    proofs, and a set of tampered / malformed ones."""
+    import json
+    from zkfl_b200 import formats
+    from zkfl_b200 import snarkjs as sj
+    vkj = export_verification_key(zk)
+    vk = formats.vkey_json_to_bytes(vkj)
+    vko = g16.vkey_from_json(vkj)
+    n = len(proofs)
+    assert P.verify_batch(vk, pubs, proofs) == [True] * n
+    psz = len(pubs[0])
+    q_le = bn.Q.to_bytes(32, "little")
+    bad = []
+    bad.append((pubs[0], proofs[1 % n] if n > 1 and proofs[1] != proofs[0] else proofs[0][:64] + proofs[0][64:192] + proofs[0][:64]))  # another proof
+    one = (int.from_bytes(pubs[0][:32], "little") + 1) % bn.R
+    bad.append((one.to_bytes(32, "little") + pubs[0][32:], proofs[0]))                     # public signal changed
+    bad.append((pubs[0], proofs[0][:192] + proofs[0][:64]))                                   # C replaced by A
+    bad.append((pubs[0], bytes(64) + proofs[0][64:]))                                         # A = infinity
+    bad.append((pubs[0], proofs[0][:32] + (1).to_bytes(32, "little") + proofs[0][64:]))       # A off the curve
+    bad.append((pubs[0], q_le + proofs[0][32:]))                                              # coordinate not reduced mod q
+    bad.append((bn.R.to_bytes(32, "little") + pubs[0][32:], proofs[0]))                       # public signal not reduced mod r
+    bad.append((pubs[0], proofs[0][:64] + bytes(128) + proofs[0][192:]))                      # B = infinity
+    assert all(len(b[0]) == psz and len(b[1]) == 256 for b in bad)
+    mixed_pubs = [b[0] for b in bad] + list(pubs)
+    mixed_proofs = [b[1] for b in bad] + list(proofs)
+    got = P.verify_batch(vk, mixed_pubs, mixed_proofs)
+    assert got == [False] * len(bad) + [True] * n, got
+    # the single-proof host verifier and the oracle agree item by item
+    for k in range(len(mixed_proofs)):
+        sig, pj = formats.publics_bytes_to_json(mixed_pubs[k]), formats.proof_bytes_to_json(mixed_proofs[k])
+        assert sj.groth16.verify(vkj, sig, pj) == got[k], k
+    for k in (1, len(bad)):     # pure-Python pairing: slow, two items
+        assert g16.verify(vko, ol.ints(mixed_pubs[k]), g16.proof_from_bytes(mixed_proofs[k])) == got[k]
+    # snarkjs-shaped entry point, including items it cannot even encode
+    items = [(formats.publics_bytes_to_json(q), formats.proof_bytes_to_json(p)) for p, q in zip(proofs, pubs)]
+    items.append((items[0][0][:-1], items[0][1]))                                             # one signal missing
+    assert sj.groth16.verifyBatch(vkj, items, prover=P) == [True] * n + [False]
+    assert sj.groth16.verifyBatch(json.loads(json.dumps(vkj)), items[:2], device=False) == [True] * min(2, n)

@@ -47,6 +47,14 @@ def test_batch_affine_accumulation(emul_prover, monkeypatch):
     pc.case_prove(emul_prover, cc, pc.tiny_inputs(), [(11, 22), (33, 44), (0, 0)])
 
 
+def test_batch_verifier_matches_oracle_and_host_verifier(emul_prover, monkeypatch):
+    import __graft_entry__ as ge
+    monkeypatch.setenv("ZKFL_LIBRARY_PATH", ge.build_emul())   # the single-proof verifier of the same (emulated) build
+    cc = pc.tiny_circuit()
+    zk, proofs, pubs = pc.case_prove(emul_prover, cc, pc.tiny_inputs(), [(11, 22), (33, 44), (0, 0)], python_verify=0)
+    pc.case_verify_batch(emul_prover, zk, proofs, pubs)
+
+
 def test_failed_constraint_raises_assert(emul_prover):
     cc = pc.tiny_circuit()
     circ = emul_prover.load_circuit(cc)

@@ -169,6 +169,34 @@ def test_product_verifier_agrees_with_oracle(gpu_prover):
     assert not sj.groth16.verify(vkj, formats.publics_bytes_to_json(pubs[1]), swapped)
 
 
+def test_batch_verifier_on_gpu(gpu_prover):
+    """all proofs of a round verified in one GPU pass.  Valid and tampered sgd_verified proofs against the
+    oracle's pairing check and the single-proof host verifier; then 1024 and 3072 proofs (a 1024-client round has 3072) with
+    every 7th one corrupted, timed."""
+    import time
+    from zkfl_b200 import formats
+    cc = build_circuit("sgd_verified")
+    ins = I.sgd_verified_batch(3) + I.sgd_verified_batch(1, nonzero_weights=True)
+    zk, proofs, pubs = pc.case_prove(gpu_prover, cc, ins, [(1, 2), (3, 4), (5, 6), (7, 8)], python_verify=0)
+    pc.case_verify_batch(gpu_prover, zk, proofs, pubs)
+    vk = formats.vkey_json_to_bytes(formats.export_verification_key(zk))
+    for B in (1024, 3072):
+        ps = [proofs[i % 4] for i in range(B)]
+        qs = [pubs[i % 4] for i in range(B)]
+        for i in range(0, B, 7):
+            ps[i] = ps[i][:192] + ps[(i + 1) % B][192:] if i % 14 else ps[i][:64] + proofs[(i + 1) % 4][64:192] + ps[i][192:]
+        expect = [(i % 7 != 0) or ps[i] == proofs[i % 4] for i in range(B)]
+        gpu_prover.verify_batch(vk, qs[:8], ps[:8])      # workspace
+        gpu_prover.prof_enable(True)
+        t = time.time()
+        got = gpu_prover.verify_batch(vk, qs, ps)
+        dt = time.time() - t
+        prof = gpu_prover.prof_read()
+        gpu_prover.prof_enable(False)
+        assert got == expect
+        print(f"verify_batch B={B}: {dt * 1e3:.1f} ms ({B / dt:.0f} proofs/s)", {k: round(v["ms"], 1) for k, v in prof.items() if k.startswith("verify")})
+
+
 def test_split_msm_partials_single_gpu(gpu_prover):
     """the multi-GPU split of one proof (point ranges + gather + add), with the ranks emulated one after another on one GPU"""
     cc = build_circuit("sgd_verified")
@@ -368,7 +396,7 @@ def test_secure_aggregation_batch_of_256(gpu_prover):
     for b in (0, 100, n - 1):
         assert (proofs[b], pubs[b]) == ol.groth16_prove(zk, ws[b], *rs[b])
     vk = formats.export_verification_key(zk)
-    ok = sj.groth16.verifyBatch(vk, [(formats.publics_bytes_to_json(q), formats.proof_bytes_to_json(p)) for p, q in zip(proofs, pubs)])
+    ok = sj.groth16.verifyBatch(vk, [(formats.publics_bytes_to_json(q), formats.proof_bytes_to_json(p)) for p, q in zip(proofs, pubs)], prover=gpu_prover)
     assert all(ok) and len(ok) == n
     Z.close()
     circ.close()

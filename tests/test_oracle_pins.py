@@ -108,3 +108,27 @@ def test_groth16_python_reference_end_to_end_and_cpp_parity(oracle):
     w_bad[3] = 4
     proof2, pub2 = g16.prove(zk, w_bad, r=11, s=22)
     assert not g16.verify(vk, pub2, proof2)
+
+
+def test_final_exponentiation_identities_used_by_the_batch_verifier():
+    """csrc/pairing.cuh avoids the Fq12 inversion and the 2816-bit power: f^((p^12-1)/r) == 1 <=> (frob2(conj f) conj f)^h ==
+    (frob2(f) f)^h with h = (p^4 - p^2 + 1)/r, conj = odd coefficients negated, frob2 = coefficient i times zeta^i.
+    The constants in that header and both maps are checked here against plain powers in the oracle's Fq12."""
+    import random
+    import re
+    Q, R = bn.Q, bn.R
+    src = open(os.path.join(os.path.dirname(__file__), "..", "verifiable-federated-training-with-zero-knowledge-proofs-zk-fl-_b200", "csrc", "pairing.cuh")).read()
+
+    def words(name):
+        body = re.search(name + r"\[\d+\]\s*=\s*\{([^}]*)\}", src).group(1)
+        return sum(int(w.strip().rstrip("u"), 16) << (32 * i) for i, w in enumerate(body.split(",")))
+    zeta, h = words("ZETA"), words("H")
+    w = bn.Fq12([0, 1] + [0] * 10)
+    assert w.pow(Q * Q - 1) == bn.Fq12([zeta] + [0] * 11)            # zeta = xi^((p^2-1)/6) lies in Fq
+    assert w.pow(Q ** 6 - 1) == bn.Fq12([Q - 1] + [0] * 11)          # conj: w -> -w
+    assert (Q ** 4 - Q * Q + 1) % R == 0 and h == (Q ** 4 - Q * Q + 1) // R
+    assert (Q ** 12 - 1) // R == (Q ** 6 - 1) * (Q * Q + 1) * h
+    rnd = random.Random(12)
+    x = bn.Fq12([rnd.randrange(Q) for _ in range(12)])
+    assert bn.Fq12([c * pow(zeta, i, Q) for i, c in enumerate(x.c)]) == x.pow(Q * Q)
+    assert bn.Fq12([c if i % 2 == 0 else -c for i, c in enumerate(x.c)]) == x.pow(Q ** 6)

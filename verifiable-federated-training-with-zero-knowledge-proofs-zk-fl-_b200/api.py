@@ -217,6 +217,21 @@ class Prover:
         self._check(self.lib.zkfl_g2_mul_generator(self.ctx, _lib.as_ptr(sc), n, out))
         return out.raw
 
+    # ---------------------------------------------------------------- batch verification on the device
+    def verify_batch(self, vk: dict, publics: list[bytes], proofs: list[bytes]) -> list[bool]:
+        """vk: formats.vkey_json_to_bytes(vkey.json); publics[b]: n_public*32 B canonical; proofs[b]: 256 B.
+        One GPU pass over all proofs of a round; malformed proofs come back False."""
+        B = len(proofs)
+        if B == 0:
+            return []
+        n_public = vk["n_public"]
+        ok = (ctypes.c_int32 * B)()
+        self._check(self.lib.zkfl_groth16_verify_batch(self.ctx, _lib.as_ptr(vk["alpha1"]), _lib.as_ptr(vk["beta2"]),
+                                                       _lib.as_ptr(vk["gamma2"]), _lib.as_ptr(vk["delta2"]), _lib.as_ptr(vk["ic"]),
+                                                       n_public, _lib.as_ptr(b"".join(publics)) if n_public else None,
+                                                       _lib.as_ptr(b"".join(proofs)), B, ok))
+        return [v == 1 for v in ok]
+
     # ---------------------------------------------------------------- measurement
     def prof_enable(self, on: bool = True):
         self._check(self.lib.zkfl_prof_enable(self.ctx, 1 if on else 0))

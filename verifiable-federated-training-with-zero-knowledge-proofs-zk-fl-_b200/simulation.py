@@ -46,7 +46,7 @@ def run_round(prover, n_clients: int = 3, seed: int = 12345, weights=None, verif
         return vk, [formats.proof_bytes_to_json(p) for p in proofs], [formats.publics_bytes_to_json(q) for q in pubs]
 
     def verify_all(vk, sigs, proofs):
-        return [True] * len(sigs) if not verify else sj.groth16.verifyBatch(vk, list(zip(sigs, proofs)))
+        return [True] * len(sigs) if not verify else sj.groth16.verifyBatch(vk, list(zip(sigs, proofs)), prover=prover)
 
     # phase 3: balance proofs; Server.verifyBalanceProof (:848-880)
     vk, proofs, sigs = prove_phase("balance_unified", [c.balance_input() for c in clients])

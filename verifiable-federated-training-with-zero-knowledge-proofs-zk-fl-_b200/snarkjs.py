@@ -165,9 +165,30 @@ class groth16:
         return _result(proofs[0], pubs[0])
 
     @staticmethod
-    def verifyBatch(vkey: dict, items, threads: int = 0) -> list:
-        """items: [(publicSignals, proof), ...] -> [bool, ...]. The pairing check is host code that releases the GIL, so the
-        proofs of a round are checked on all host cores (the reference runs one `snarkjs groth16 verify` process per proof)."""
+    def verifyBatch(vkey: dict, items, threads: int = 0, prover: Prover | None = None, device: bool = True) -> list:
+        """items: [(publicSignals, proof), ...] -> [bool, ...] (the reference runs one `snarkjs groth16 verify` process per
+        proof).  device=True: all proofs in one pass of the GPU batch verifier (zkfl_groth16_verify_batch) on `prover`'s context
+        (default: the module's); items that cannot be encoded (wrong count of signals, values out of range) are False.
+        device=False: the single-proof host verifier on all host cores (it releases the GIL)."""
+        if isinstance(vkey, str):
+            vkey = json.load(open(vkey))
+        if device:
+            vk = formats.vkey_json_to_bytes(vkey)
+            enc, slots = [], []
+            for k, (sig, proof) in enumerate(items):
+                try:
+                    if len(sig) != vk["n_public"]:
+                        raise ValueError("public signal count")
+                    enc.append((b"".join(int(x).to_bytes(32, "little") for x in sig), formats.proof_json_to_bytes(proof)))
+                    slots.append(k)
+                except (OverflowError, ValueError):
+                    pass
+            res = [False] * len(items)
+            if enc:
+                oks = (prover or _prover()).verify_batch(vk, [e[0] for e in enc], [e[1] for e in enc])
+                for k, v in zip(slots, oks):
+                    res[k] = v
+            return res
         from concurrent.futures import ThreadPoolExecutor
         n = threads or len(os.sched_getaffinity(0))
         with ThreadPoolExecutor(max_workers=max(1, min(n, len(items) or 1))) as ex:
