@@ -443,8 +443,8 @@ def main():
                          "peak": mac_peak / 1e9, "unit": "GMAC/s", "frac": achieved / (mac_peak / 1e9),
                          # DRAM bytes per launch from the committed ncu capture (taken at 256 proofs per launch; the traffic
                          # -- sorted references, keys, bucket writes -- is proportional to the proofs per launch)
-                         "traffic": 613.6e6 * (B // lanes) / 256,
-                         "traffic_source": "profiles/r01_ncu_full_k_msm_accumulate_chunks_v2.csv (dram read + write per launch at 256 "
+                         "traffic": 613.7e6 * (B // lanes) / 256,
+                         "traffic_source": "profiles/r01_ncu_full_k_msm_accumulate_chunks_v4.csv (dram read + write per launch at 256 "
                                            "proofs, scaled to the proofs per launch of this run)",
                          "share_of_step": acc_ms / prof_total,
                          "peak_imad32_gops": imad_peak / 1e9, "modmul_per_s": modmul_rate,
