@@ -134,7 +134,8 @@ class Prover:
         r1 = circuit.r1cs_handle if (check and circuit.r1cs_handle) else None
         self._check(self.lib.zkfl_wtns_calculate_batch(self.ctx, circuit.handle, r1, _lib.as_ptr(packed), B, out, bad))
         sz = 32 * circuit.n_wires
-        return [out.raw[b * sz:(b + 1) * sz] for b in range(B)]
+        raw = memoryview(out)      # `.raw` copies the whole buffer on every access: slice one view instead
+        return [bytes(raw[b * sz:(b + 1) * sz]) for b in range(B)]
 
     def eval_wires(self, circuit: Circuit, packed_inputs: bytes, wires: list[int]) -> list[list[int]]:
         """runs the program for every instance and returns the selected wires as Python ints, one list per instance"""
@@ -167,7 +168,8 @@ class Prover:
         self._check(self.lib.zkfl_groth16_prove_batch(self.ctx, zkey.handle, _lib.as_ptr(b"".join(wtns)),
                                                      _lib.as_ptr(self._pack_rs(rs, B)), B, proofs, pubs))
         psz = 32 * zkey.n_public
-        return ([proofs.raw[256 * b:256 * (b + 1)] for b in range(B)], [pubs.raw[psz * b:psz * (b + 1)] for b in range(B)])
+        praw, qraw = proofs.raw, pubs.raw
+        return ([praw[256 * b:256 * (b + 1)] for b in range(B)], [qraw[psz * b:psz * (b + 1)] for b in range(B)])
 
     def full_prove(self, circuit: Circuit, zkey: Zkey, inputs, rs=None):
         packed = inputs if isinstance(inputs, (bytes, bytearray)) else circuit.pack_inputs(inputs)
@@ -177,7 +179,8 @@ class Prover:
         self._check(self.lib.zkfl_groth16_full_prove_batch(self.ctx, circuit.handle, zkey.handle, _lib.as_ptr(packed),
                                                           _lib.as_ptr(self._pack_rs(rs, B)), B, proofs, pubs))
         psz = 32 * zkey.n_public
-        return ([proofs.raw[256 * b:256 * (b + 1)] for b in range(B)], [pubs.raw[psz * b:psz * (b + 1)] for b in range(B)])
+        praw, qraw = proofs.raw, pubs.raw
+        return ([praw[256 * b:256 * (b + 1)] for b in range(B)], [qraw[psz * b:psz * (b + 1)] for b in range(B)])
 
     def msm_partials(self, zkey: Zkey, wtns: list[bytes], part: int, nparts: int) -> bytes:
         """the five MSM sums over this rank's point range (B x 384 bytes), see zkfl_groth16_msm_partials"""
@@ -190,7 +193,8 @@ class Prover:
         proofs = ctypes.create_string_buffer(256 * B)
         self._check(self.lib.zkfl_groth16_finalize(self.ctx, zkey.handle, _lib.as_ptr(b"".join(partials)), len(partials),
                                                   _lib.as_ptr(self._pack_rs(rs, B)), B, proofs))
-        return [proofs.raw[256 * b:256 * (b + 1)] for b in range(B)]
+        praw = proofs.raw
+        return [praw[256 * b:256 * (b + 1)] for b in range(B)]
 
     # ---------------------------------------------------------------- MSM / setup support
     def g1_msm(self, bases: bytes, scalars: bytes) -> bytes:

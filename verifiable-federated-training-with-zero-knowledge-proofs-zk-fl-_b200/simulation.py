@@ -46,7 +46,12 @@ def run_round(prover, n_clients: int = 3, seed: int = 12345, weights=None, verif
         return vk, [formats.proof_bytes_to_json(p) for p in proofs], [formats.publics_bytes_to_json(q) for q in pubs]
 
     def verify_all(vk, sigs, proofs):
-        return [True] * len(sigs) if not verify else sj.groth16.verifyBatch(vk, list(zip(sigs, proofs)), prover=prover)
+        if not verify:
+            return [True] * len(sigs)
+        t = time.perf_counter()
+        ok = sj.groth16.verifyBatch(vk, list(zip(sigs, proofs)), prover=prover)   # one GPU pass per phase
+        timing["verify_s"] = timing.get("verify_s", 0.0) + time.perf_counter() - t
+        return ok
 
     # phase 3: balance proofs; Server.verifyBalanceProof (:848-880)
     vk, proofs, sigs = prove_phase("balance_unified", [c.balance_input() for c in clients])
@@ -107,5 +112,12 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--clients", type=int, default=3)
     ap.add_argument("--no-verify", action="store_true")
+    ap.add_argument("--repeat", type=int, default=1, help="run the round this many times on one prover (keys cached) and print the last")
+    ap.add_argument("--brief", action="store_true", help="print counts and timings only")
     a = ap.parse_args()
-    print(json.dumps(run_round(Prover(0), a.clients, verify=not a.no_verify), indent=1))
+    P, cache, rep = Prover(0), {}, None
+    for _ in range(max(1, a.repeat)):
+        rep = run_round(P, a.clients, verify=not a.no_verify, cache=cache)
+    if a.brief:
+        rep = {k: rep[k] for k in ("clients", "proofs", "verified", "timing")}
+    print(json.dumps(rep, indent=1))
