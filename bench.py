@@ -425,6 +425,17 @@ def main():
         pubs0 = oracle_lib.ints(bytes(pin_pubs.numpy()[:32 * l].tobytes()))
         verified = groth16_ref.verify(vk, pubs0, groth16_ref.proof_from_bytes(first))
         msm = bench_msm_2pow20(prover, torch) if not args.no_msm else None
+        # ---- the batch verifier on this step's proofs (reported beside the headline, not part of it)
+        from zkfl_b200.formats import vkey_json_to_bytes
+        vkb = vkey_json_to_bytes(export_verification_key(zk))
+        all_p, all_q = bytes(pin_proofs.numpy().tobytes()), bytes(pin_pubs.numpy().tobytes())
+        vp = [all_p[256 * b:256 * (b + 1)] for b in range(B)]
+        vq = [all_q[32 * l * b:32 * l * (b + 1)] for b in range(B)]
+        prover.verify_batch(vkb, vq[:8], vp[:8])
+        prover.verify_batch(vkb, vq, vp)                       # first full-size call allocates the workspace
+        t0 = time.perf_counter()
+        vok = prover.verify_batch(vkb, vq, vp)
+        verify_ms = (time.perf_counter() - t0) * 1e3
         line = {
             "metric": METRIC, "value": world * B * K / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak",
@@ -456,6 +467,8 @@ def main():
                              "traffic": None, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
             "stages_ms": {k: round(v["ms"], 3) for k, v in prof.items()},
             "msm_g1_2pow20": msm,
+            "verify_batch": {"proofs": B, "all_valid": bool(all(vok)), "ms": verify_ms, "proofs_per_s": B / (verify_ms * 1e-3),
+                             "note": "zkfl_groth16_verify_batch on this step's proofs, host buffers, wall clock of the blocking call"},
             "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": ncores, "kind": "port",
                              "sample": f"{sample} proofs, one proof per thread (amortised per proof: witness {cpu_w_ms:.1f} ms + prove {cpu_p_ms:.0f} ms); "
                                        "C++ oracle restating snarkjs (snarkjs cannot run: no Node.js on this image)"},

@@ -3,7 +3,7 @@
 // Server.verify*Proof, :848-1131).
 //
 // Optimal ate pairing on BN254 over Fq12 = Fq[w]/(w^12 - 18 w^6 + 82) (xi = w^6 = 9 + u), the flat basis of the oracle
-// (oracle/bn254_ref.py Fq12), G2 arithmetic affine on the twist.  Every function is written once for host and device; the
+// (the same representation the test oracle uses, so intermediate values can be compared), G2 arithmetic affine on the twist.  Every function is written once for host and device; the
 // big ones are loops over small bodies (no unrolling, local arrays) so that a kernel holds ONE copy of the Fq12 product, the
 // line step and the sparse product -- the device code has no calls with stack frames, only the Fq product leaf call.
 //   * lines are sparse: l = c0 + c1 w + c3 w^3 + c7 w^7 + c9 w^9 -> 60 products instead of 144;
