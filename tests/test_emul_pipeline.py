@@ -26,6 +26,18 @@ def test_g2_msm(emul_prover):
     pc.case_g2_msm(emul_prover, 40)
 
 
+def test_both_bucket_reductions(emul_prover, monkeypatch):
+    """few rows take the bit-decomposed tree of plain sums (latency variant), batches the three-level running sums; both forced
+    here on the same MSMs and proofs"""
+    for mode in ("0", "1"):
+        monkeypatch.setenv("ZKFL_REDUCE_DEEP", mode)
+        for n in (1, 33, 300):
+            pc.case_g1_msm(emul_prover, n)
+        pc.case_g1_msm_degenerate(emul_prover)
+        pc.case_g2_msm(emul_prover, 40)
+        pc.case_prove(emul_prover, pc.tiny_circuit(), pc.tiny_inputs(), [(11, 22), (33, 44), (0, 0)], python_verify=0)
+
+
 def test_tiny_circuit_witness_prove_verify(emul_prover):
     cc = pc.tiny_circuit()
     pc.case_witness(emul_prover, cc, pc.tiny_inputs())

@@ -682,6 +682,59 @@ ZK_GLOBAL void k_reduce_final(const Xyzz<F>* __restrict__ R2, const Xyzz<F>* __r
   xyzz_add(z, sum_r);                                                                     // + sum(X)
   out[row] = z;
 }
+// pass 5, LATENCY variant (few rows: single proofs, the per-rank share of a split proof).  With one row the tree above is a
+// serial chain of ~2*L1 + 2*L2 + 5*N2 additions (288 for 2^15 buckets: 9-12 ms).  Here the weights are taken bit by bit:
+//   S = sum_k (k+1) X[k] = Y_all + sum_b 2^b Y_b,   Y_b = sum of the X[k] whose index has bit b set,
+// so everything is PLAIN sums, done as a fan-in-L tree (L = 8: three index bits per level).  One launch per level; thread =
+// (part, row, output element): part 0 sums a chunk of the main array (-> next main array), parts 1..n_pool sum a chunk of a
+// pending bit array, the last lgL parts sum the chunk elements whose local index has bit b set (-> new pending arrays).
+// Every thread adds at most L points; depth = L per level + 2 per bit in the final Horner (~70 additions for 2^15 buckets),
+// about 3*nb additions of work per row instead of 2*nb -- irrelevant at this size, the GPU is otherwise idle.
+// pool layout: [array][row][element]; arrays are in bit order (level 0 creates bits 0..lgL-1, and so on).
+template <class F>
+ZK_GLOBAL void k_reduce_bits_level(const Xyzz<F>* __restrict__ main_in, const Xyzz<F>* __restrict__ pool_in, uint32_t n_pool_in,
+                                   size_t rows, uint32_t N_in, uint32_t lgL, Xyzz<F>* __restrict__ main_out,
+                                   Xyzz<F>* __restrict__ pool_out) {
+  const uint32_t N_out = N_in >> lgL, L = 1u << lgL;
+  const size_t per_part = rows * N_out, tid = ZK_TID;
+  if (tid >= per_part * (1 + n_pool_in + lgL)) return;
+  const uint32_t part = (uint32_t)(tid / per_part);
+  const size_t rem = tid % per_part, row = rem / N_out;
+  const uint32_t t = (uint32_t)(rem % N_out);
+  const Xyzz<F>* src;
+  Xyzz<F>* dst;
+  uint32_t bit = 0xFFFFFFFFu;                       // no filter: every element of the chunk
+  if (part == 0) {
+    src = main_in + row * N_in + (size_t)t * L;
+    dst = main_out + row * N_out + t;
+  } else if (part <= n_pool_in) {
+    const size_t a = part - 1;
+    src = pool_in + (a * rows + row) * N_in + (size_t)t * L;
+    dst = pool_out + (a * rows + row) * N_out + t;
+  } else {
+    bit = part - 1 - n_pool_in;
+    src = main_in + row * N_in + (size_t)t * L;
+    dst = pool_out + ((size_t)(n_pool_in + bit) * rows + row) * N_out + t;
+  }
+  Xyzz<F> acc = Xyzz<F>::infinity();
+  for (uint32_t j = 0; j < L; j++)
+    if (bit == 0xFFFFFFFFu || ((j >> bit) & 1u)) xyzz_add(acc, src[j]);
+  *dst = acc;
+}
+// main: [rows] (Y_all), pool: [n_bits][rows] (Y_b): out[row] = Y_all + sum_b 2^b Y_b by Horner from the top bit
+template <class F>
+ZK_GLOBAL void k_reduce_bits_final(const Xyzz<F>* __restrict__ main_in, const Xyzz<F>* __restrict__ pool, uint32_t n_bits, size_t rows,
+                                   Xyzz<F>* __restrict__ out) {
+  size_t row = ZK_TID;
+  if (row >= rows) return;
+  Xyzz<F> z = Xyzz<F>::infinity();
+  for (int b = (int)n_bits - 1; b >= 0; b--) {
+    z = xyzz_dbl(z);
+    xyzz_add(z, pool[(size_t)b * rows + row]);
+  }
+  xyzz_add(z, main_in[row]);
+  out[row] = z;
+}
 // pass 6: Horner over the windows, one thread per proof: out[b] = sum_j 2^(c*j) * win[b][j]
 template <class F>
 ZK_GLOBAL void k_msm_combine(const Xyzz<F>* __restrict__ win, MsmShape s, Xyzz<F>* __restrict__ out) {

@@ -95,6 +95,7 @@ struct zkfl_ctx {
   // five MSMs per proof batch (A, C, B1, H on G1; B2 on G2): own bucket / reduction buffers each, so the
   // latency-bound bucket reduction of one MSM runs on `side` while the next MSM accumulates on `stream`
   DevBuf buckets[5], Rs[5], Ts[5], lvl2[5], win[5];
+  DevBuf red_main[5][2], red_pool[5][2];   // ping-pong buffers of the latency variant of the bucket reduction
   cudaStream_t side[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // one per MSM slot: the reductions are latency-bound and run concurrently
   cudaEvent_t ev_acc[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}, ev_red[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   DevBuf res_g1, res_g2, t_g1, t_g2, pis, var, proofs, pubs, bad;
@@ -315,9 +316,20 @@ static int msm_accumulate(zkfl_ctx* c, const Affine<F>* bases, const MsmShape& s
   CU(cudaGetLastError());
   return 0;
 }
+// few rows: the bit-decomposed tree of plain sums (k_reduce_bits_level) instead of the three-level running sums
+static bool reduce_deep(const MsmShape& s) {
+  const uint32_t mode = env_u32("ZKFL_REDUCE_DEEP", 2);   // 0 never, 1 always, 2 by size
+  return mode == 1 || (mode == 2 && (size_t)s.B * s.R <= 32 && s.nb >= 64);
+}
 static int msm_reserve_reduce(zkfl_ctx* c, const MsmShape& s, int slot, size_t elem) {
   size_t rows = (size_t)s.B * s.R;
   ReducePlan p = reduce_plan(s);
+  if (reduce_deep(s)) {
+    for (int k = 0; k < 2; k++) {
+      TRY(c->red_main[slot][k].reserve(rows * (s.nb / 2) * elem));
+      TRY(c->red_pool[slot][k].reserve(rows * s.nb * elem));   // <= 3/8 + 6/64 + ... of nb per row, with slack for small fan-ins
+    }
+  }
   TRY(c->Rs[slot].reserve(rows * p.N1 * elem));
   TRY(c->Ts[slot].reserve(rows * p.N1 * elem));
   TRY(c->lvl2[slot].reserve(3 * rows * p.N2 * elem));
@@ -335,6 +347,26 @@ static int msm_reduce(zkfl_ctx* c, const MsmShape& s, int slot, Xyzz<F>* out, cu
   Xyzz<F>* T2 = R2 + rows * p.N2;
   Xyzz<F>* RT = T2 + rows * p.N2;
   Stage st(c, tag, stream);
+  if (reduce_deep(s)) {
+    uint32_t lg = 0; while ((1u << lg) < s.nb) lg++;
+    const Xyzz<F>* main_in = c->buckets[slot].as<Xyzz<F>>();
+    uint32_t N = s.nb, n_pool = 0;
+    int pp = 0;
+    for (uint32_t done = 0; done < lg;) {
+      const uint32_t lgL = lg - done >= 3 ? 3 : lg - done;
+      Xyzz<F>* main_out = c->red_main[slot][pp].as<Xyzz<F>>();
+      Xyzz<F>* pool_out = c->red_pool[slot][pp].as<Xyzz<F>>();
+      const Xyzz<F>* pool_in = c->red_pool[slot][pp ^ 1].as<Xyzz<F>>();
+      ZK_LAUNCH(k_reduce_bits_level<F>, rows * (N >> lgL) * (1 + n_pool + lgL), 64, stream, main_in, pool_in, n_pool, rows, N, lgL,
+                main_out, pool_out);
+      main_in = main_out; N >>= lgL; n_pool += lgL; done += lgL; pp ^= 1;
+    }
+    ZK_LAUNCH(k_reduce_bits_final<F>, rows, 32, stream, main_in, (const Xyzz<F>*)c->red_pool[slot][pp ^ 1].as<Xyzz<F>>(), n_pool, rows,
+              c->win[slot].as<Xyzz<F>>());
+    ZK_LAUNCH(k_msm_combine<F>, s.B, 32, stream, c->win[slot].as<Xyzz<F>>(), s, out);
+    CU(cudaGetLastError());
+    return 0;
+  }
   ZK_LAUNCH(k_reduce_level<F>, rows * p.N1, 64, stream, c->buckets[slot].as<Xyzz<F>>(), rows, s.nb, p.L1, R1, T1);
   ZK_LAUNCH(k_reduce_level<F>, rows * p.N2, 64, stream, (const Xyzz<F>*)R1, rows, p.N1, p.L2, R2, T2);
   ZK_LAUNCH(k_reduce_level<F>, rows * p.N2, 64, stream, (const Xyzz<F>*)T1, rows, p.N1, p.L2, RT, (Xyzz<F>*)nullptr);
