@@ -75,6 +75,21 @@ def test_witness_all_circuits(gpu_prover):
         pc.case_witness(gpu_prover, build_circuit(name), ins)
 
 
+def test_latency_variants_match_the_batch_kernels(gpu_prover, monkeypatch):
+    """few instances use one warp per (op, instance) in the witness evaluator and the bit-decomposed bucket reduction; both are
+    forced off and on here: same witnesses (vs the oracle) and same proofs (vs the oracle) either way."""
+    cc = build_circuit("sgd_verified")
+    ins = I.sgd_verified_batch(2) + I.sgd_verified_batch(1, nonzero_weights=True)
+    for coop, deep in (("0", "0"), ("1", "1"), ("1", "0")):
+        monkeypatch.setenv("ZKFL_WITNESS_COOP", coop)
+        monkeypatch.setenv("ZKFL_REDUCE_DEEP", deep)
+        pc.case_witness(gpu_prover, cc, ins)
+        pc.case_witness(gpu_prover, build_circuit("secure_agg_client"), [I.secure_agg_client_input()])   # Poseidon t = 2, 3, 9
+        pc.case_prove(gpu_prover, cc, ins, [(1, 2), (3, 4), (5, 6)], python_verify=0)
+        pc.case_g1_msm(gpu_prover, 1 << 14)
+        pc.case_g2_msm(gpu_prover, 300)
+
+
 def test_prove_sgd_verified_batch(gpu_prover):
     """the metric circuit: 8 clients in one batch, fixed (r, s), bit-exact proofs, pairing-verified."""
     ins = I.sgd_verified_batch(6) + I.sgd_verified_batch(2, nonzero_weights=True)

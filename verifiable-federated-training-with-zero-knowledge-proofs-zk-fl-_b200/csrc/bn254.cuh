@@ -561,8 +561,8 @@ ZK_HD Fq2 to_mont_any(const Fq2& x) { Fq2 r; r.a = x.a.to_mont(); r.b = x.b.to_m
 // ------------------------------------------------------------------------------ warp exchange of field elements (device)
 #if !defined(ZKFL_EMUL)
 enum { ZK_SHFL_UP = 0, ZK_SHFL_DOWN = 1, ZK_SHFL_IDX = 2 };
-template <int MODE> __device__ __forceinline__ Fq warp_shfl(const Fq& x, uint32_t arg) {
-  Fq r;
+template <int MODE, class P> __device__ __forceinline__ Fp<P> warp_shfl(const Fp<P>& x, uint32_t arg) {
+  Fp<P> r;
   ZK_UNROLL for (int i = 0; i < 8; i++)
     r.v[i] = MODE == ZK_SHFL_UP ? __shfl_up_sync(0xffffffffu, x.v[i], arg)
            : MODE == ZK_SHFL_DOWN ? __shfl_down_sync(0xffffffffu, x.v[i], arg) : __shfl_sync(0xffffffffu, x.v[i], (int)arg);

@@ -155,6 +155,67 @@ ZK_GLOBAL void k_witness_level(ProgramDev p, Fr* __restrict__ w, uint32_t B, uin
   }
 }
 
+#ifndef ZKFL_EMUL
+// LATENCY variant of a witness level (few client instances): one WARP per (op, client).  A Poseidon permutation is a serial
+// chain of rounds; with one thread per instance a round costs t^2 + 6 products (MDS row by row, S-box, canonical copies of the
+// three S-box wires), ~1 ms per t = 6 permutation and 5 ms for the 7 dependency levels of sgd_verified.  Here lane i owns state
+// element i: a round is t + 6 products per lane (its MDS row over shuffled state, its own S-box).  Every lane runs the same
+// instruction stream (lanes >= t mirror element t-1, S-box results are selected, stores are predicated): no divergent calls.
+// Other ops are evaluated redundantly by all lanes (same value, same address).  Wire numbering is identical to k_witness_level.
+__global__ void k_witness_level_coop(ProgramDev p, Fr* __restrict__ w, uint32_t B, uint32_t op_lo, uint32_t op_hi) {
+  const size_t gw = ZK_TID >> 5;
+  const uint32_t lane = threadIdx.x & 31u;
+  if (gw >= (size_t)(op_hi - op_lo) * B) return;      // a whole warp at a time
+  const uint32_t o = op_lo + (uint32_t)(gw / B), b = (uint32_t)(gw % B);
+  const uint32_t* op = p.ops + 5 * (size_t)o;
+  const uint32_t code = ZK_LDG(op), dst = ZK_LDG(op + 1), a = ZK_LDG(op + 2), bb = ZK_LDG(op + 3), c = ZK_LDG(op + 4);
+  if (code == 1) {
+    w[(size_t)dst * B + b] = lc_eval(p, a, w, B, b).from_mont();
+  } else if (code == 2) {
+    Fr v = lc_eval(p, a, w, B, b) * lc_eval(p, bb, w, B, b);
+    if (c != 0xFFFFFFFFu) v = v + lc_eval(p, c, w, B, b);
+    w[(size_t)dst * B + b] = v.from_mont();
+  } else if (code == 3) {
+    Fr v = lc_eval(p, a, w, B, b).from_mont();
+    for (uint32_t i = lane; i < bb; i += 32) {      // the bits of the value: one per lane
+      Fr bit = Fr::zero();
+      bit.v[0] = (v.v[i >> 5] >> (i & 31)) & 1u;
+      w[(size_t)(dst + i) * B + b] = bit;
+    }
+  } else if (code == 4) {
+    const uint32_t t = a;
+    const PoseidonDev K = p.pk[t];
+    const uint32_t li = lane < t ? lane : t - 1;
+    Fr st = Fr::zero();
+    if (li) st = w[(size_t)ZK_LDG(p.pos_in + bb + li - 1) * B + b];
+    st = st.to_mont();                                // (0 stays 0)
+    size_t k = dst;
+    ZK_NOUNROLL for (uint32_t r = 0; r < K.rounds; r++) {
+      st = st + K.C[r * t + li];
+      const bool full = r < 4 || r >= 4 + K.rp;
+      const Fr x2 = st.sqr(), x4 = x2.sqr(), x5 = x4 * st;
+      const Fr c2 = x2.from_mont(), c4 = x4.from_mont(), c5 = x5.from_mont();
+      if (full ? lane < t : lane == 0) {
+        const size_t kk = k + (full ? 3 * (size_t)li : 0);
+        w[kk * B + b] = c2;
+        w[(kk + 1) * B + b] = c4;
+        w[(kk + 2) * B + b] = c5;
+      }
+      if (full || li == 0) st = x5;
+      k += full ? 3 * (size_t)t : 3;
+      Fr acc = Fr::zero();
+      ZK_NOUNROLL for (uint32_t j = 0; j < t; j++) {
+        const Fr sj = warp_shfl<ZK_SHFL_IDX>(st, j);
+        acc = acc + K.M[li * t + j] * sj;
+      }
+      st = acc;
+    }
+    const Fr out = st.from_mont();
+    if (lane == 0) w[k * B + b] = out;
+  }
+}
+#endif
+
 // ================================================================================ K1: sparse A.w, B.w, C = A o B
 struct CsrDev {
   const uint32_t* row_off;  // n_rows + 1

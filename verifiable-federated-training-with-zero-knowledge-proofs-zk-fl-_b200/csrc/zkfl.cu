@@ -538,6 +538,14 @@ static int run_witness(zkfl_ctx* c, const zkfl_circuit* circ, const uint8_t* inp
   ZK_LAUNCH(k_witness_init, B, 128, c->stream, c->w.as<Fr>(), B);
   for (size_t k = 0; k + 1 < circ->level_off.size(); k++) {
     uint32_t lo = circ->level_off[k], hi = circ->level_off[k + 1];
+#ifndef ZKFL_EMUL
+    // few instances: one warp per (op, instance), Poseidon state across the lanes (ZKFL_WITNESS_COOP = 0 never, 1 always)
+    const uint32_t coop = env_u32("ZKFL_WITNESS_COOP", 2);
+    if (coop == 1 || (coop == 2 && B <= 32)) {
+      ZK_LAUNCH(k_witness_level_coop, (size_t)(hi - lo) * B * 32, 128, c->stream, circ->dev, c->w.as<Fr>(), B, lo, hi);
+      continue;
+    }
+#endif
     ZK_LAUNCH(k_witness_level, (size_t)(hi - lo) * B, 64, c->stream, circ->dev, c->w.as<Fr>(), B, lo, hi);
   }
   CU(cudaGetLastError());
