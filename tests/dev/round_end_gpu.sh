@@ -1,8 +1,8 @@
-# one GPU call: full GPU test-suite, the default bench, launch list + full ncu capture of the dominant kernels
+# one GPU call: full GPU test-suite, smoke, the default bench (+ one variant)
 set -x; mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -5
-timeout 900 python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; tail -c 3000 gpurun_out/bench_default.json
-CMD="python bench.py --batch 256 --lanes 1 --steps 1 --warmup 1 --no-msm"
-$CMD > gpurun_out/plain.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-file gpurun_out/launches_r01_v4.csv $CMD > gpurun_out/ncu_l.log 2>&1
-$CMD > gpurun_out/plain.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:k_msm_accumulate_chunks -s 5 -c 5 -o gpurun_out/prof_chunks_v4 $CMD > gpurun_out/ncu_f.log 2>&1
-tail -2 gpurun_out/ncu_f.log
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+timeout 900 python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; tail -c 2500 gpurun_out/bench_default.json
+ZKFL_WITNESS_COOP=1 timeout 600 python bench.py --steps 3 --warmup 3 --no-msm 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('coop forced:', round(d['value'],1), d['stages_ms']['witness'])"
