@@ -54,6 +54,14 @@ def timed(fn, reps=5):
 whole, t_whole = timed(lambda: P.prove(Z, ws, rs)[0])
 split, t_split = timed(lambda: sharding.prove_split(P, Z, ws, rs))
 assert split == whole, "split proof differs from the whole proof"
+# the same with the witness in pinned host memory and resident on the device (no pageable staging copy)
+wpin = torch.frombuffer(bytearray(ws[0]), dtype=torch.uint8).pin_memory()
+wdev = wpin.cuda()
+whole_pin, t_whole_pin = timed(lambda: P.prove(Z, wpin, rs)[0])
+split_pin, t_split_pin = timed(lambda: sharding.prove_split(P, Z, wpin, rs))
+whole_dev, t_whole_dev = timed(lambda: P.prove(Z, wdev, rs)[0])
+split_dev, t_split_dev = timed(lambda: sharding.prove_split(P, Z, wdev, rs))
+assert whole_pin == whole and split_pin == whole and whole_dev == whole and split_dev == whole
 P.prof_enable(True); P.prove(Z, ws, rs); prof_whole = P.prof_read()
 sharding.prove_split(P, Z, ws, rs); prof_split = P.prof_read(); P.prof_enable(False)
 if rank == 0:
@@ -70,6 +78,8 @@ if rank == 0:
     assert sj.groth16.verify(formats.export_verification_key(zk), formats.publics_bytes_to_json(P.prove(Z, ws, rs)[1][0]), formats.proof_bytes_to_json(whole[0]))
     print(json.dumps({"circuit": f"TrainingStepVerified({BATCH},{DIM},{DEPTH},1000)", "n_wires": cc.n_wires, "domain": Z.domain, "n_gpus": world,
                       "whole_proof_one_gpu_ms": round(1e3 * t_whole, 2), "split_proof_ms": round(1e3 * t_split, 2),
+                      "pinned_witness": {"whole_ms": round(1e3 * t_whole_pin, 2), "split_ms": round(1e3 * t_split_pin, 2)},
+                      "device_witness": {"whole_ms": round(1e3 * t_whole_dev, 2), "split_ms": round(1e3 * t_split_dev, 2)},
                       "oracle_cpu_s": None if t_cpu is None else round(t_cpu, 2), "oracle_threads": ol.ncores(),
                       "bit_exact_vs_oracle": t_cpu is not None, "verified": True}), flush=True)
 dist.barrier(); dist.destroy_process_group()

@@ -160,12 +160,23 @@ class Prover:
         assert len(rs) == B
         return b"".join(int(r).to_bytes(32, "little") + int(s).to_bytes(32, "little") for r, s in rs)
 
-    def prove(self, zkey: Zkey, wtns: list[bytes], rs=None):
+    @staticmethod
+    def _wtns_buffer(zkey: Zkey, wtns):
+        """list of per-proof witnesses, or ONE buffer holding them back to back: bytes / bytearray, or a torch uint8 tensor
+        (pinned host memory uploads at PCIe speed, a CUDA tensor is copied on the device). -> (buffer, B)"""
+        if isinstance(wtns, (list, tuple)):
+            return b"".join(wtns), len(wtns)
+        n = wtns.numel() * wtns.element_size() if hasattr(wtns, "data_ptr") else len(wtns)
+        if n % (32 * zkey.n_vars):
+            raise ValueError("witness buffer is not a multiple of 32 * n_vars bytes")
+        return wtns, n // (32 * zkey.n_vars)
+
+    def prove(self, zkey: Zkey, wtns, rs=None):
         """-> (list of 256-byte proofs, list of public-signal byte strings)"""
-        B = len(wtns)
+        buf, B = self._wtns_buffer(zkey, wtns)
         proofs = ctypes.create_string_buffer(256 * B)
         pubs = ctypes.create_string_buffer(max(32 * zkey.n_public * B, 1))
-        self._check(self.lib.zkfl_groth16_prove_batch(self.ctx, zkey.handle, _lib.as_ptr(b"".join(wtns)),
+        self._check(self.lib.zkfl_groth16_prove_batch(self.ctx, zkey.handle, _lib.as_ptr(buf),
                                                      _lib.as_ptr(self._pack_rs(rs, B)), B, proofs, pubs))
         psz = 32 * zkey.n_public
         praw, qraw = proofs.raw, pubs.raw
@@ -182,11 +193,11 @@ class Prover:
         praw, qraw = proofs.raw, pubs.raw
         return ([praw[256 * b:256 * (b + 1)] for b in range(B)], [qraw[psz * b:psz * (b + 1)] for b in range(B)])
 
-    def msm_partials(self, zkey: Zkey, wtns: list[bytes], part: int, nparts: int) -> bytes:
+    def msm_partials(self, zkey: Zkey, wtns, part: int, nparts: int) -> bytes:
         """the five MSM sums over this rank's point range (B x 384 bytes), see zkfl_groth16_msm_partials"""
-        B = len(wtns)
+        buf, B = self._wtns_buffer(zkey, wtns)
         out = ctypes.create_string_buffer(384 * B)
-        self._check(self.lib.zkfl_groth16_msm_partials(self.ctx, zkey.handle, _lib.as_ptr(b"".join(wtns)), B, part, nparts, out))
+        self._check(self.lib.zkfl_groth16_msm_partials(self.ctx, zkey.handle, _lib.as_ptr(buf), B, part, nparts, out))
         return out.raw
 
     def finalize(self, zkey: Zkey, partials: list[bytes], B: int, rs=None) -> list[bytes]:

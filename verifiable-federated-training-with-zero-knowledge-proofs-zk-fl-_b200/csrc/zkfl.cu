@@ -919,7 +919,7 @@ int zkfl_r1cs_check_batch(zkfl_ctx* c, const zkfl_r1cs* r, const uint8_t* wtns, 
   CU(cudaSetDevice(c->device));
   size_t cnt = (size_t)r->n_wires * B;
   TRY(c->aos.reserve(cnt * sizeof(Fr))); TRY(c->w.reserve(cnt * sizeof(Fr)));
-  CU(cudaMemcpyAsync(c->aos.p, wtns, cnt * sizeof(Fr), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(c->aos.p, wtns, cnt * sizeof(Fr), cudaMemcpyDefault, c->stream));   // pageable, pinned or device memory
   ZK_LAUNCH(k_aos_to_soa, cnt, 256, c->stream, c->aos.as<Fr>(), c->w.as<Fr>(), r->n_wires, (uint32_t)B, 0u);
   return check_r1cs_device(c, r, (uint32_t)B, first_bad);
 }
@@ -934,7 +934,7 @@ int zkfl_groth16_prove_batch(zkfl_ctx* c, const zkfl_zkey* z, const uint8_t* wtn
   {
     Stage st(c, "upload_wtns");
     TRY(c->aos.reserve(cnt * sizeof(Fr))); TRY(c->w.reserve(cnt * sizeof(Fr)));
-    CU(cudaMemcpyAsync(c->aos.p, wtns, cnt * sizeof(Fr), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->aos.p, wtns, cnt * sizeof(Fr), cudaMemcpyDefault, c->stream));   // pageable, pinned or device memory
     ZK_LAUNCH(k_aos_to_soa, cnt, 256, c->stream, c->aos.as<Fr>(), c->w.as<Fr>(), z->n_vars, (uint32_t)B, 0u);
   }
   TRY(prove_from_device_witness(c, z, c->stage_rs.as<Fr>(), (uint32_t)B));
@@ -988,7 +988,7 @@ int zkfl_groth16_msm_partials(zkfl_ctx* c, const zkfl_zkey* z, const uint8_t* wt
   CU(cudaSetDevice(c->device));
   size_t cnt = (size_t)z->n_vars * B;
   TRY(c->aos.reserve(cnt * sizeof(Fr))); TRY(c->w.reserve(cnt * sizeof(Fr)));
-  CU(cudaMemcpyAsync(c->aos.p, wtns, cnt * sizeof(Fr), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(c->aos.p, wtns, cnt * sizeof(Fr), cudaMemcpyDefault, c->stream));   // pageable, pinned or device memory
   ZK_LAUNCH(k_aos_to_soa, cnt, 256, c->stream, c->aos.as<Fr>(), c->w.as<Fr>(), z->n_vars, (uint32_t)B, 0u);
   TRY(prove_from_device_witness(c, z, nullptr, (uint32_t)B, part, nparts, false));
   // layout per proof b: A | B1 | C | H (64 B each, affine canonical) | B2 (128 B)  -> stored as [5 blocks][B]

@@ -60,7 +60,7 @@ typedef int cudaError_t;
 typedef void* cudaStream_t;
 typedef void* cudaEvent_t;
 #define cudaSuccess 0
-enum { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
+enum { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice, cudaMemcpyDefault };
 namespace zkrt {
 typedef void* stream_t;
 inline const char* err_str(int) { return "emul"; }

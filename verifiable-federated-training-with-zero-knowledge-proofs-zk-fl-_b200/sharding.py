@@ -64,7 +64,7 @@ def prove_independent(prover, circuit, zkey, inputs: list, rs: list | None = Non
 def prove_split(prover, zkey, wtns: list[bytes], rs: list | None):
     """One (or a few) large proofs with every MSM split by point range over the ranks. Every rank returns the proofs."""
     world, rank = dist.get_world_size(), dist.get_rank()
-    B = len(wtns)
+    B = len(wtns) if isinstance(wtns, (list, tuple)) else (wtns.numel() * wtns.element_size() if hasattr(wtns, "data_ptr") else len(wtns)) // (32 * zkey.n_vars)
     part = prover.msm_partials(zkey, wtns, rank, world)
     mine = torch.frombuffer(bytearray(part), dtype=torch.uint8).to(_device())
     allp = [torch.zeros_like(mine) for _ in range(world)]
