@@ -125,6 +125,8 @@ int zkfl_groth16_verify_batch(zkfl_ctx* ctx, const uint8_t* alpha1, const uint8_
 
 /* dev / test hook: intermediate buffers of the last zkfl_groth16_verify_batch ("v_t", "v_g1", "v_g2", "v_flags", "v_f", "v_halves") */
 int zkfl_debug_read(zkfl_ctx* ctx, const char* name, void* out, size_t bytes);
+/* host-side consistency check of the verifier's two Fq12 views (products, inverse, Frobenius maps); 0 = ok, else the failing check */
+int zkfl_debug_pairing_selftest(void);
 
 /* ---- standalone multi-scalar multiplication (BASELINE.json: "G1 MSM pts/s at 2^20") ----------- */
 /* bases: n affine points, Montgomery little-endian (zkey point layout, 64 B G1 / 128 B G2);

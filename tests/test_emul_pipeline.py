@@ -62,8 +62,11 @@ def test_batch_affine_accumulation(emul_prover, monkeypatch):
 def test_batch_verifier_matches_oracle_and_host_verifier(emul_prover, monkeypatch):
     import __graft_entry__ as ge
     monkeypatch.setenv("ZKFL_LIBRARY_PATH", ge.build_emul())   # the single-proof verifier of the same (emulated) build
+    assert emul_prover.lib.zkfl_debug_pairing_selftest() == 0     # tower view of Fq12 against the flat basis
     cc = pc.tiny_circuit()
     zk, proofs, pubs = pc.case_prove(emul_prover, cc, pc.tiny_inputs(), [(11, 22), (33, 44), (0, 0)], python_verify=0)
+    pc.case_verify_batch(emul_prover, zk, proofs, pubs)            # default: easy part + x-power chain
+    monkeypatch.setenv("ZKFL_VERIFY_FLAT", "1")                     # the inversion-free two-power form agrees
     pc.case_verify_batch(emul_prover, zk, proofs, pubs)
 
 

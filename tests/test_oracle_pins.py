@@ -132,3 +132,25 @@ def test_final_exponentiation_identities_used_by_the_batch_verifier():
     x = bn.Fq12([rnd.randrange(Q) for _ in range(12)])
     assert bn.Fq12([c * pow(zeta, i, Q) for i, c in enumerate(x.c)]) == x.pow(Q * Q)
     assert bn.Fq12([c if i % 2 == 0 else -c for i, c in enumerate(x.c)]) == x.pow(Q ** 6)
+
+
+def test_hard_part_chain_of_the_verifier_is_a_multiple_of_h():
+    """pairing.cuh's final_exp_is_one raises the easy-part value g to E through conj / squarings / three powers of -x /
+    Frobenius^1,2,3; replayed here on exponents modulo the cyclotomic order p^4 - p^2 + 1 = r h: E must be k h with r not
+    dividing k, so that g^E == 1 exactly when g^h == 1."""
+    p, r = bn.Q, bn.R
+    x = 0x44e992b44a6909f1
+    assert 36 * x ** 4 + 36 * x ** 3 + 24 * x ** 2 + 6 * x + 1 == p and 36 * x ** 4 + 36 * x ** 3 + 18 * x ** 2 + 6 * x + 1 == r
+    phi = p ** 4 - p * p + 1
+    h = phi // r
+
+    def negx(e):
+        return -e * x % phi
+    g = 1
+    y0 = negx(g); y1 = 2 * y0; y2 = 2 * y1; y3 = y2 + y1; y4 = negx(y3); y6 = negx(2 * y4)
+    y3, y6 = -y3, -y6
+    y8 = y6 + y4 + y3
+    y9 = y8 + y1
+    y11 = y8 + y4 + g
+    e = (y9 * p + y11 + y8 * p * p + (y9 - g) * p ** 3) % phi
+    assert e % h == 0 and (e // h) % r != 0

@@ -982,6 +982,16 @@ ZK_GLOBAL void k_vfy_final(zkp::PairingConsts k, const zkp::F12* __restrict__ f,
   zkp::final_half(F, side, g, k);
   halves[2 * b + side] = g;
 }
+// thread b: the whole final exponentiation of proof b in the tower view (easy part + x-power chain, ~20 k products)
+ZK_GLOBAL void k_vfy_final_tower(zkp::PairingConsts k, const zkp::F12* __restrict__ f, const uint32_t* __restrict__ flags, uint32_t B,
+                                 int32_t* __restrict__ ok) {
+  const size_t b = ZK_TID;
+  if (b >= B) return;
+  if (!flags[b]) { ok[b] = 0; return; }
+  zkp::F12 F = f[3 * b], g;
+  ZK_NOUNROLL for (int i = 1; i < 4; i++) { g = f[i < 3 ? 3 * b + i : (size_t)3 * B]; zkp::f12_mul(F, F, g, k); }
+  ok[b] = zkp::final_exp_is_one(F, k) ? 1 : 0;
+}
 ZK_GLOBAL void k_vfy_compare(const zkp::F12* __restrict__ halves, const uint32_t* __restrict__ flags, uint32_t B,
                              int32_t* __restrict__ ok) {
   size_t b = ZK_TID;

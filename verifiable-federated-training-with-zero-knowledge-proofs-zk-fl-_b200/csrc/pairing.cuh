@@ -8,9 +8,10 @@
 // line step and the sparse product -- the device code has no calls with stack frames, only the Fq product leaf call.
 //   * lines are sparse: l = c0 + c1 w + c3 w^3 + c7 w^7 + c9 w^9 -> 60 products instead of 144;
 //   * squarings use the symmetric half: 78 products;
-//   * final exponentiation: f^((p^12-1)/r) == 1  <=>  (conj(f)/f)^((p^2+1) h) == 1, h = (p^4 - p^2 + 1)/r,
-//     <=>  (frob2(conj f) conj f)^h == (frob2(f) f)^h  -- no Fq12 inversion, two independent 761-bit powers (the device runs
-//     them in two threads) instead of one 2816-bit power.  conj = Frobenius^6 flips the odd coefficients; frob2 = Frobenius^2
+//   * final exponentiation: easy part + x-power chain in the tower view (final_exp_is_one below, the default); the first
+//     version is kept for cross-checking (`ZKFL_VERIFY_FLAT=1`): f^((p^12-1)/r) == 1  <=>  (conj(f)/f)^((p^2+1) h) == 1,
+//     h = (p^4 - p^2 + 1)/r,  <=>  (frob2(conj f) conj f)^h == (frob2(f) f)^h  -- no Fq12 inversion, two independent 761-bit
+//     powers (two warps per 32 proofs on the device) instead of one 2816-bit power.  conj = Frobenius^6 flips the odd coefficients; frob2 = Frobenius^2
 //     multiplies coefficient i by zeta^i, zeta = xi^((p^2-1)/6) in Fq (both identities are checked in tests/test_oracle_pins.py).
 #pragma once
 #include "bn254.cuh"
@@ -30,6 +31,7 @@ struct PairingConsts {
   Fq zeta[12];        // zeta^i
   Fq2 twist_b;        // 3 / xi
   Fq2 g12, g13;       // xi^((p-1)/3), xi^((p-1)/2): Frobenius on the twist
+  Fq2 frob[3][6];     // frob[k-1][m] = xi^(m (p^k - 1)/6): Frobenius^k on the coefficient of w^m (tower view below)
 };
 
 ZK_HD Fq fq_small(uint32_t v) { Fq r = Fq::zero(); r.v[0] = v; return r.to_mont(); }
@@ -54,6 +56,18 @@ static inline PairingConsts make_consts() {
   static const uint32_t E2[8] = {0x6c3e7ea3u, 0x9e10460bu, 0xb438e546u, 0xcbc0b548u, 0x40c0ac2eu, 0xdc2822dbu, 0x7098d014u, 0x18322739u};
   k.g12 = fq2_pow_host(xi, E3, 8);
   k.g13 = fq2_pow_host(xi, E2, 8);
+  // (p^k - 1) / 6 for k = 1, 2, 3
+  static const uint32_t F1[8] = {0x2414d4e1u,0x34b01759u,0xe6bda1c2u,0xee9591c2u,0xc0403964u,0xf40d60f3u,0xd032f006u,0x0810b7bdu};
+  static const uint32_t F2[16] = {0xb13a3c48u,0x348e0ec5u,0xd6fc7580u,0xc655abdcu,0xbcee7724u,0x0c62aec4u,0xe9adb5ccu,0x2b66c518u,
+                                  0xb3767342u,0x5bd25464u,0x2e5e8e56u,0x72ac9638u,0xab36cdafu,0x0eef1294u,0x13b4ca9au,0x01864b74u};
+  static const uint32_t F3[24] = {0xcbaeb4d9u,0x9ef31995u,0xec487080u,0xac3dad95u,0xf63bddf5u,0x8b33bea5u,0x984eeb22u,0x9fefedd1u,
+                                  0x6ca1caa5u,0x6fea09beu,0x3f9c6113u,0x67d81a82u,0xd6398826u,0x00daed7bu,0xeb1f2783u,0x2667434cu,
+                                  0x32525cfau,0xa0605a09u,0xd0fb6bfdu,0x3c036d4du,0x4083ea9du,0x88852038u,0xd72be447u,0x0049c712u};
+  const Fq2 gam[3] = {fq2_pow_host(xi, F1, 8), fq2_pow_host(xi, F2, 16), fq2_pow_host(xi, F3, 24)};
+  for (int q = 0; q < 3; q++) {
+    k.frob[q][0] = Fq2::one();
+    for (int m = 1; m < 6; m++) k.frob[q][m] = k.frob[q][m - 1] * gam[q];
+  }
   return k;
 }
 
@@ -196,6 +210,127 @@ ZK_HD G1P g1_from_xyzz(const zk::G1Xyzz& p) {
   return r;
 }
 ZK_HD zk::G1Affine g1_to_affine(const G1P& p) { zk::G1Affine a; a.x = p.inf ? Fq::zero() : p.x; a.y = p.inf ? Fq::zero() : p.y; return a; }
+
+// ------------------------------------------------------------------------------ final exponentiation in the tower view
+// The same field seen as Fq2[w]/(w^6 - xi): element = sum_m c[m] w^m, c[m] in Fq2.  From the flat basis (u = w^6 - 9):
+// c[m] = (flat[m] + 9 flat[m+6]) + flat[m+6] u.  Products are degree-6 schoolbook over Fq2 (36 Fq2 = 108 Fq products, loops
+// only), squarings the symmetric half (57), Frobenius^k = conj^k on the coefficients times frob[k-1][m], inversion through
+// Fq6 = Fq2[v]/(v^3 - xi), v = w^2 (even / odd coefficients).  With those the classic split is affordable:
+//   easy part  g = (conj(f) / f)^(p^2 + 1)   (one inversion),
+//   hard part  g^(k h), k not divisible by r, by the x-power chain of Fuentes-Castaneda et al. (three 63-bit powers of the BN
+//   parameter x = 0x44e992b44a6909f1, Frobenius^1,2,3): ~20 k Fq products instead of the 2 x 140 k of the two flat powers.
+// The chain's exponent is checked symbolically in tests/test_oracle_pins.py; zkfl_debug_pairing_selftest checks the maps.
+struct T12 { Fq2 c[6]; };
+ZK_HD Fq2 mul_xi(const Fq2& x) {   // (9 + u) x
+  const Fq a9 = x.a.dbl().dbl().dbl() + x.a, b9 = x.b.dbl().dbl().dbl() + x.b;
+  Fq2 r; r.a = a9 - x.b; r.b = b9 + x.a; return r;
+}
+ZK_HD void t12_from_flat(T12& r, const F12& f, const PairingConsts& k) {
+  ZK_NOUNROLL for (int m = 0; m < 6; m++) { r.c[m].b = f.c[m + 6]; r.c[m].a = f.c[m] + k.k9 * f.c[m + 6]; }
+}
+ZK_HD void t12_to_flat(F12& f, const T12& a, const PairingConsts& k) {
+  ZK_NOUNROLL for (int m = 0; m < 6; m++) { f.c[m + 6] = a.c[m].b; f.c[m] = a.c[m].a - k.k9 * a.c[m].b; }
+}
+ZK_HD bool t12_is_one(const T12& a) {
+  bool e = a.c[0] == Fq2::one();
+  ZK_NOUNROLL for (int m = 1; m < 6; m++) e = e && a.c[m].is_zero();
+  return e;
+}
+ZK_HD void t12_reduce(T12& r, Fq2* t) {   // w^6 = xi
+  ZK_NOUNROLL for (int i = 10; i >= 6; i--) t[i - 6] = t[i - 6] + mul_xi(t[i]);
+  ZK_NOUNROLL for (int i = 0; i < 6; i++) r.c[i] = t[i];
+}
+ZK_HD void t12_mul(T12& r, const T12& a, const T12& b) {   // r may alias a or b
+  Fq2 t[11];
+  ZK_NOUNROLL for (int i = 0; i < 11; i++) t[i] = Fq2::zero();
+  ZK_NOUNROLL for (int i = 0; i < 6; i++) {
+    const Fq2 ai = a.c[i];
+    ZK_NOUNROLL for (int j = 0; j < 6; j++) t[i + j] = t[i + j] + ai * b.c[j];
+  }
+  t12_reduce(r, t);
+}
+ZK_HD void t12_sqr(T12& r, const T12& a) {
+  Fq2 t[11];
+  ZK_NOUNROLL for (int i = 0; i < 11; i++) t[i] = Fq2::zero();
+  ZK_NOUNROLL for (int i = 0; i < 6; i++) {
+    const Fq2 ai = a.c[i];
+    t[2 * i] = t[2 * i] + ai.sqr();
+    ZK_NOUNROLL for (int j = i + 1; j < 6; j++) t[i + j] = t[i + j] + (ai * a.c[j]).dbl();
+  }
+  t12_reduce(r, t);
+}
+ZK_HD void t12_conj(T12& r, const T12& a) { ZK_NOUNROLL for (int m = 0; m < 6; m++) r.c[m] = (m & 1) ? a.c[m].neg() : a.c[m]; }
+ZK_HD void t12_frob(T12& r, const T12& a, int q, const PairingConsts& k) {   // Frobenius^q, q = 1, 2, 3
+  ZK_NOUNROLL for (int m = 0; m < 6; m++) r.c[m] = ((q & 1) ? fq2_conj(a.c[m]) : a.c[m]) * k.frob[q - 1][m];
+}
+// a^-1 = (a0 - w a1) / (a0^2 - v a1^2), a = a0(v) + w a1(v) with a0, a1 in Fq6 (even / odd coefficients), v = w^2, v^3 = xi
+ZK_HD void f6_mul(Fq2* r, const Fq2* x, const Fq2* y) {   // r must not alias
+  Fq2 t[5];
+  ZK_NOUNROLL for (int i = 0; i < 5; i++) t[i] = Fq2::zero();
+  ZK_NOUNROLL for (int i = 0; i < 3; i++) ZK_NOUNROLL for (int j = 0; j < 3; j++) t[i + j] = t[i + j] + x[i] * y[j];
+  r[0] = t[0] + mul_xi(t[3]); r[1] = t[1] + mul_xi(t[4]); r[2] = t[2];
+}
+ZK_HD void t12_inv(T12& r, const T12& a) {
+  Fq2 a0[3], a1[3], s0[3], s1[3], d[3];
+  ZK_NOUNROLL for (int j = 0; j < 3; j++) { a0[j] = a.c[2 * j]; a1[j] = a.c[2 * j + 1]; }
+  f6_mul(s0, a0, a0);
+  f6_mul(s1, a1, a1);
+  // d = a0^2 - v a1^2;  v (s1_0, s1_1, s1_2) = (xi s1_2, s1_0, s1_1)
+  d[0] = s0[0] - mul_xi(s1[2]); d[1] = s0[1] - s1[0]; d[2] = s0[2] - s1[1];
+  // d^-1 in Fq6
+  const Fq2 t0 = d[0].sqr() - mul_xi(d[1] * d[2]);
+  const Fq2 t1 = mul_xi(d[2].sqr()) - d[0] * d[1];
+  const Fq2 t2 = d[1].sqr() - d[0] * d[2];
+  const Fq2 n = (d[0] * t0 + mul_xi(d[2] * t1 + d[1] * t2)).inv_gcd();
+  Fq2 di[3]; di[0] = t0 * n; di[1] = t1 * n; di[2] = t2 * n;
+  f6_mul(s0, a0, di);
+  f6_mul(s1, a1, di);
+  ZK_NOUNROLL for (int j = 0; j < 3; j++) { r.c[2 * j] = s0[j]; r.c[2 * j + 1] = s1[j].neg(); }
+}
+ZK_HD void t12_exp_neg_x(T12& r, const T12& a) {   // conj(a^x): a^(-x) inside the cyclotomic subgroup
+  const uint64_t x = 0x44e992b44a6909f1ull;      // bit 62 is the leading one
+  T12 acc = a;
+  ZK_NOUNROLL for (int i = 61; i >= 0; i--) {
+    t12_sqr(acc, acc);
+    if ((x >> i) & 1) t12_mul(acc, acc, a);
+  }
+  t12_conj(r, acc);
+}
+// f^((p^12 - 1)/r * k) == 1 ?  (k not divisible by r)
+ZK_HD bool final_exp_is_one(const F12& flat, const PairingConsts& k) {
+  T12 f, g, y0, y1, y2, y3, y4, y6, t;
+  t12_from_flat(f, flat, k);
+  // easy part
+  t12_inv(t, f);
+  t12_conj(g, f);
+  t12_mul(g, g, t);            // f^(p^6 - 1)
+  t12_frob(t, g, 2, k);
+  t12_mul(g, t, g);            // ^(p^2 + 1): g is in the cyclotomic subgroup, where conj = inverse
+  // hard part
+  t12_exp_neg_x(y0, g);
+  t12_sqr(y1, y0);
+  t12_sqr(y2, y1);
+  t12_mul(y3, y2, y1);
+  t12_exp_neg_x(y4, y3);
+  t12_sqr(t, y4);              // y5
+  t12_exp_neg_x(y6, t);
+  t12_conj(y3, y3);
+  t12_conj(y6, y6);
+  t12_mul(y6, y6, y4);         // y7
+  t12_mul(y6, y6, y3);         // y8
+  t12_mul(y2, y6, y1);         // y9
+  t12_mul(y3, y6, y4);         // y10
+  t12_mul(y3, y3, g);          // y11
+  t12_frob(t, y2, 1, k);       // y12
+  t12_mul(y3, t, y3);          // y13
+  t12_frob(t, y6, 2, k);
+  t12_mul(y3, t, y3);          // y14
+  t12_conj(t, g);
+  t12_mul(t, t, y2);           // r^-1 y9
+  t12_frob(y0, t, 3, k);       // y15
+  t12_mul(y3, y0, y3);         // y16
+  return t12_is_one(y3);
+}
 
 // the proof-dependent part of the check, as the batch kernels split it:
 //   F = miller(B, -A) * miller(gamma, vk_x) * miller(delta, C) * miller(beta, alpha);   valid <=> final_exp(F) == 1

@@ -4,6 +4,7 @@
 // (SURVEY 2.4 row V1); batches go through zkfl_groth16_verify_batch on the GPU.
 #pragma once
 #include "pairing.cuh"
+#include <cstdlib>
 
 namespace zkv {
 using namespace zkp;
@@ -41,8 +42,43 @@ static int groth16_verify(const uint8_t alpha1[64], const uint8_t beta2[128], co
     if (!miller(g2s[i], g1s[i], t, k)) return 0;
     f12_mul(f, f, t, k);
   }
+  const char* flat = getenv("ZKFL_VERIFY_FLAT");   // cross-check knob: the inversion-free two-power form
+  if (!(flat && *flat && *flat != '0')) return final_exp_is_one(f, k) ? 1 : 0;
   final_half(f, 0, lhs, k);
   final_half(f, 1, rhs, k);
   return f12_eq(lhs, rhs) ? 1 : 0;
+}
+
+// consistency of the tower view with the flat basis on pseudo-random elements; 0 = all good, else the failing check
+static int pairing_selftest() {
+  const PairingConsts& k = consts();
+  F12 a, b, c, d;
+  Fq seed = fq_small(0x1234567u);
+  for (int i = 0; i < 12; i++) { seed = seed * seed + fq_small(i + 3); a.c[i] = seed; seed = seed * seed + fq_small(77); b.c[i] = seed; }
+  T12 ta, tb, tc, td;
+  t12_from_flat(ta, a, k); t12_from_flat(tb, b, k);
+  t12_to_flat(c, ta, k);
+  if (!f12_eq(c, a)) return 1;                                   // round trip
+  f12_mul(c, a, b, k); t12_mul(tc, ta, tb); t12_to_flat(d, tc, k);
+  if (!f12_eq(c, d)) return 2;                                   // product
+  f12_sqr(c, a, k); t12_sqr(tc, ta); t12_to_flat(d, tc, k);
+  if (!f12_eq(c, d)) return 3;                                   // square
+  t12_inv(tc, ta); t12_mul(tc, tc, ta);
+  if (!t12_is_one(tc)) return 4;                                 // inverse
+  f12_frob2(c, a, k); t12_frob(tc, ta, 2, k); t12_to_flat(d, tc, k);
+  if (!f12_eq(c, d)) return 5;                                   // Frobenius^2 against the flat map
+  t12_frob(tc, ta, 1, k); t12_frob(tc, tc, 1, k); t12_to_flat(d, tc, k);
+  if (!f12_eq(c, d)) return 6;                                   // Frobenius o Frobenius
+  t12_frob(tc, ta, 1, k); t12_frob(tc, tc, 2, k); t12_frob(td, ta, 3, k);
+  t12_to_flat(c, tc, k); t12_to_flat(d, td, k);
+  if (!f12_eq(c, d)) return 7;                                   // Frobenius^3
+  t12_frob(tc, td, 3, k); t12_conj(td, ta);                      // Frobenius^6 = conj
+  t12_to_flat(c, tc, k); t12_to_flat(d, td, k);
+  if (!f12_eq(c, d)) return 8;
+  t12_frob(tc, ta, 1, k); t12_frob(td, tb, 1, k); t12_mul(tc, tc, td);   // Frobenius is multiplicative
+  t12_mul(td, ta, tb); t12_frob(td, td, 1, k);
+  t12_to_flat(c, tc, k); t12_to_flat(d, td, k);
+  if (!f12_eq(c, d)) return 9;
+  return 0;
 }
 }  // namespace zkv

@@ -1154,7 +1154,10 @@ int zkfl_groth16_verify_batch(zkfl_ctx* c, const uint8_t* alpha1, const uint8_t*
     ZK_LAUNCH(k_vfy_miller, (size_t)3 * Bu + 1, 32, c->stream, k, beta, gamma, delta, alpha, c->v_g1.as<zkp::G1P>(),
               c->v_g2.as<zkp::G2P>(), Bu, c->v_f.as<zkp::F12>(), c->v_flags.as<uint32_t>());
   }
-  {
+  if (!env_u32("ZKFL_VERIFY_FLAT", 0)) {
+    Stage st(c, "verify_final_exp");
+    ZK_LAUNCH(k_vfy_final_tower, Bu, 32, c->stream, k, c->v_f.as<zkp::F12>(), c->v_flags.as<uint32_t>(), Bu, c->v_ok.as<int32_t>());
+  } else {   // cross-check knob: the inversion-free two-power form in the flat basis
     Stage st(c, "verify_final_exp");
     ZK_LAUNCH(k_vfy_final, ((size_t)Bu + 31) / 32 * 64, 64, c->stream, k, c->v_f.as<zkp::F12>(), c->v_flags.as<uint32_t>(), Bu,
               c->v_halves.as<zkp::F12>());
@@ -1165,6 +1168,7 @@ int zkfl_groth16_verify_batch(zkfl_ctx* c, const uint8_t* alpha1, const uint8_t*
   CU(cudaStreamSynchronize(c->stream));
   return 0;
 }
+int zkfl_debug_pairing_selftest(void) { return zkv::pairing_selftest(); }
 // dev / test hook: copies a named workspace buffer of the batch verifier to the host (intermediate values of the last call)
 int zkfl_debug_read(zkfl_ctx* c, const char* name, void* out, size_t bytes) {
   if (!c || !name || !out) return fail(ZKFL_ERR_ARG, "bad argument");
