@@ -953,18 +953,20 @@ ZK_GLOBAL void k_vfy_prepare(zkp::PairingConsts k, const G1Affine* __restrict__ 
 // thread t < 3B: Miller loop of pair t % 3 of proof t / 3 ((B, -A), (gamma, vk_x), (delta, C)); thread 3B: (beta, alpha), shared
 ZK_GLOBAL void k_vfy_miller(zkp::PairingConsts k, zkp::G2P beta, zkp::G2P gamma, zkp::G2P delta, zkp::G1P alpha,
                             const zkp::G1P* __restrict__ g1s, const zkp::G2P* __restrict__ g2b, uint32_t B,
-                            zkp::F12* __restrict__ f, uint32_t* __restrict__ flags) {
+                            zkp::F12* __restrict__ f, uint32_t* __restrict__ flags, int affine) {
   size_t tid = ZK_TID;
   if (tid > (size_t)3 * B) return;
+  const size_t b = tid < (size_t)3 * B ? tid / 3 : 0;
+  const uint32_t pair = tid < (size_t)3 * B ? (uint32_t)(tid % 3) : 3u;
+  if (pair < 3 && !flags[b]) return;                // malformed input: nothing to pair
+  // one code path for all four kinds of pair (selected operands, no divergent copies of the loop)
+  const zkp::G2P Q = pair == 0 ? g2b[b] : pair == 1 ? gamma : pair == 2 ? delta : beta;
+  const zkp::G1P P = pair < 3 ? g1s[tid] : alpha;
   zkp::F12 out;
-  if (tid == (size_t)3 * B) {
-    zkp::miller(beta, alpha, out, k);
+  if (affine) {                                     // cross-check form: affine line steps in the flat basis
+    if (!zkp::miller(Q, P, out, k)) { if (pair < 3) flags[b] = 0; return; }
   } else {
-    const size_t b = tid / 3;
-    const uint32_t pair = (uint32_t)(tid % 3);
-    if (!flags[b]) return;                          // malformed input: nothing to pair
-    const zkp::G2P Q = pair == 0 ? g2b[b] : pair == 1 ? gamma : delta;
-    if (!zkp::miller(Q, g1s[tid], out, k)) { flags[b] = 0; return; }
+    zkp::miller_proj(Q, P, out, k);
   }
   f[tid] = out;
 }

@@ -6,8 +6,9 @@
 // (the same representation the test oracle uses, so intermediate values can be compared), G2 arithmetic affine on the twist.  Every function is written once for host and device; the
 // big ones are loops over small bodies (no unrolling, local arrays) so that a kernel holds ONE copy of the Fq12 product, the
 // line step and the sparse product -- the device code has no calls with stack frames, only the Fq product leaf call.
-//   * lines are sparse: l = c0 + c1 w + c3 w^3 + c7 w^7 + c9 w^9 -> 60 products instead of 144;
-//   * squarings use the symmetric half: 78 products;
+//   * default Miller loop: homogeneous projective steps, accumulator in the tower view (miller_proj below); the affine loop
+//     in the flat basis (miller) is the cross-check form (`ZKFL_VERIFY_FLAT=1`): sparse lines l = c0 + c1 w + c3 w^3 + c7 w^7 +
+//     c9 w^9 -> 60 products instead of 144, squarings over the symmetric half: 78 products;
 //   * final exponentiation: easy part + x-power chain in the tower view (final_exp_is_one below, the default); the first
 //     version is kept for cross-checking (`ZKFL_VERIFY_FLAT=1`): f^((p^12-1)/r) == 1  <=>  (conj(f)/f)^((p^2+1) h) == 1,
 //     h = (p^4 - p^2 + 1)/r,  <=>  (frob2(conj f) conj f)^h == (frob2(f) f)^h  -- no Fq12 inversion, two independent 761-bit
@@ -32,6 +33,7 @@ struct PairingConsts {
   Fq2 twist_b;        // 3 / xi
   Fq2 g12, g13;       // xi^((p-1)/3), xi^((p-1)/2): Frobenius on the twist
   Fq2 frob[3][6];     // frob[k-1][m] = xi^(m (p^k - 1)/6): Frobenius^k on the coefficient of w^m (tower view below)
+  Fq half;            // 1/2
 };
 
 ZK_HD Fq fq_small(uint32_t v) { Fq r = Fq::zero(); r.v[0] = v; return r.to_mont(); }
@@ -64,6 +66,7 @@ static inline PairingConsts make_consts() {
                                   0x6ca1caa5u,0x6fea09beu,0x3f9c6113u,0x67d81a82u,0xd6398826u,0x00daed7bu,0xeb1f2783u,0x2667434cu,
                                   0x32525cfau,0xa0605a09u,0xd0fb6bfdu,0x3c036d4du,0x4083ea9du,0x88852038u,0xd72be447u,0x0049c712u};
   const Fq2 gam[3] = {fq2_pow_host(xi, F1, 8), fq2_pow_host(xi, F2, 16), fq2_pow_host(xi, F3, 24)};
+  k.half = fq_small(2).inv();
   for (int q = 0; q < 3; q++) {
     k.frob[q][0] = Fq2::one();
     for (int m = 1; m < 6; m++) k.frob[q][m] = k.frob[q][m - 1] * gam[q];
@@ -296,9 +299,9 @@ ZK_HD void t12_exp_neg_x(T12& r, const T12& a) {   // conj(a^x): a^(-x) inside t
   }
   t12_conj(r, acc);
 }
-// f^((p^12 - 1)/r * k) == 1 ?  (k not divisible by r)
-ZK_HD bool final_exp_is_one(const F12& flat, const PairingConsts& k) {
-  T12 f, g, y0, y1, y2, y3, y4, y6, t;
+// out = f^((p^12 - 1)/r * k)  (k not divisible by r)
+ZK_HD void final_exp_value(const F12& flat, T12& y3, const PairingConsts& k) {
+  T12 f, g, y0, y1, y2, y4, y6, t;
   t12_from_flat(f, flat, k);
   // easy part
   t12_inv(t, f);
@@ -329,7 +332,82 @@ ZK_HD bool final_exp_is_one(const F12& flat, const PairingConsts& k) {
   t12_mul(t, t, y2);           // r^-1 y9
   t12_frob(y0, t, 3, k);       // y15
   t12_mul(y3, y0, y3);         // y16
-  return t12_is_one(y3);
+}
+ZK_HD bool final_exp_is_one(const F12& flat, const PairingConsts& k) {
+  T12 v;
+  final_exp_value(flat, v, k);
+  return t12_is_one(v);
+}
+
+// ------------------------------------------------------------------------------ Miller loop without inversions
+// Homogeneous projective steps on the twist (Costello-Lange-Naehrig formulas as commonly implemented for D-type twists) and
+// the accumulator in the tower view: a doubling step is 57 (square) + 28 (point and line) + 58 (sparse product) Fq products
+// against ~290 with the affine line step, whose slope inversion alone is a third of the loop.  The lines differ from the
+// affine ones by Fq2 factors, which the final exponentiation removes: the Miller values differ, the pairing values do not
+// (zkfl_debug_pairing_selftest compares the exponentiated values of both loops).
+struct G2H { Fq2 x, y, z; };
+struct LineT { Fq2 c0, c1, c3; };   // c0 + c1 w + c3 w^3, before the evaluation at P (c0 *= yP, c1 *= xP)
+ZK_HD Fq2 fq2_scale(const Fq2& x, const Fq& s) { Fq2 r; r.a = x.a * s; r.b = x.b * s; return r; }
+ZK_HD void proj_dbl_step(G2H& r, LineT& l, const PairingConsts& k) {
+  const Fq2 a = fq2_scale(r.x * r.y, k.half);
+  const Fq2 b = r.y.sqr(), c = r.z.sqr();
+  const Fq2 e = k.twist_b * (c.dbl() + c);
+  const Fq2 f = e.dbl() + e;
+  const Fq2 g = fq2_scale(b + f, k.half);
+  const Fq2 h = (r.y + r.z).sqr() - (b + c);
+  const Fq2 j = r.x.sqr();
+  const Fq2 e2 = e.sqr();
+  l.c0 = h.neg(); l.c1 = j.dbl() + j; l.c3 = e - b;
+  r.x = a * (b - f);
+  r.y = g.sqr() - (e2.dbl() + e2);
+  r.z = b * h;
+}
+ZK_HD void proj_add_step(G2H& r, const G2P& q, LineT& l) {
+  const Fq2 theta = r.y - q.y * r.z, lambda = r.x - q.x * r.z;
+  const Fq2 c = theta.sqr(), d = lambda.sqr();
+  const Fq2 e = lambda * d, f = r.z * c, g = r.x * d;
+  const Fq2 h = e + f - g.dbl();
+  l.c0 = lambda; l.c1 = theta.neg(); l.c3 = theta * q.x - lambda * q.y;
+  r.x = lambda * h;
+  r.y = theta * (g - h) - e * r.y;
+  r.z = r.z * e;
+}
+// f <- f * (c0 yP + c1 xP w + c3 w^3)
+ZK_HD void t12_mul_line(T12& f, const LineT& l, const G1P& P) {
+  const Fq2 c0 = fq2_scale(l.c0, P.y), c1 = fq2_scale(l.c1, P.x);
+  Fq2 t[11];
+  ZK_NOUNROLL for (int i = 0; i < 11; i++) t[i] = Fq2::zero();
+  ZK_NOUNROLL for (int s = 0; s < 3; s++) {
+    const int d = s == 0 ? 0 : s == 1 ? 1 : 3;
+    const Fq2 li = s == 0 ? c0 : s == 1 ? c1 : l.c3;
+    ZK_NOUNROLL for (int j = 0; j < 6; j++) t[d + j] = t[d + j] + li * f.c[j];
+  }
+  t12_reduce(f, t);
+}
+ZK_HD void miller_proj(const G2P& Q, const G1P& P, F12& out, const PairingConsts& k) {
+  T12 f;
+  ZK_NOUNROLL for (int m = 0; m < 6; m++) f.c[m] = Fq2::zero();
+  f.c[0] = Fq2::one();
+  if (!(Q.inf || P.inf)) {
+    const uint64_t ate = 0x9d797039be763ba8ull;  // low 64 bits of 6x + 2, bit 64 is the implicit leading one
+    G2P Q1; Q1.inf = 0; Q1.x = fq2_conj(Q.x) * k.g12; Q1.y = fq2_conj(Q.y) * k.g13;
+    G2P Q2; Q2.inf = 0; Q2.x = fq2_conj(Q1.x) * k.g12; Q2.y = (fq2_conj(Q1.y) * k.g13).neg();
+    G2H R; R.x = Q.x; R.y = Q.y; R.z = Fq2::one();
+    LineT l;
+    int i = 63, phase = 0;   // phase 0: doubling of bit i, 1: addition of bit i, 2: + Q1, 3: + Q2
+    ZK_NOUNROLL for (;;) {
+      if (phase == 0) { t12_sqr(f, f); proj_dbl_step(R, l, k); }
+      else proj_add_step(R, phase == 1 ? Q : phase == 2 ? Q1 : Q2, l);
+      t12_mul_line(f, l, P);
+      if (phase == 0) {
+        if ((ate >> i) & 1) phase = 1; else if (i == 0) phase = 2; else i--;
+      } else if (phase == 1) {
+        if (i == 0) phase = 2; else { phase = 0; i--; }
+      } else if (phase == 2) phase = 3;
+      else break;
+    }
+  }
+  t12_to_flat(out, f, k);
 }
 
 // the proof-dependent part of the check, as the batch kernels split it:

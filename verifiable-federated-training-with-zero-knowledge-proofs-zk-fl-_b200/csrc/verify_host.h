@@ -38,12 +38,14 @@ static int groth16_verify(const uint8_t alpha1[64], const uint8_t beta2[128], co
   memcpy(w, delta2, 128); g2s[3] = g2_from_canonical(w);
   F12 f, t, lhs, rhs;
   f12_set_one(f);
+  const char* flat_env = getenv("ZKFL_VERIFY_FLAT");   // cross-check knob: affine line steps + the two-power final check
+  const bool flat = flat_env && *flat_env && *flat_env != '0';
   for (int i = 0; i < 4; i++) {
-    if (!miller(g2s[i], g1s[i], t, k)) return 0;
+    if (flat) { if (!miller(g2s[i], g1s[i], t, k)) return 0; }
+    else miller_proj(g2s[i], g1s[i], t, k);
     f12_mul(f, f, t, k);
   }
-  const char* flat = getenv("ZKFL_VERIFY_FLAT");   // cross-check knob: the inversion-free two-power form
-  if (!(flat && *flat && *flat != '0')) return final_exp_is_one(f, k) ? 1 : 0;
+  if (!flat) return final_exp_is_one(f, k) ? 1 : 0;
   final_half(f, 0, lhs, k);
   final_half(f, 1, rhs, k);
   return f12_eq(lhs, rhs) ? 1 : 0;
@@ -79,6 +81,31 @@ static int pairing_selftest() {
   t12_mul(td, ta, tb); t12_frob(td, td, 1, k);
   t12_to_flat(c, tc, k); t12_to_flat(d, td, k);
   if (!f12_eq(c, d)) return 9;
+  // the inversion-free Miller loop against the affine one: different Miller values, same pairing value
+  {
+    static const uint32_t G2X0[8] = {0xd992f6edu, 0x46debd5cu, 0xf75edaddu, 0x674322d4u, 0x5e5c4479u, 0x426a0066u, 0x121f1e76u, 0x1800deefu};
+    static const uint32_t G2X1[8] = {0xaef312c2u, 0x97e485b7u, 0x35a9e712u, 0xf1aa4933u, 0x31fb5d25u, 0x7260bfb7u, 0x920d483au, 0x198e9393u};
+    static const uint32_t G2Y0[8] = {0x66fa7daau, 0x4ce6cc01u, 0x0c43d37bu, 0xe3d1e769u, 0x8dcb408fu, 0x4aab7180u, 0xdb8c6debu, 0x12c85ea5u};
+    static const uint32_t G2Y1[8] = {0xd122975bu, 0x55acdadcu, 0x70b38ef3u, 0xbc4b3133u, 0x690c3395u, 0xec9e99adu, 0x585ff075u, 0x090689d0u};
+    uint32_t w[32];
+    memcpy(w, G2X0, 32); memcpy(w + 8, G2X1, 32); memcpy(w + 16, G2Y0, 32); memcpy(w + 24, G2Y1, 32);
+    const G2P Q = g2_from_canonical(w);
+    uint32_t g[16] = {1, 0, 0, 0, 0, 0, 0, 0, 2, 0, 0, 0, 0, 0, 0, 0};
+    G1P P = g1_from_canonical(g);
+    if (!g2_on_curve(Q, k) || !g1_on_curve(P, k)) return 10;
+    for (int rep = 0; rep < 2; rep++) {
+      F12 ma, mp;
+      if (!miller(Q, P, ma, k)) return 11;
+      miller_proj(Q, P, mp, k);
+      T12 va, vp;
+      final_exp_value(ma, va, k); final_exp_value(mp, vp, k);
+      t12_to_flat(c, va, k); t12_to_flat(d, vp, k);
+      if (!f12_eq(c, d)) return 12 + rep;
+      if (t12_is_one(va)) return 14;                             // e(G1, G2) != 1
+      zk::G1Xyzz P5 = zk::xyzz_dbl(zk::xyzz_dbl(zk::G1Xyzz::from_affine(g1_to_affine(P))));   // another G1 point: 4 G
+      P = g1_from_xyzz(P5);
+    }
+  }
   return 0;
 }
 }  // namespace zkv

@@ -1152,7 +1152,7 @@ int zkfl_groth16_verify_batch(zkfl_ctx* c, const uint8_t* alpha1, const uint8_t*
   {
     Stage st(c, "verify_miller");
     ZK_LAUNCH(k_vfy_miller, (size_t)3 * Bu + 1, 32, c->stream, k, beta, gamma, delta, alpha, c->v_g1.as<zkp::G1P>(),
-              c->v_g2.as<zkp::G2P>(), Bu, c->v_f.as<zkp::F12>(), c->v_flags.as<uint32_t>());
+              c->v_g2.as<zkp::G2P>(), Bu, c->v_f.as<zkp::F12>(), c->v_flags.as<uint32_t>(), (int)env_u32("ZKFL_VERIFY_FLAT", 0));
   }
   if (!env_u32("ZKFL_VERIFY_FLAT", 0)) {
     Stage st(c, "verify_final_exp");
