@@ -72,3 +72,6 @@ def test_host_verifier_in_the_real_library_without_a_gpu():
     assert not sj.groth16.verify(vk, [str(2 ** 255), "17"], proof)
     bad = dict(proof, pi_a=[proof["pi_a"][1], proof["pi_a"][0], "1"])
     assert not sj.groth16.verify(vk, ["228", "17"], bad)
+    # the two views of Fq12, the Frobenius maps and both Miller loops agree in the nvcc host build as well
+    from zkfl_b200 import _lib
+    assert _lib.load().zkfl_debug_pairing_selftest() == 0
