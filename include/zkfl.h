@@ -106,6 +106,19 @@ int zkfl_groth16_msm_partials(zkfl_ctx* ctx, const zkfl_zkey* z, const uint8_t* 
 int zkfl_groth16_finalize(zkfl_ctx* ctx, const zkfl_zkey* z, const uint8_t* partials /* nparts x B x 384 */, uint32_t nparts,
                           const uint8_t* rs, int B, uint8_t* proofs_out /* B x 256 */);
 
+/* ---- single-proof forms (what one `generate_witness.cjs` / `snarkjs groth16 prove` process does,
+ *      tests/full_system_simulation.mjs:760-762,773-775): the batch entry points above with B = 1.
+ *      r, s: 32-byte canonical blinding scalars, or NULL for random ones (what snarkjs does). ------------------------- */
+int zkfl_wtns_calculate(zkfl_ctx* ctx, const zkfl_circuit* c, const zkfl_r1cs* r1cs, const uint8_t* inputs, uint8_t* wtns_out,
+                        uint32_t* first_bad);
+int zkfl_groth16_prove(zkfl_ctx* ctx, const zkfl_zkey* z, const uint8_t* wtns, const uint8_t* r, const uint8_t* s,
+                       uint8_t proof_out[256], uint8_t* public_out);
+int zkfl_groth16_full_prove(zkfl_ctx* ctx, const zkfl_circuit* c, const zkfl_zkey* z, const uint8_t* inputs, const uint8_t* r,
+                            const uint8_t* s, uint8_t proof_out[256], uint8_t* public_out);
+/* snarkjs's proof.json / public.json texts from the binary encodings (decimal strings, "protocol": "groth16", "curve": "bn128") */
+int zkfl_proof_to_json(const uint8_t proof[256], char* buf, size_t cap);
+int zkfl_public_to_json(const uint8_t* publics, uint32_t n_public, char* buf, size_t cap);
+
 /* ---- verify: `snarkjs groth16 verify vkey.json public.json proof.json`
  *      (tests/full_system_simulation.mjs:865-868,975-978,1116-1119). Host-side pairing check (SURVEY 2.4 row V1:
  *      verification stays on the CPU). All points affine canonical little-endian as in vkey.json / proof.json:

@@ -70,6 +70,47 @@ def test_batch_verifier_matches_oracle_and_host_verifier(emul_prover, monkeypatc
     pc.case_verify_batch(emul_prover, zk, proofs, pubs)
 
 
+def test_single_proof_entry_points_and_json_writers(emul_prover):
+    """SURVEY 8b's single-proof forms (zkfl_wtns_calculate / zkfl_groth16_prove / zkfl_groth16_full_prove) equal the batch
+    calls with B = 1, and zkfl_proof_to_json / zkfl_public_to_json write snarkjs's proof.json / public.json."""
+    import ctypes
+    import json
+    from zkfl_b200 import formats
+    P, lib = emul_prover, emul_prover.lib
+    cc = pc.tiny_circuit()
+    circ = P.load_circuit(cc)
+    zk = P.new_zkey(cc, b"single")
+    Z = P.load_zkey(zk)
+    packed = circ.pack_inputs(pc.tiny_inputs()[:1])
+    ws = P.calculate_witness(circ, packed)
+    proofs, pubs = P.prove(Z, ws, [(5, 9)])
+    w1 = ctypes.create_string_buffer(32 * cc.n_wires)
+    bad = (ctypes.c_uint32 * 1)()
+    P._check(lib.zkfl_wtns_calculate(P.ctx, circ.handle, circ.r1cs_handle, _lib.as_ptr(packed), w1, bad))
+    assert w1.raw == ws[0]
+    r, s_ = (5).to_bytes(32, "little"), (9).to_bytes(32, "little")
+    p1, q1 = ctypes.create_string_buffer(256), ctypes.create_string_buffer(32 * Z.n_public)
+    P._check(lib.zkfl_groth16_prove(P.ctx, Z.handle, _lib.as_ptr(ws[0]), _lib.as_ptr(r), _lib.as_ptr(s_), p1, q1))
+    assert (p1.raw, q1.raw) == (proofs[0], pubs[0])
+    p2, q2 = ctypes.create_string_buffer(256), ctypes.create_string_buffer(32 * Z.n_public)
+    P._check(lib.zkfl_groth16_full_prove(P.ctx, circ.handle, Z.handle, _lib.as_ptr(packed), _lib.as_ptr(r), _lib.as_ptr(s_), p2, q2))
+    assert (p2.raw, q2.raw) == (proofs[0], pubs[0])
+    p3 = ctypes.create_string_buffer(256)                                   # r, s = NULL: random blinding, still a valid proof
+    P._check(lib.zkfl_groth16_prove(P.ctx, Z.handle, _lib.as_ptr(ws[0]), None, None, p3, q2))
+    assert p3.raw != proofs[0] and P.verify_batch(formats.vkey_json_to_bytes(formats.export_verification_key(zk)), [pubs[0]], [p3.raw]) == [True]
+    buf = ctypes.create_string_buffer(4096)
+    P._check(lib.zkfl_proof_to_json(_lib.as_ptr(proofs[0]), buf, len(buf)))
+    assert json.loads(buf.value) == formats.proof_bytes_to_json(proofs[0])
+    P._check(lib.zkfl_public_to_json(_lib.as_ptr(pubs[0]), Z.n_public, buf, len(buf)))
+    assert json.loads(buf.value) == formats.publics_bytes_to_json(pubs[0])
+    edge = b"".join(v.to_bytes(32, "little") for v in (0, 1, 10 ** 9, 10 ** 18 - 1, 2 ** 256 - 1))
+    P._check(lib.zkfl_public_to_json(_lib.as_ptr(edge), 5, buf, len(buf)))
+    assert json.loads(buf.value) == [str(v) for v in (0, 1, 10 ** 9, 10 ** 18 - 1, 2 ** 256 - 1)]
+    assert lib.zkfl_proof_to_json(_lib.as_ptr(proofs[0]), buf, 10) != 0     # buffer too small: an error, not a truncation
+    Z.close()
+    circ.close()
+
+
 def test_failed_constraint_raises_assert(emul_prover):
     cc = pc.tiny_circuit()
     circ = emul_prover.load_circuit(cc)

@@ -19,7 +19,8 @@ SYMBOLS = [
     "zkfl_full_prove_run", "zkfl_full_prove_fetch", "zkfl_g1_msm", "zkfl_g2_msm", "zkfl_msm_bases_load",
     "zkfl_msm_bases_free", "zkfl_msm_run", "zkfl_g1_mul_generator", "zkfl_g2_mul_generator",
     "zkfl_launch_count", "zkfl_prof_enable", "zkfl_prof_read", "zkfl_bench_modmul", "zkfl_bench_imad", "zkfl_bench_widemac",
-    "zkfl_timer_begin", "zkfl_timer_end", "zkfl_groth16_verify", "zkfl_groth16_verify_batch", "zkfl_debug_read", "zkfl_debug_pairing_selftest", "zkfl_groth16_msm_partials", "zkfl_groth16_finalize", "zkfl_ctx_wait_other",
+    "zkfl_timer_begin", "zkfl_timer_end", "zkfl_groth16_verify", "zkfl_groth16_verify_batch", "zkfl_debug_read", "zkfl_debug_pairing_selftest", "zkfl_wtns_calculate", "zkfl_groth16_prove", "zkfl_groth16_full_prove",
+    "zkfl_proof_to_json", "zkfl_public_to_json", "zkfl_groth16_msm_partials", "zkfl_groth16_finalize", "zkfl_ctx_wait_other",
 ]
 
 _libs = {}
@@ -78,6 +79,11 @@ def load(path: str | None = None):
         "zkfl_groth16_verify_batch": (i, [vp, vp, vp, vp, vp, vp, ctypes.c_uint32, vp, vp, i, vp]),
         "zkfl_debug_read": (i, [vp, ctypes.c_char_p, vp, sz]),
         "zkfl_debug_pairing_selftest": (i, []),
+        "zkfl_wtns_calculate": (i, [vp, vp, vp, vp, vp, vp]),
+        "zkfl_groth16_prove": (i, [vp, vp, vp, vp, vp, vp, vp]),
+        "zkfl_groth16_full_prove": (i, [vp, vp, vp, vp, vp, vp, vp, vp]),
+        "zkfl_proof_to_json": (i, [vp, ctypes.c_char_p, sz]),
+        "zkfl_public_to_json": (i, [vp, ctypes.c_uint32, ctypes.c_char_p, sz]),
         "zkfl_groth16_msm_partials": (i, [vp, vp, vp, i, ctypes.c_uint32, ctypes.c_uint32, vp]),
         "zkfl_groth16_finalize": (i, [vp, vp, vp, ctypes.c_uint32, vp, i, vp]),
         "zkfl_ctx_wait_other": (i, [vp, vp]),

@@ -1168,6 +1168,59 @@ int zkfl_groth16_verify_batch(zkfl_ctx* c, const uint8_t* alpha1, const uint8_t*
   CU(cudaStreamSynchronize(c->stream));
   return 0;
 }
+// ---- single-proof forms of SURVEY 8b's list (one snarkjs / witness-calculator process each in the reference): B = 1 of the batch
+int zkfl_wtns_calculate(zkfl_ctx* c, const zkfl_circuit* k, const zkfl_r1cs* r, const uint8_t* inputs, uint8_t* wtns_out, uint32_t* first_bad) {
+  return zkfl_wtns_calculate_batch(c, k, r, inputs, 1, wtns_out, first_bad);
+}
+static const uint8_t* join_rs(const uint8_t* r, const uint8_t* s, uint8_t out[64]) {
+  if (!r || !s) return nullptr;            // NULL -> CSPRNG, like snarkjs
+  memcpy(out, r, 32); memcpy(out + 32, s, 32);
+  return out;
+}
+int zkfl_groth16_prove(zkfl_ctx* c, const zkfl_zkey* z, const uint8_t* wtns, const uint8_t* r, const uint8_t* s, uint8_t proof_out[256],
+                       uint8_t* public_out) {
+  uint8_t rs[64];
+  return zkfl_groth16_prove_batch(c, z, wtns, join_rs(r, s, rs), 1, proof_out, public_out);
+}
+int zkfl_groth16_full_prove(zkfl_ctx* c, const zkfl_circuit* k, const zkfl_zkey* z, const uint8_t* inputs, const uint8_t* r, const uint8_t* s,
+                            uint8_t proof_out[256], uint8_t* public_out) {
+  uint8_t rs[64];
+  return zkfl_groth16_full_prove_batch(c, k, z, inputs, join_rs(r, s, rs), 1, proof_out, public_out);
+}
+// ---- snarkjs JSON shapes (proof.json / public.json) from the binary encodings; host code
+static std::string dec_from_le32(const uint8_t* p) {
+  uint32_t w[8]; memcpy(w, p, 32);
+  std::string digits;
+  for (;;) {
+    uint64_t rem = 0; bool nz = false;
+    for (int i = 7; i >= 0; i--) { uint64_t cur = (rem << 32) | w[i]; w[i] = (uint32_t)(cur / 1000000000u); rem = cur % 1000000000u; nz = nz || w[i]; }
+    char buf[16];
+    snprintf(buf, sizeof buf, nz ? "%09u" : "%u", (unsigned)rem);
+    digits.insert(0, buf);
+    if (!nz) break;
+  }
+  return digits;
+}
+static int put_json(const std::string& s, char* buf, size_t cap) {
+  if (s.size() + 1 > cap) return fail(ZKFL_ERR_ARG, "buffer too small");
+  memcpy(buf, s.c_str(), s.size() + 1);
+  return 0;
+}
+int zkfl_proof_to_json(const uint8_t proof[256], char* buf, size_t cap) {
+  if (!proof || !buf) return fail(ZKFL_ERR_ARG, "bad argument");
+  std::string v[8];
+  for (int i = 0; i < 8; i++) v[i] = "\"" + dec_from_le32(proof + 32 * i) + "\"";
+  std::string j = "{\"pi_a\": [" + v[0] + ", " + v[1] + ", \"1\"], \"pi_b\": [[" + v[2] + ", " + v[3] + "], [" + v[4] + ", " + v[5] +
+                  "], [\"1\", \"0\"]], \"pi_c\": [" + v[6] + ", " + v[7] + ", \"1\"], \"protocol\": \"groth16\", \"curve\": \"bn128\"}";
+  return put_json(j, buf, cap);
+}
+int zkfl_public_to_json(const uint8_t* publics, uint32_t n_public, char* buf, size_t cap) {
+  if ((!publics && n_public) || !buf) return fail(ZKFL_ERR_ARG, "bad argument");
+  std::string j = "[";
+  for (uint32_t i = 0; i < n_public; i++) j += (i ? ", \"" : "\"") + dec_from_le32(publics + 32 * (size_t)i) + "\"";
+  j += "]";
+  return put_json(j, buf, cap);
+}
 int zkfl_debug_pairing_selftest(void) { return zkv::pairing_selftest(); }
 // dev / test hook: copies a named workspace buffer of the batch verifier to the host (intermediate values of the last call)
 int zkfl_debug_read(zkfl_ctx* c, const char* name, void* out, size_t bytes) {
