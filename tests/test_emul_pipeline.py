@@ -98,6 +98,14 @@ def test_single_proof_entry_points_and_json_writers(emul_prover):
     p3 = ctypes.create_string_buffer(256)                                   # r, s = NULL: random blinding, still a valid proof
     P._check(lib.zkfl_groth16_prove(P.ctx, Z.handle, _lib.as_ptr(ws[0]), None, None, p3, q2))
     assert p3.raw != proofs[0] and P.verify_batch(formats.vkey_json_to_bytes(formats.export_verification_key(zk)), [pubs[0]], [p3.raw]) == [True]
+    # one contiguous witness buffer (bytearray / torch tensor: pinned or device memory on the GPU) instead of a list
+    import torch
+    two = P.calculate_witness(circ, circ.pack_inputs(pc.tiny_inputs()[:2]))
+    ref2 = P.prove(Z, two, [(5, 9), (6, 7)])
+    assert P.prove(Z, bytearray(b"".join(two)), [(5, 9), (6, 7)]) == ref2
+    assert P.prove(Z, torch.frombuffer(bytearray(b"".join(two)), dtype=torch.uint8), [(5, 9), (6, 7)]) == ref2
+    with pytest.raises(ValueError):
+        P.prove(Z, bytearray(b"".join(two))[:-1], [(5, 9), (6, 7)])
     buf = ctypes.create_string_buffer(4096)
     P._check(lib.zkfl_proof_to_json(_lib.as_ptr(proofs[0]), buf, len(buf)))
     assert json.loads(buf.value) == formats.proof_bytes_to_json(proofs[0])
