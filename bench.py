@@ -295,7 +295,7 @@ def main():
     prover = provers[0]
     # the compiled program and the proving key (coefficients, window-shifted base tables: ~100 MB) are read-only device
     # data: ONE resident copy is shared by all contexts of this GPU, so the tables stay L2-resident
-    circuit = prover.load_circuit(cc, check_constraints=False)
+    circuit = prover.load_circuit(cc)      # with its R1CS: the `===` check runs on the device inside every proving pass, as fullProve does
     zkey = prover.load_zkey(zk)
     circuits, zkeys = [circuit] * lanes, [zkey] * lanes
     ins, rs = synth_inputs(circuit, B, args.distinct, rank)
@@ -315,7 +315,7 @@ def main():
 
     def run_resident():
         for k, p in enumerate(provers):
-            p.run_staged(circuits[k], zkeys[k], bounds[k][1] - bounds[k][0])
+            p.run_staged(circuits[k], zkeys[k], bounds[k][1] - bounds[k][0], check=True)
 
     def fetch_all():
         for k, p in enumerate(provers):
@@ -389,10 +389,10 @@ def main():
         # ---- per-stage profile of one more step (CUDA events on the library's stream) + rooflines
         # (a full batch on one context, so the stage times below are for B proofs without lane overlap)
         prover.stage(circuit, zkey, pin_in.data_ptr(), pin_rs.data_ptr(), B)
-        prover.run_staged(circuit, zkey, B)
+        prover.run_staged(circuit, zkey, B, check=True)
         prover.fetch(1, None)
         prover.prof_enable(True)
-        prover.run_staged(circuit, zkey, B)
+        prover.run_staged(circuit, zkey, B, check=True)
         prof = prover.prof_read()
         prover.prof_enable(False)
         m, n, l = zkey.n_vars, zkey.domain, zkey.n_public

@@ -83,18 +83,25 @@ int zkfl_wtns_eval_wires(zkfl_ctx* ctx, const zkfl_circuit* c, const uint8_t* in
 /* ---- prove: `snarkjs groth16 prove zkey wtns proof.json public.json`
  *      (tests/full_system_simulation.mjs:773-775 and five more call sites), batched ---- */
 /* wtns: B x n_vars; rs: B x 64 bytes (r then s, canonical, < r) or NULL for OS randomness
- * (snarkjs draws r,s from a CSPRNG); proofs_out: B x 256; publics_out: B x n_public x 32 (may be NULL) */
+ * (snarkjs draws r,s from a CSPRNG); proofs_out: B x 256; publics_out: B x n_public x 32 (may be NULL).
+ * The witness must be well-formed (every element < r, wire 0 == 1; checked on the device) else ZKFL_ERR_ARG. */
 int zkfl_groth16_prove_batch(zkfl_ctx* ctx, const zkfl_zkey* z, const uint8_t* wtns, const uint8_t* rs, int B,
                              uint8_t* proofs_out, uint8_t* publics_out);
-/* `snarkjs.groth16.fullProve(input, wasm, zkey)` batched: witness stays in HBM between the two steps */
-int zkfl_groth16_full_prove_batch(zkfl_ctx* ctx, const zkfl_circuit* c, const zkfl_zkey* z, const uint8_t* inputs,
-                                  const uint8_t* rs, int B, uint8_t* proofs_out, uint8_t* publics_out);
+/* `snarkjs.groth16.fullProve(input, wasm, zkey)` batched: witness stays in HBM between the two steps.
+ * Inputs must be reduced mod r (else ZKFL_ERR_ARG).  r1cs != NULL: every `===` is checked on the HBM-resident witness in
+ * the same pass (circom aborts fullProve on a failed assert): any violation -> ZKFL_ERR_ASSERT, proofs_out zeroed,
+ * first_bad[b] (B entries, may be NULL) = first violated constraint or 0xFFFFFFFF.  r1cs == NULL: no check (the caller
+ * vouches for the inputs, e.g. a benchmark replaying known-good instances). */
+int zkfl_groth16_full_prove_batch(zkfl_ctx* ctx, const zkfl_circuit* c, const zkfl_zkey* z, const zkfl_r1cs* r1cs,
+                                  const uint8_t* inputs, const uint8_t* rs, int B, uint8_t* proofs_out, uint8_t* publics_out,
+                                  uint32_t* first_bad);
 /* device-resident variant for steady-state measurement: stage() copies inputs and rs to HBM once,
  * run() proves from HBM leaving proofs in HBM, fetch() copies B x 256 proof bytes back. */
 int zkfl_full_prove_stage(zkfl_ctx* ctx, const zkfl_circuit* c, const zkfl_zkey* z, const uint8_t* inputs,
                           const uint8_t* rs, int B);
-int zkfl_full_prove_run(zkfl_ctx* ctx, const zkfl_circuit* c, const zkfl_zkey* z, int B);
-int zkfl_full_prove_fetch(zkfl_ctx* ctx, int B, uint8_t* proofs_out);
+int zkfl_full_prove_run(zkfl_ctx* ctx, const zkfl_circuit* c, const zkfl_zkey* z, const zkfl_r1cs* r1cs /* may be NULL */, int B);
+/* synchronises; reports the constraint check of the run (ZKFL_ERR_ASSERT, first_bad as above; first_bad may be NULL) */
+int zkfl_full_prove_fetch(zkfl_ctx* ctx, int B, uint8_t* proofs_out, uint32_t* first_bad);
 
 /* ---- one large proof split across GPUs (BASELINE.json configs[4]): rank `part` of `nparts` runs the five
  *      multi-scalar multiplications over ITS point range [part*m/nparts, (part+1)*m/nparts) and returns the partial
@@ -113,8 +120,8 @@ int zkfl_wtns_calculate(zkfl_ctx* ctx, const zkfl_circuit* c, const zkfl_r1cs* r
                         uint32_t* first_bad);
 int zkfl_groth16_prove(zkfl_ctx* ctx, const zkfl_zkey* z, const uint8_t* wtns, const uint8_t* r, const uint8_t* s,
                        uint8_t proof_out[256], uint8_t* public_out);
-int zkfl_groth16_full_prove(zkfl_ctx* ctx, const zkfl_circuit* c, const zkfl_zkey* z, const uint8_t* inputs, const uint8_t* r,
-                            const uint8_t* s, uint8_t proof_out[256], uint8_t* public_out);
+int zkfl_groth16_full_prove(zkfl_ctx* ctx, const zkfl_circuit* c, const zkfl_zkey* z, const zkfl_r1cs* r1cs /* may be NULL */,
+                            const uint8_t* inputs, const uint8_t* r, const uint8_t* s, uint8_t proof_out[256], uint8_t* public_out);
 /* snarkjs's proof.json / public.json texts from the binary encodings (decimal strings, "protocol": "groth16", "curve": "bn128") */
 int zkfl_proof_to_json(const uint8_t proof[256], char* buf, size_t cap);
 int zkfl_public_to_json(const uint8_t* publics, uint32_t n_public, char* buf, size_t cap);
@@ -156,6 +163,11 @@ int zkfl_msm_run(zkfl_ctx* ctx, void* handle, const uint8_t* scalars /* host, or
  *      k_i * G for every key scalar; out = affine Montgomery (zkey point layout) ------------------ */
 int zkfl_g1_mul_generator(zkfl_ctx* ctx, const uint8_t* scalars, size_t n, uint8_t* out /* n x 64 */);
 int zkfl_g2_mul_generator(zkfl_ctx* ctx, const uint8_t* scalars, size_t n, uint8_t* out /* n x 128 */);
+
+/* `snarkjs zkey contribute <in> <out> --name= -e=` (tests/full_system_simulation.mjs:726-731) multiplies delta by a fresh
+ * secret d and the C / H sections by 1/d: out[i] = scalar * pts[i], points affine Montgomery (zkey layout), scalar canonical */
+int zkfl_g1_scale_points(zkfl_ctx* ctx, const uint8_t* pts, size_t n, const uint8_t scalar[32], uint8_t* out /* n x 64 */);
+int zkfl_g2_scale_points(zkfl_ctx* ctx, const uint8_t* pts, size_t n, const uint8_t scalar[32], uint8_t* out /* n x 128 */);
 
 /* ---- measurement --------------------------------------------------------------------------- */
 /* number of CUDA kernels this library has launched in this process */

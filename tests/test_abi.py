@@ -75,3 +75,17 @@ def test_host_verifier_in_the_real_library_without_a_gpu():
     # the two views of Fq12, the Frobenius maps and both Miller loops agree in the nvcc host build as well
     from zkfl_b200 import _lib
     assert _lib.load().zkfl_debug_pairing_selftest() == 0
+
+
+def test_napi_addon_source_compiles_and_binds_only_declared_symbols():
+    """bindings/node/zkfl_napi.cc (the in-process Node.js binding of INTEGRATION.md section 2) cannot be built into an addon here
+    (no Node.js headers on the image), but its source must stay in step with the C ABI: it compiles against the declaration stub
+    of <node_api.h> with include/zkfl.h's real prototypes (so every call has the right arity and types), and every zkfl_* it
+    calls is a symbol the header declares."""
+    src = os.path.join(ROOT, "bindings", "node", "zkfl_napi.cc")
+    subprocess.check_call(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-Werror", "-DNODE_GYP_MODULE_NAME=zkfl_napi",
+                           "-I" + os.path.join(ROOT, "tests", "stubs"), "-I" + os.path.join(ROOT, "include"), src])
+    code = re.sub(r"//[^\n]*", "", open(src).read())
+    used = set(re.findall(r"\b(zkfl_[a-z0-9_]+)\s*\(", code))
+    assert used and used <= set(declared_symbols()), used - set(declared_symbols())
+    assert {"zkfl_groth16_full_prove_batch", "zkfl_groth16_verify_batch", "zkfl_wtns_calculate_batch", "zkfl_groth16_prove_batch"} <= used

@@ -61,7 +61,8 @@ def test_batch_affine_accumulation(emul_prover, monkeypatch):
 
 def test_batch_verifier_matches_oracle_and_host_verifier(emul_prover, monkeypatch):
     import __graft_entry__ as ge
-    monkeypatch.setenv("ZKFL_LIBRARY_PATH", ge.build_emul())   # the single-proof verifier of the same (emulated) build
+    from zkfl_b200 import snarkjs as sj
+    monkeypatch.setitem(sj._state, "lib_path", ge.build_emul())   # the single-proof verifier of the same (emulated) build
     assert emul_prover.lib.zkfl_debug_pairing_selftest() == 0     # tower view of Fq12 against the flat basis
     cc = pc.tiny_circuit()
     zk, proofs, pubs = pc.case_prove(emul_prover, cc, pc.tiny_inputs(), [(11, 22), (33, 44), (0, 0)], python_verify=0)
@@ -93,7 +94,7 @@ def test_single_proof_entry_points_and_json_writers(emul_prover):
     P._check(lib.zkfl_groth16_prove(P.ctx, Z.handle, _lib.as_ptr(ws[0]), _lib.as_ptr(r), _lib.as_ptr(s_), p1, q1))
     assert (p1.raw, q1.raw) == (proofs[0], pubs[0])
     p2, q2 = ctypes.create_string_buffer(256), ctypes.create_string_buffer(32 * Z.n_public)
-    P._check(lib.zkfl_groth16_full_prove(P.ctx, circ.handle, Z.handle, _lib.as_ptr(packed), _lib.as_ptr(r), _lib.as_ptr(s_), p2, q2))
+    P._check(lib.zkfl_groth16_full_prove(P.ctx, circ.handle, Z.handle, circ.r1cs_handle, _lib.as_ptr(packed), _lib.as_ptr(r), _lib.as_ptr(s_), p2, q2))
     assert (p2.raw, q2.raw) == (proofs[0], pubs[0])
     p3 = ctypes.create_string_buffer(256)                                   # r, s = NULL: random blinding, still a valid proof
     P._check(lib.zkfl_groth16_prove(P.ctx, Z.handle, _lib.as_ptr(ws[0]), None, None, p3, q2))
@@ -148,9 +149,9 @@ def test_snarkjs_surface_and_cli_round_trip(tmp_path, monkeypatch):
     import __graft_entry__ as ge
     import groth16_ref as g16
     import oracle_lib as ol
-    monkeypatch.setenv("ZKFL_LIBRARY_PATH", ge.build_emul())
     from zkfl_b200 import snarkjs as sj
     from zkfl_b200 import cli, formats
+    monkeypatch.setitem(sj._state, "lib_path", ge.build_emul())   # test double, handed over in code (no environment redirect exists)
     monkeypatch.setitem(sj._state, "prover", None)
     monkeypatch.setitem(sj._state, "circuits", {})
     monkeypatch.setitem(sj._state, "zkeys", {})
@@ -219,6 +220,8 @@ def test_c_abi_argument_and_format_errors(emul_prover):
     zk = open(os.path.join(os.path.dirname(__file__), "golden", "tiny.zkey"), "rb").read()
     Z = emul_prover.load_zkey(zk)
     with pytest.raises(_lib.ZkflError, match="do not match"):
+        emul_prover.full_prove(other, Z, [I.secure_agg_client_input()], [(1, 2)], check=False)
+    with pytest.raises(ValueError, match="r1cs"):      # a constraint check that cannot be done is refused, never skipped
         emul_prover.full_prove(other, Z, [I.secure_agg_client_input()], [(1, 2)])
     with pytest.raises(_lib.ZkflError, match="not reduced"):
         emul_prover.full_prove(circ, Z, pc.tiny_inputs()[:1], [(2 ** 255, 1)])
@@ -230,6 +233,58 @@ def test_c_abi_argument_and_format_errors(emul_prover):
     bad[12 + 12 + 12] ^= 0xFF   # n_ops in the header no longer matches the op section
     with pytest.raises(_lib.ZkflError):
         Circuit(emul_prover, bytes(bad))
+    # every index of a program loaded from disk is validated at load time (ops, LC ids, LC offsets, term wires, Poseidon inputs)
+    import struct
+    from zkfl_b200.formats import read_container, write_container
+    secs = read_container(cc.program_bytes(), b"zkwp")
+    hdr = struct.unpack("<8I", secs[1])
+    n_wires, n_ops, n_lcs, n_terms, n_pos = hdr[0], hdr[3], hdr[4], hdr[5], hdr[6]
+
+    def mutated(sid, off, value):
+        m = dict(secs)
+        b = bytearray(m[sid]); b[off:off + 4] = struct.pack("<I", value); m[sid] = bytes(b)
+        return write_container(b"zkwp", 1, sorted(m.items()))
+    ops = struct.unpack(f"<{5 * n_ops}I", secs[2])
+    first = {code: next(o for o in range(n_ops) if ops[5 * o] == code) for code in (1, 2, 3, 4) if code in ops[0::5]}
+    cases = [(3, 4, n_terms + 1),                                  # LC offsets not monotone
+             (4, 0, n_wires),                                      # term wire out of range
+             (6, 0, n_wires)]                                      # Poseidon input wire out of range
+    for code, o in first.items():
+        cases.append((2, 20 * o + 4, n_wires))                     # dst out of range
+        cases.append((2, 20 * o + 4, 0))                           # dst inside the inputs
+        if code <= 3:
+            cases.append((2, 20 * o + 8, n_lcs))                   # LC id out of range
+        if code == 2:
+            cases.append((2, 20 * o + 12, n_lcs + 7))
+        if code == 3:
+            cases.append((2, 20 * o + 12, 255))                    # more bits than the field has
+            cases.append((2, 20 * o + 4, n_wires - 1))             # dst + n_bits past the end
+        if code == 4:
+            cases.append((2, 20 * o + 12, n_pos))                  # Poseidon input list past the end
+            cases.append((2, 20 * o + 8, 18))                      # width without constants
+            cases.append((2, 20 * o + 4, n_wires - 5))             # outputs past the end
+    assert set(first) >= {2, 3, 4}
+    for sid, off, value in cases:
+        with pytest.raises(_lib.ZkflError):
+            Circuit(emul_prover, mutated(sid, off, value))
+    Circuit(emul_prover, write_container(b"zkwp", 1, sorted(secs.items()))).close()   # the unmutated container still loads
+    # a witness handed to `groth16 prove` must be well-formed: every element reduced, wire 0 == 1
+    good = emul_prover.calculate_witness(circ, pc.tiny_inputs()[:1])[0]
+    emul_prover.prove(Z, [good], [(1, 2)])
+    with pytest.raises(_lib.ZkflError, match="wire 0"):
+        emul_prover.prove(Z, [(2).to_bytes(32, "little") + good[32:]], [(1, 2)])
+    with pytest.raises(_lib.ZkflError, match="not reduced"):
+        emul_prover.prove(Z, [good[:64] + b"\xff" * 32 + good[96:]], [(1, 2)])
+    # fullProve aborts on a failed === (one pass, check on the device) and returns no proof; unreduced inputs are refused
+    with pytest.raises(_lib.AssertFailed):
+        emul_prover.full_prove(circ, Z, [pc.tiny_inputs()[0], {"out": "5", "bound": "17", "x": "3", "y": "5"}], [(1, 2), (3, 4)])
+    bad_first = (ctypes.c_uint32 * 2)()
+    packed = circ.pack_inputs([pc.tiny_inputs()[0], {"out": "5", "bound": "17", "x": "3", "y": "5"}])
+    out_p = ctypes.create_string_buffer(b"\x01" * 512, 512)
+    rc = lib.zkfl_groth16_full_prove_batch(ctx, circ.handle, Z.handle, circ.r1cs_handle, _lib.as_ptr(packed), None, 2, out_p, None, bad_first)
+    assert rc == -5 and bad_first[0] == 0xFFFFFFFF and bad_first[1] != 0xFFFFFFFF and out_p.raw == bytes(512)
+    with pytest.raises(_lib.ZkflError, match="not reduced"):
+        emul_prover.full_prove(circ, Z, b"\xff" * (32 * circ.n_inputs), [(1, 2)])
     h = ctypes.c_void_p()
     assert lib.zkfl_zkey_load(ctx, None, 0, ctypes.byref(h)) != 0 and lib.zkfl_last_error()
     assert lib.zkfl_groth16_prove_batch(ctx, Z.handle, None, None, 1, None, None) != 0
@@ -258,3 +313,50 @@ def test_commitment_pipeline_matches_the_reference_helpers(emul_prover):
         assert g["root_K"] == bn.key_material_commitment(r["master_key"], r["shared_keys"])
         for j, key, mask in zip(r["peer_ids"], r["shared_keys"], g["masks"]):
             assert mask == bn.derive_pairwise_mask(key, c.ROUND, c.id, j, 4)
+
+
+def test_setup_entropy_and_contribution(emul_prover, oracle):
+    """keys must not be derivable.  Default setup draws OS randomness (two setups differ); `zkey contribute`
+    re-randomises delta (delta1/delta2, C and H sections change, A/B sections and IC stay) and appends a contribution record;
+    proofs under the contributed key verify under ITS verification key and not under the old one."""
+    import groth16_ref as g16
+    import witness_ref as wr
+    from zkfl_b200 import formats
+    cc = pc.tiny_circuit()
+    k1, k2 = emul_prover.new_zkey(cc), emul_prover.new_zkey(cc)
+    assert k1 != k2
+    base = emul_prover.new_zkey(cc, b"contrib-test")
+    assert base == emul_prover.new_zkey(cc, b"contrib-test")          # explicit seed: reproducible (tests only)
+    c1 = emul_prover.contribute_zkey(base, "alice", b"e1")
+    c2 = emul_prover.contribute_zkey(base, "alice", b"e1")
+    assert c1 != base and c1 != c2                                     # fresh CSPRNG secret each time
+    _, a = wr.read_sections(base, b"zkey")
+    _, b = wr.read_sections(c1, b"zkey")
+    for sid in (1, 3, 4, 5, 6, 7):
+        assert a[sid] == b[sid]
+    assert a[8] != b[8] and a[9] != b[9] and a[2] != b[2] and a[2][:84 + 64 + 64 + 128 + 128] == b[2][:84 + 64 + 64 + 128 + 128]
+    import struct
+    assert struct.unpack_from("<I", b[10], 64)[0] == 1 and b"alice" in b[10]
+    c12 = emul_prover.contribute_zkey(c1, "bob")
+    assert struct.unpack_from("<I", wr.read_sections(c12, b"zkey")[1][10], 64)[0] == 2
+    circ = emul_prover.load_circuit(cc)
+    Z = emul_prover.load_zkey(c12)
+    proofs, pubs = emul_prover.full_prove(circ, Z, pc.tiny_inputs()[:1], [(5, 6)])
+    w = emul_prover.calculate_witness(circ, pc.tiny_inputs()[:1])[0]
+    assert (proofs[0], pubs[0]) == oracle.groth16_prove(c12, w, 5, 6)
+    vk_new = g16.vkey_from_json(formats.export_verification_key(c12))
+    vk_old = g16.vkey_from_json(formats.export_verification_key(base))
+    assert g16.verify(vk_new, oracle.ints(pubs[0]), g16.proof_from_bytes(proofs[0]))
+    assert not g16.verify(vk_old, oracle.ints(pubs[0]), g16.proof_from_bytes(proofs[0]))
+    Z.close(); circ.close()
+
+
+def test_proof_json_decoding_is_strict():
+    """proof.json must say groth16 / bn128 and carry affine points (z = 1)"""
+    from zkfl_b200 import formats
+    pj = formats.proof_bytes_to_json(bytes(range(1, 33)) * 8)
+    assert formats.proof_json_to_bytes(pj) == bytes(range(1, 33)) * 8
+    for bad in (dict(pj, protocol="plonk"), dict(pj, curve="bls12381"), dict(pj, pi_a=pj["pi_a"][:2] + ["2"]),
+                dict(pj, pi_b=pj["pi_b"][:2] + [["0", "1"]]), dict(pj, pi_c=pj["pi_c"][:2])):
+        with pytest.raises((ValueError, IndexError)):
+            formats.proof_json_to_bytes(bad)

@@ -415,3 +415,141 @@ def test_secure_aggregation_batch_of_256(gpu_prover):
     assert all(ok) and len(ok) == n
     Z.close()
     circ.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the reference's OWN fixture on the CUDA path, and the two parity checks that ran on the CPU only
+def _v5():
+    import json
+    import os
+    return json.load(open(os.path.join(os.path.dirname(__file__), "golden", "test_input_v5.json")))
+
+
+def test_reference_fixture_sgd_step_v5_on_gpu(gpu_prover):
+    """`sgd_step_v5(8,16,7)` (src/circuits/training/sgd_step_v5.circom:86-168) over data/test_input_v5.json -- the only input the
+    reference tree holds (BASELINE configs[0] names the file).  On the device: witness == both oracle interpreters (C++ and
+    pure Python), public signals == [client_id, round, root_D, root_G, tauSquared] of the fixture, every constraint holds
+    (device check AND the Python R1CS checker on the `.r1cs` bytes), proof bit-exact vs the oracle with fixed (r, s) at B = 1 and
+    for a tiled batch of 64, accepted by the oracle's pairing, the host verifier and the GPU batch verifier."""
+    import groth16_ref as g16
+    import witness_ref as wr
+    from zkfl_b200 import formats
+    from zkfl_b200 import snarkjs as sj
+    d = _v5()
+    cc = build_circuit("sgd_step_v5")
+    circ = gpu_prover.load_circuit(cc)
+    ws = gpu_prover.calculate_witness(circ, [d])                     # device witness + device constraint check
+    assert ws[0] == ol.witness_batch(cc.program_bytes(), circ.pack_inputs([d]), cc.n_inputs, cc.n_wires)
+    w_int = ol.ints(ws[0])
+    assert w_int == wr.calculate_witness(wr.Program(cc.program_bytes()), cc.flatten_input(d))
+    assert wr.R1cs(cc.r1cs_bytes()).first_violation(w_int) is None
+    expect_pub = [1, 1, int(d["root_D"]), int(d["root_G"]), int(d["tauSquared"])]
+    assert w_int[1:6] == expect_pub and int(d["tauSquared"]) == 76014
+    zk = gpu_prover.new_zkey(cc, b"v5-fixture")
+    Z = gpu_prover.load_zkey(zk)
+    assert Z.domain == 1 << 15
+    ref1 = ol.groth16_prove(zk, ws[0], 11, 13)
+    p1, q1 = gpu_prover.full_prove(circ, Z, [d], [(11, 13)])         # B = 1: latency kernels
+    assert (p1[0], q1[0]) == ref1 and ol.ints(q1[0]) == expect_pub
+    assert gpu_prover.prove(Z, ws, [(11, 13)])[0][0] == ref1[0]
+    B = 64                                                            # tiled batch: throughput kernels
+    rs = [(11, 13)] + [(1000 + b, 7 * b + 1) for b in range(1, B)]
+    pB, qB = gpu_prover.full_prove(circ, Z, [d] * B, rs)
+    assert pB[0] == ref1[0] and all(q == ref1[1] for q in qB)
+    for b in (1, 31, 63):
+        assert pB[b] == ol.groth16_prove(zk, ws[0], *rs[b])[0]
+    vkj = formats.export_verification_key(zk)
+    assert g16.verify(g16.vkey_from_json(vkj), expect_pub, g16.proof_from_bytes(p1[0]))
+    sig = formats.publics_bytes_to_json(q1[0])
+    assert sig == [str(v) for v in expect_pub]
+    assert sj.groth16.verify(vkj, sig, formats.proof_bytes_to_json(p1[0]))
+    assert gpu_prover.verify_batch(formats.vkey_json_to_bytes(vkj), qB, pB) == [True] * B
+    # tampered public inputs: the circuit's === fails ON THE DEVICE, in the witness call and inside the one-pass fullProve
+    for key, delta in (("root_G", 1), ("root_D", 1), ("tauSquared", -70000)):
+        t = dict(d)
+        t[key] = str(int(d[key]) + delta)
+        with pytest.raises(_lib.AssertFailed):
+            gpu_prover.calculate_witness(circ, [t])
+        with pytest.raises(_lib.AssertFailed):
+            gpu_prover.full_prove(circ, Z, [d, t], [(1, 2), (3, 4)])
+    Z.close()
+    circ.close()
+
+
+def test_product_setup_matches_the_oracle_setup_on_gpu(gpu_prover):
+    """`groth16 setup` replacement on the REAL library (device scalar multiplications) against the oracle's own setup from the
+    same toxic waste: header and every point section byte-identical, coefficient sections equal as sets -- for the fixture's
+    circuit and the metric circuit."""
+    import struct
+    import groth16_ref as g16
+    import witness_ref as wr
+    from zkfl_b200.zkey_setup import toxic_from_seed
+
+    def coeff_set(sec):
+        n = struct.unpack_from("<I", sec, 0)[0]
+        return {sec[4 + 44 * i:48 + 44 * i] for i in range(n)}
+    for name in ("sgd_step_v5", "sgd_verified"):
+        cc = build_circuit(name)
+        mine = gpu_prover.new_zkey(cc, b"gpu-setup-parity")
+        ref = g16.setup_fast(wr.R1cs(cc.r1cs_bytes()), *toxic_from_seed(b"gpu-setup-parity"))
+        _, a = wr.read_sections(mine, b"zkey")
+        _, b = wr.read_sections(ref, b"zkey")
+        for sid in (1, 2, 3, 5, 6, 7, 8, 9):
+            assert a[sid] == b[sid], f"{name}: section {sid} differs"
+        assert coeff_set(a[4]) == coeff_set(b[4]) and len(a[4]) == len(b[4])
+
+
+def test_full_prove_checks_constraints_in_one_pass(gpu_prover):
+    """full_prove validates inputs and runs the R1CS check on the HBM-resident witness; a failing batch
+    returns ZKFL_ERR_ASSERT with first_bad per instance and no proof bytes; malformed witnesses are refused by prove."""
+    import ctypes
+    cc = build_circuit("sgd_verified")
+    circ = gpu_prover.load_circuit(cc)
+    Z = gpu_prover.load_zkey(gpu_prover.new_zkey(cc, b"check"))
+    good = I.sgd_verified_batch(3)
+    bad = dict(good[1])
+    bad["gradPos"] = ["1"] + good[1]["gradPos"][1:]
+    packed = circ.pack_inputs([good[0], bad, good[2]])
+    first_bad = (ctypes.c_uint32 * 3)()
+    out_p = ctypes.create_string_buffer(b"\x01" * 768, 768)
+    before = gpu_prover.launch_count()
+    rc = gpu_prover.lib.zkfl_groth16_full_prove_batch(gpu_prover.ctx, circ.handle, Z.handle, circ.r1cs_handle, _lib.as_ptr(packed), None, 3,
+                                                      out_p, None, first_bad)
+    assert rc == -5 and out_p.raw == bytes(768)
+    assert first_bad[0] == 0xFFFFFFFF and first_bad[1] != 0xFFFFFFFF and first_bad[2] == 0xFFFFFFFF
+    assert gpu_prover.launch_count() > before
+    proofs, _ = gpu_prover.full_prove(circ, Z, good, [(1, 2), (3, 4), (5, 6)])
+    ws = gpu_prover.calculate_witness(circ, good)
+    assert proofs == gpu_prover.prove(Z, ws, [(1, 2), (3, 4), (5, 6)])[0]
+    with pytest.raises(_lib.ZkflError, match="wire 0"):
+        gpu_prover.prove(Z, [bytes(32) + ws[0][32:]], [(1, 2)])
+    with pytest.raises(_lib.ZkflError, match="not reduced"):
+        gpu_prover.prove(Z, [ws[0][:32 * 50] + b"\xff" * 32 + ws[0][32 * 51:]], [(1, 2)])
+    with pytest.raises(_lib.ZkflError, match="not reduced"):
+        gpu_prover.full_prove(circ, Z, b"\xff" * (32 * circ.n_inputs), [(1, 2)])
+    Z.close()
+    circ.close()
+
+
+def test_contributed_key_on_gpu(gpu_prover):
+    """`zkey contribute` on the device (point sections rescaled by the fresh secret): proofs under the contributed key are
+    bit-exact against the oracle reading the same key bytes and verify under its verification key only."""
+    import groth16_ref as g16
+    from zkfl_b200 import formats
+    cc = build_circuit("secure_agg_client")
+    base = gpu_prover.new_zkey(cc)                                    # OS randomness: not reproducible
+    assert base != gpu_prover.new_zkey(cc)
+    final = gpu_prover.contribute_zkey(base, "contributor", b"entropy")
+    circ = gpu_prover.load_circuit(cc)
+    Z = gpu_prover.load_zkey(final)
+    ins = [I.secure_agg_client_input()]
+    proofs, pubs = gpu_prover.full_prove(circ, Z, ins, [(21, 34)])
+    w = gpu_prover.calculate_witness(circ, ins)[0]
+    assert (proofs[0], pubs[0]) == ol.groth16_prove(final, w, 21, 34)
+    vk_new = formats.vkey_json_to_bytes(formats.export_verification_key(final))
+    vk_old = formats.vkey_json_to_bytes(formats.export_verification_key(base))
+    assert gpu_prover.verify_batch(vk_new, pubs, proofs) == [True]
+    assert gpu_prover.verify_batch(vk_old, pubs, proofs) == [False]
+    assert g16.verify(g16.vkey_from_json(formats.export_verification_key(final)), ol.ints(pubs[0]), g16.proof_from_bytes(proofs[0]))
+    Z.close()
+    circ.close()

@@ -1,8 +1,9 @@
 """ctypes binding of libzkfl.so (include/zkfl.h). No CPU fallback: if the CUDA library is missing or
 no CUDA device is usable, loading / context creation raises.
 
-`ZKFL_LIBRARY_PATH` may point at another build of the same ABI; the CPU test-suite uses it to load the
-host-emulation build of the kernels (tests/_emul/, never shipped)."""
+The library loaded is always the package's own libzkfl.so; no environment variable redirects it.  The CPU test-suite hands the
+path of the host-emulation build of the kernels (tests/_emul/, a test double, never shipped) to `load(path)` / `Prover(lib_path=)`
+explicitly."""
 from __future__ import annotations
 
 import ctypes
@@ -20,7 +21,7 @@ SYMBOLS = [
     "zkfl_msm_bases_free", "zkfl_msm_run", "zkfl_g1_mul_generator", "zkfl_g2_mul_generator",
     "zkfl_launch_count", "zkfl_prof_enable", "zkfl_prof_read", "zkfl_bench_modmul", "zkfl_bench_imad", "zkfl_bench_widemac",
     "zkfl_timer_begin", "zkfl_timer_end", "zkfl_groth16_verify", "zkfl_groth16_verify_batch", "zkfl_debug_read", "zkfl_debug_pairing_selftest", "zkfl_wtns_calculate", "zkfl_groth16_prove", "zkfl_groth16_full_prove",
-    "zkfl_proof_to_json", "zkfl_public_to_json", "zkfl_groth16_msm_partials", "zkfl_groth16_finalize", "zkfl_ctx_wait_other",
+    "zkfl_proof_to_json", "zkfl_public_to_json", "zkfl_g1_scale_points", "zkfl_g2_scale_points", "zkfl_groth16_msm_partials", "zkfl_groth16_finalize", "zkfl_ctx_wait_other",
 ]
 
 _libs = {}
@@ -37,7 +38,7 @@ class AssertFailed(ZkflError):
 
 
 def library_path() -> str:
-    return os.environ.get("ZKFL_LIBRARY_PATH") or DEFAULT_PATH
+    return DEFAULT_PATH
 
 
 def load(path: str | None = None):
@@ -62,10 +63,10 @@ def load(path: str | None = None):
         "zkfl_r1cs_check_batch": (i, [vp, vp, vp, i, vp]),
         "zkfl_wtns_eval_wires": (i, [vp, vp, vp, i, vp, ctypes.c_uint32, vp]),
         "zkfl_groth16_prove_batch": (i, [vp, vp, vp, vp, i, vp, vp]),
-        "zkfl_groth16_full_prove_batch": (i, [vp, vp, vp, vp, vp, i, vp, vp]),
+        "zkfl_groth16_full_prove_batch": (i, [vp, vp, vp, vp, vp, vp, i, vp, vp, vp]),
         "zkfl_full_prove_stage": (i, [vp, vp, vp, vp, vp, i]),
-        "zkfl_full_prove_run": (i, [vp, vp, vp, i]),
-        "zkfl_full_prove_fetch": (i, [vp, i, vp]),
+        "zkfl_full_prove_run": (i, [vp, vp, vp, vp, i]),
+        "zkfl_full_prove_fetch": (i, [vp, i, vp, vp]),
         "zkfl_g1_msm": (i, [vp, vp, vp, sz, vp]), "zkfl_g2_msm": (i, [vp, vp, vp, sz, vp]),
         "zkfl_msm_bases_load": (i, [vp, vp, sz, i, pp]), "zkfl_msm_bases_free": (None, [vp]),
         "zkfl_msm_run": (i, [vp, vp, vp, sz, vp]),
@@ -81,12 +82,13 @@ def load(path: str | None = None):
         "zkfl_debug_pairing_selftest": (i, []),
         "zkfl_wtns_calculate": (i, [vp, vp, vp, vp, vp, vp]),
         "zkfl_groth16_prove": (i, [vp, vp, vp, vp, vp, vp, vp]),
-        "zkfl_groth16_full_prove": (i, [vp, vp, vp, vp, vp, vp, vp, vp]),
+        "zkfl_groth16_full_prove": (i, [vp, vp, vp, vp, vp, vp, vp, vp, vp]),
         "zkfl_proof_to_json": (i, [vp, ctypes.c_char_p, sz]),
         "zkfl_public_to_json": (i, [vp, ctypes.c_uint32, ctypes.c_char_p, sz]),
         "zkfl_groth16_msm_partials": (i, [vp, vp, vp, i, ctypes.c_uint32, ctypes.c_uint32, vp]),
         "zkfl_groth16_finalize": (i, [vp, vp, vp, ctypes.c_uint32, vp, i, vp]),
         "zkfl_ctx_wait_other": (i, [vp, vp]),
+        "zkfl_g1_scale_points": (i, [vp, vp, sz, vp, vp]), "zkfl_g2_scale_points": (i, [vp, vp, sz, vp, vp]),
         "zkfl_timer_begin": (i, [vp]), "zkfl_timer_end": (i, [vp, ctypes.POINTER(ctypes.c_float)]),
     }
     for name, (res, args) in sig.items():

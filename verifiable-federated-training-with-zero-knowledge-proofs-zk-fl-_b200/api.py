@@ -119,10 +119,25 @@ class Prover:
     def load_zkey(self, data: bytes) -> Zkey:
         return Zkey(self, data)
 
-    def new_zkey(self, r1cs, seed: bytes) -> bytes:
-        """r1cs: `.r1cs` bytes or a CompiledCircuit"""
+    def new_zkey(self, r1cs, seed: bytes | None = None) -> bytes:
+        """r1cs: `.r1cs` bytes or a CompiledCircuit.  seed=None (the default, what every non-test caller should use): the toxic
+        waste is drawn from the OS CSPRNG and discarded.  An explicit seed makes the key reproducible -- and FORGEABLE by anyone
+        who knows the seed: tests, benchmarks and parity checks only."""
         from .zkey_setup import new_zkey
-        return new_zkey(self, r1cs, seed)
+        return new_zkey(self, r1cs, os.urandom(64) if seed is None else seed)
+
+    def contribute_zkey(self, zkey: bytes, name: str = "", entropy: bytes = b"") -> bytes:
+        from .zkey_setup import contribute
+        return contribute(self, zkey, name, entropy)
+
+    def scale_points(self, pts: bytes, scalar: int, group: int = 1) -> bytes:
+        """every point of a zkey section (affine Montgomery) times one scalar, on the GPU"""
+        sz = 64 if group == 1 else 128
+        n = len(pts) // sz
+        out = ctypes.create_string_buffer(sz * n)
+        fn = self.lib.zkfl_g1_scale_points if group == 1 else self.lib.zkfl_g2_scale_points
+        self._check(fn(self.ctx, _lib.as_ptr(pts), n, _lib.as_ptr(int(scalar).to_bytes(32, "little")), out))
+        return out.raw
 
     # ---------------------------------------------------------------- witness
     def calculate_witness(self, circuit: Circuit, inputs, check: bool = True) -> list[bytes]:
@@ -167,6 +182,10 @@ class Prover:
         if isinstance(wtns, (list, tuple)):
             return b"".join(wtns), len(wtns)
         n = wtns.numel() * wtns.element_size() if hasattr(wtns, "data_ptr") else len(wtns)
+        if getattr(wtns, "is_cuda", False):
+            # the library copies on its own stream: whatever produced the tensor on torch's current stream must be done first
+            import torch
+            torch.cuda.current_stream(wtns.device).synchronize()
         if n % (32 * zkey.n_vars):
             raise ValueError("witness buffer is not a multiple of 32 * n_vars bytes")
         return wtns, n // (32 * zkey.n_vars)
@@ -182,13 +201,19 @@ class Prover:
         praw, qraw = proofs.raw, pubs.raw
         return ([praw[256 * b:256 * (b + 1)] for b in range(B)], [qraw[psz * b:psz * (b + 1)] for b in range(B)])
 
-    def full_prove(self, circuit: Circuit, zkey: Zkey, inputs, rs=None):
+    def full_prove(self, circuit: Circuit, zkey: Zkey, inputs, rs=None, check: bool = True):
+        """witness + prove in one GPU pass.  check=True (default): the circuit's constraints are checked on the device inside
+        the pass and a failed `===` raises AssertFailed, as circom/snarkjs `fullProve` does; it needs the circuit's R1CS
+        (load_circuit(..., check_constraints=True)) and raises if that is missing rather than skipping the check."""
         packed = inputs if isinstance(inputs, (bytes, bytearray)) else circuit.pack_inputs(inputs)
         B = len(packed) // (32 * circuit.n_inputs)
         proofs = ctypes.create_string_buffer(256 * B)
         pubs = ctypes.create_string_buffer(max(32 * zkey.n_public * B, 1))
-        self._check(self.lib.zkfl_groth16_full_prove_batch(self.ctx, circuit.handle, zkey.handle, _lib.as_ptr(packed),
-                                                          _lib.as_ptr(self._pack_rs(rs, B)), B, proofs, pubs))
+        if check and not circuit.r1cs_handle:
+            raise ValueError("full_prove(check=True) needs the circuit's .r1cs (it was loaded without one); pass check=False to skip the constraint check explicitly")
+        bad = (ctypes.c_uint32 * B)()
+        self._check(self.lib.zkfl_groth16_full_prove_batch(self.ctx, circuit.handle, zkey.handle, circuit.r1cs_handle if check else None,
+                                                          _lib.as_ptr(packed), _lib.as_ptr(self._pack_rs(rs, B)), B, proofs, pubs, bad))
         psz = 32 * zkey.n_public
         praw, qraw = proofs.raw, pubs.raw
         return ([praw[256 * b:256 * (b + 1)] for b in range(B)], [qraw[psz * b:psz * (b + 1)] for b in range(B)])
@@ -306,18 +331,21 @@ class Prover:
         self._check(self.lib.zkfl_full_prove_stage(self.ctx, circuit.handle, zkey.handle, _lib.as_ptr(packed_inputs),
                                                    _lib.as_ptr(rs_packed), B))
 
-    def run_staged(self, circuit: Circuit, zkey: Zkey, B: int):
-        self._check(self.lib.zkfl_full_prove_run(self.ctx, circuit.handle, zkey.handle, B))
+    def run_staged(self, circuit: Circuit, zkey: Zkey, B: int, check: bool = False):
+        self._check(self.lib.zkfl_full_prove_run(self.ctx, circuit.handle, zkey.handle, circuit.r1cs_handle if check else None, B))
 
     def fetch(self, B: int, out=None):
         buf = out if out is not None else ctypes.create_string_buffer(256 * B)
-        self._check(self.lib.zkfl_full_prove_fetch(self.ctx, B, _lib.as_ptr(buf) if out is not None else buf))
+        self._check(self.lib.zkfl_full_prove_fetch(self.ctx, B, _lib.as_ptr(buf) if out is not None else buf, None))
         return buf
 
-    def full_prove_raw(self, circuit: Circuit, zkey: Zkey, inputs_ptr, rs_ptr, B: int, proofs_ptr, pubs_ptr):
-        """pointer-level call (pinned host buffers) used by the end-to-end benchmark"""
-        self._check(self.lib.zkfl_groth16_full_prove_batch(self.ctx, circuit.handle, zkey.handle, _lib.as_ptr(inputs_ptr),
-                                                          _lib.as_ptr(rs_ptr), B, _lib.as_ptr(proofs_ptr), _lib.as_ptr(pubs_ptr)))
+    def full_prove_raw(self, circuit: Circuit, zkey: Zkey, inputs_ptr, rs_ptr, B: int, proofs_ptr, pubs_ptr, check: bool = True):
+        """pointer-level call (pinned host buffers) used by the end-to-end benchmark; constraint check on the device as in full_prove"""
+        if check and not circuit.r1cs_handle:
+            raise ValueError("full_prove_raw(check=True) needs the circuit's .r1cs")
+        self._check(self.lib.zkfl_groth16_full_prove_batch(self.ctx, circuit.handle, zkey.handle, circuit.r1cs_handle if check else None,
+                                                          _lib.as_ptr(inputs_ptr), _lib.as_ptr(rs_ptr), B, _lib.as_ptr(proofs_ptr),
+                                                          _lib.as_ptr(pubs_ptr), None))
 
     def launch_count(self) -> int:
         return int(self.lib.zkfl_launch_count())

@@ -13,6 +13,8 @@
 // law, the Montgomery products and -- at the batch sizes used -- even the NTT passes; tensor cores do not apply
 // (no dense contraction anywhere on the path). Balance comes from the work decomposition (fixed-size chunks of the
 // bucket-sorted lists, dependency levels of the witness program), not from intra-CTA cooperation.
+// Non-template kernels are grouped in sections (ZK_K_WITNESS, ZK_K_MSM_SORT, ZK_K_FIN, ZK_K_VERIFY, ZK_K_BENCH): every .cu file of
+// the library defines the sections it launches before including this header, so each kernel is compiled exactly once.
 #pragma once
 #include "bn254.cuh"
 #include "pairing.cuh"
@@ -43,11 +45,14 @@ static inline void zk_atomic_min_u32(uint32_t* p, uint32_t v) {
 #endif
 #if defined(__CUDACC__) && !defined(ZKFL_EMUL)
 #define ZK_ACC_BOUNDS(F) __launch_bounds__(128, sizeof(F) > 32 ? ZKFL_G2_MIN_CTAS : 4)
+#define ZK_RED_BOUNDS __launch_bounds__(128)     // bucket-reduction kernels: 128-thread CTAs, registers as needed (no spills)
 #else
 #define ZK_ACC_BOUNDS(F)
+#define ZK_RED_BOUNDS
 #endif
 
 // ================================================================================ layout helpers
+#ifdef ZK_K_WITNESS
 // host layout [b][e] (what .wtns / the C ABI use)  ->  device layout [e][b]
 ZK_GLOBAL void k_aos_to_soa(const Fr* __restrict__ src, Fr* __restrict__ dst, uint32_t n_elem, uint32_t B,
                             uint32_t dst_elem_off) {
@@ -72,6 +77,7 @@ ZK_GLOBAL void k_gather_wires(const Fr* __restrict__ w, const uint32_t* __restri
   out[(size_t)b * n_sel + k] = w[(size_t)ZK_LDG(wires + k) * B + b];
 }
 
+#endif  // ZK_K_WITNESS
 // ================================================================================ W1: batched witness evaluator
 struct PoseidonDev {
   uint32_t rounds, rp;
@@ -88,6 +94,7 @@ struct ProgramDev {
   PoseidonDev pk[18];
 };
 
+#ifdef ZK_K_WITNESS
 ZK_D Fr lc_eval(const ProgramDev& p, uint32_t k, const Fr* __restrict__ w, uint32_t B, uint32_t b) {
   Fr acc = Fr::zero();
   uint32_t e = ZK_LDG(p.lc_off + k + 1);
@@ -162,7 +169,7 @@ ZK_GLOBAL void k_witness_level(ProgramDev p, Fr* __restrict__ w, uint32_t B, uin
 // element i: a round is t + 6 products per lane (its MDS row over shuffled state, its own S-box).  Every lane runs the same
 // instruction stream (lanes >= t mirror element t-1, S-box results are selected, stores are predicated): no divergent calls.
 // Other ops are evaluated redundantly by all lanes (same value, same address).  Wire numbering is identical to k_witness_level.
-__global__ void k_witness_level_coop(ProgramDev p, Fr* __restrict__ w, uint32_t B, uint32_t op_lo, uint32_t op_hi) {
+ZK_GLOBAL void k_witness_level_coop(ProgramDev p, Fr* __restrict__ w, uint32_t B, uint32_t op_lo, uint32_t op_hi) {
   const size_t gw = ZK_TID >> 5;
   const uint32_t lane = threadIdx.x & 31u;
   if (gw >= (size_t)(op_hi - op_lo) * B) return;      // a whole warp at a time
@@ -216,12 +223,14 @@ __global__ void k_witness_level_coop(ProgramDev p, Fr* __restrict__ w, uint32_t 
 }
 #endif
 
+#endif  // ZK_K_WITNESS
 // ================================================================================ K1: sparse A.w, B.w, C = A o B
 struct CsrDev {
   const uint32_t* row_off;  // n_rows + 1
   const uint32_t* wire;
   const Fr* coef;           // coef * R^2 (the bytes zkey section 4 stores)
 };
+#ifdef ZK_K_WITNESS
 ZK_D Fr csr_row(const CsrDev& m, uint32_t row, const Fr* __restrict__ w, uint32_t B, uint32_t b) {
   Fr acc = Fr::zero();
   uint32_t e = ZK_LDG(m.row_off + row + 1);
@@ -248,6 +257,21 @@ ZK_GLOBAL void k_r1cs_check(CsrDev A, CsrDev Bm, CsrDev C, const Fr* __restrict_
   Fr a = csr_row(A, row, w, B, b), bv = csr_row(Bm, row, w, B, b), c = csr_row(C, row, w, B, b);
   // a, bv, c are Montgomery(value): a*bv = Mont(product), compare in Montgomery form
   if (!((a * bv) == c)) ZK_ATOMIC_MIN(first_bad + b, row);
+}
+
+// well-formedness of a witness handed in from outside (`groth16 prove <zkey> <wtns>`): every element reduced mod r, wire 0 == 1.
+// flags: bit 0 = some element >= r, bit 1 = some instance has w[0] != 1
+ZK_GLOBAL void k_wtns_validate(const Fr* __restrict__ w, uint32_t n_wires, uint32_t B, uint32_t* __restrict__ flags) {
+  size_t tid = ZK_TID;
+  if (tid >= (size_t)n_wires * B) return;
+  const Fr v = w[tid];
+  bool lt = false, decided = false;
+  ZK_UNROLL for (int i = 7; i >= 0; i--) {
+    if (!decided && v.v[i] != FrP::mod(i)) { lt = v.v[i] < FrP::mod(i); decided = true; }
+  }
+  uint32_t f = lt ? 0u : 1u;
+  if (tid < B) { uint32_t o = v.v[0] ^ 1u; ZK_UNROLL for (int i = 1; i < 8; i++) o |= v.v[i]; if (o) f |= 2u; }
+  if (f) ZK_ATOMIC_OR(flags, f);
 }
 
 // ================================================================================ K2-K5: H polynomial
@@ -350,6 +374,7 @@ ZK_GLOBAL void k_join_abc(const Fr* __restrict__ abc, Fr* __restrict__ out, uint
   out[tid] = (a * b - c).from_mont();
 }
 
+#endif  // ZK_K_WITNESS
 // ================================================================================ K6/K7: Pippenger MSM
 // Batched over B proofs that share the bases. Signed c-bit digits: W = 254/c + 1 windows,
 // nb = 2^(c-1) buckets per bucket set, row = b*R + (R == 1 ? 0 : j) identifies one bucket set.
@@ -385,6 +410,7 @@ ZK_HD int32_t signed_digit(const uint32_t* k, uint32_t j, uint32_t c, uint32_t& 
   return (int32_t)d;
 }
 
+#ifdef ZK_K_MSM_SORT
 // pass 1: bucket histogram. scalars: canonical [m][B]. counts: [B*W][nb]. skip[i] != 0 drops point i
 // (bases that are the point at infinity: wires absent from the B matrix, public wires of the C query).
 ZK_GLOBAL void k_msm_count(const Fr* __restrict__ scalars, const uint8_t* __restrict__ skip, MsmShape s,
@@ -459,6 +485,7 @@ ZK_GLOBAL void k_msm_scatter(const Fr* __restrict__ scalars, const uint8_t* __re
     skey[at] = (uint16_t)(mag - 1);
   }
 }
+#endif  // ZK_K_MSM_SORT
 // pass 4: BALANCED bucket accumulation. One thread per (row, chunk of S consecutive sorted entries): every thread
 // performs exactly S mixed adds whatever the bucket-size distribution (witness scalars are far from uniform:
 // bits, small values, and the partial top window concentrate thousands of entries in a few buckets).
@@ -705,7 +732,7 @@ ZK_GLOBAL void k_msm_fixup(const uint32_t* __restrict__ offsets, const uint32_t*
 // Level kernel: chunk t of L consecutive elements -> R_t = sum X, T_t = sum j * X[t*L + j] (zero-based local weights).
 // With Z(X) = sum_k k * X[k]:  Z(X) = sum_t T_t + L * Z(R)  and  S = Z(X) + sum(X) = Z(X) + sum(R).
 template <class F>
-ZK_GLOBAL void k_reduce_level(const Xyzz<F>* __restrict__ in, size_t rows, uint32_t N, uint32_t L, Xyzz<F>* __restrict__ R,
+ZK_GLOBAL ZK_RED_BOUNDS void k_reduce_level(const Xyzz<F>* __restrict__ in, size_t rows, uint32_t N, uint32_t L, Xyzz<F>* __restrict__ R,
                               Xyzz<F>* __restrict__ T) {
   size_t tid = ZK_TID;
   uint32_t nchunk = N / L;
@@ -714,13 +741,49 @@ ZK_GLOBAL void k_reduce_level(const Xyzz<F>* __restrict__ in, size_t rows, uint3
   uint32_t ch = (uint32_t)(tid % nchunk);
   const Xyzz<F>* x = in + row * N + (size_t)ch * L;
   Xyzz<F> run = Xyzz<F>::infinity(), acc = Xyzz<F>::infinity();
-  for (int j = (int)L - 1; j >= 1; j--) {
-    xyzz_add(run, x[j]);
-    xyzz_add(acc, run);
+  ZK_NOUNROLL for (int j = (int)L - 1; j >= 1; j--) {
+    xyzz_add_hot(run, x[j]);
+    xyzz_add_hot(acc, run);
   }
-  xyzz_add(run, x[0]);
+  xyzz_add_hot(run, x[0]);
   R[tid] = run;
   if (T) T[tid] = acc;
+}
+// Level 1 of the tree with the FIX-UP FUSED IN (batch path): the value of bucket k is taken straight from what the accumulation
+// left -- nothing for an empty bucket, buckets[k] when one chunk held the whole run, otherwise the partial sums of the chunks
+// the run crosses (tail of the first, heads of the following ones).  Every partial is added to the running sum directly, so a
+// bucket cut by chunk borders costs the same additions as before but no separate pass over all buckets, and the bucket array is
+// neither completed nor re-read.  Thread = (row, chunk of L buckets).
+template <class F>
+ZK_GLOBAL ZK_RED_BOUNDS void k_reduce_level1_fused(const Xyzz<F>* __restrict__ buckets, const Xyzz<F>* __restrict__ head,
+                                                   const Xyzz<F>* __restrict__ tail, const uint32_t* __restrict__ offsets,
+                                                   const uint32_t* __restrict__ counts, size_t rows, uint32_t nb, uint32_t L, uint32_t S,
+                                                   uint32_t chunks_per_row, Xyzz<F>* __restrict__ R, Xyzz<F>* __restrict__ T) {
+  size_t tid = ZK_TID;
+  const uint32_t nchunk = nb / L;
+  if (tid >= rows * nchunk) return;
+  const size_t row = tid / nchunk;
+  const uint32_t ch = (uint32_t)(tid % nchunk);
+  const uint32_t* off = offsets + row * nb + (size_t)ch * L;
+  const uint32_t* cnt = counts + row * nb + (size_t)ch * L;
+  const Xyzz<F>* x = buckets + row * nb + (size_t)ch * L;
+  const Xyzz<F>* h = head + row * chunks_per_row;
+  const Xyzz<F>* t = tail + row * chunks_per_row;
+  Xyzz<F> run = Xyzz<F>::infinity(), acc = Xyzz<F>::infinity();
+  ZK_NOUNROLL for (int j = (int)L - 1; j >= 0; j--) {
+    const uint32_t n = ZK_LDG(cnt + j);
+    if (n) {
+      const uint32_t st = ZK_LDG(off + j), c0 = st / S, c1 = (st + n - 1) / S;
+      if (c0 == c1) xyzz_add_hot(run, x[j]);
+      else {
+        xyzz_add_hot(run, (st > c0 * S) ? t[c0] : h[c0]);
+        ZK_NOUNROLL for (uint32_t q = c0 + 1; q <= c1; q++) xyzz_add_hot(run, h[q]);
+      }
+    }
+    if (j >= 1) xyzz_add_hot(acc, run);
+  }
+  R[tid] = run;
+  T[tid] = acc;
 }
 // final: per row, from the level-2 outputs (N2 entries each): R2/T2 = level 2 of R1, RT = chunk sums of T1.
 //   Z(R1) = sum(T2) + L2 * Z(R2);  Z(X) = sum(T1) + L1 * Z(R1) = sum(RT) + L1 * Z(R1);  S = Z(X) + sum(R2)
@@ -854,6 +917,7 @@ struct VkDev {
   G1Affine alpha1, beta1, delta1;
   G2Affine beta2, delta2;
 };
+#ifdef ZK_K_FIN
 // phase 1: fixed-base terms. thread (b, k): k=0 r*delta1, 1 s*delta1, 2 -(r*s)*delta1 (G1) ; k=3 s*delta2 (G2)
 // rs: canonical [B][2] (host order: r then s). t_g1: [B][3], t_g2: [B]
 ZK_GLOBAL void k_fin_fixed(const G1Affine* __restrict__ tab_d1, const G2Affine* __restrict__ tab_d2, const Fr* __restrict__ rs,
@@ -911,7 +975,9 @@ ZK_GLOBAL void k_fin_write(VkDev vk, uint32_t B, const G1Xyzz* __restrict__ msm_
   }
 }
 
+#endif  // ZK_K_FIN
 // ================================================================================ V1: batch Groth16 verifier
+#ifdef ZK_K_VERIFY
 // SURVEY 8f item 1 (Server.verify*Proof, tests/full_system_simulation.mjs:848-1131: one `snarkjs groth16 verify` process per
 // proof).  B proofs under one verification key; the work of a proof is split over threads so that a whole round's proofs run
 // concurrently: (b, j) public-input scalar multiplications, (b) decoding / curve checks / vk_x, (b, pair) Miller loops,
@@ -940,6 +1006,7 @@ ZK_GLOBAL void k_vfy_prepare(zkp::PairingConsts k, const G1Affine* __restrict__ 
   ZK_NOUNROLL for (uint32_t j = 0; j < l; j++) ok = ok && zkp::canonical_lt(publics[b * l + j].v, true);
   zkp::G1P A = zkp::g1_from_canonical(pw), C = zkp::g1_from_canonical(pw + 48);
   zkp::G2P Bp = zkp::g2_from_canonical(pw + 16);
+  ok = ok && !A.inf && !C.inf && !Bp.inf;          // (0, 0) is not on the curve: malformed, as in the host verifier
   ok = ok && zkp::g1_on_curve(A, k) && zkp::g1_on_curve(C, k) && zkp::g2_on_curve(Bp, k);
   A.y = A.y.neg();
   g1s[3 * b] = A;
@@ -1001,6 +1068,7 @@ ZK_GLOBAL void k_vfy_compare(const zkp::F12* __restrict__ halves, const uint32_t
   ok[b] = (flags[b] && zkp::f12_eq(halves[2 * b], halves[2 * b + 1])) ? 1 : 0;
 }
 
+#endif  // ZK_K_VERIFY
 // ================================================================================ misc
 // out[i] = k_i * G as Montgomery affine (zkey point layout): `groth16 setup`'s scalar multiplications
 template <class F>
@@ -1009,6 +1077,14 @@ ZK_GLOBAL void k_gen_mul(Affine<F> gen, const Fr* __restrict__ scalars, size_t n
   if (i >= n) return;
   Fr k = scalars[i];
   out[i] = xyzz_to_affine(xyzz_scalar_mul(Xyzz<F>::from_affine(gen), k.v));
+}
+// out[i] = k * P_i for ONE scalar k (Montgomery affine in and out): `snarkjs zkey contribute` rescales the C and H sections by
+// 1/d and delta by d (tests/full_system_simulation.mjs:726-731)
+template <class F>
+ZK_GLOBAL void k_point_scale(const Affine<F>* __restrict__ pts, Fr k, size_t n, Affine<F>* __restrict__ out) {
+  size_t i = ZK_TID;
+  if (i >= n) return;
+  out[i] = xyzz_to_affine(xyzz_scalar_mul(Xyzz<F>::from_affine(pts[i]), k.v));
 }
 // a single XYZZ result -> affine canonical bytes (standalone MSM API)
 template <class F>
@@ -1035,6 +1111,7 @@ ZK_GLOBAL void k_sum_partials(const Affine<F>* __restrict__ parts, uint32_t npar
   }
   out[i] = acc;
 }
+#ifdef ZK_K_MSM_SORT
 // marks the points outside [lo, hi) (and those already skipped) so a rank only sorts its own range
 ZK_GLOBAL void k_range_mask(const uint8_t* __restrict__ base_skip, uint32_t m, uint32_t lo, uint32_t hi, uint8_t* __restrict__ out) {
   size_t i = ZK_TID;
@@ -1042,6 +1119,8 @@ ZK_GLOBAL void k_range_mask(const uint8_t* __restrict__ base_skip, uint32_t m, u
   out[i] = (i < lo || i >= hi || (base_skip && base_skip[i])) ? 1 : 0;
 }
 
+#endif  // ZK_K_MSM_SORT
+#ifdef ZK_K_BENCH
 // integer-pipe microbenchmark: `iters` dependent Montgomery products per thread (roofline denominator)
 ZK_GLOBAL void k_bench_modmul(Fq* __restrict__ data, size_t n, uint32_t iters) {
   size_t i = ZK_TID;
@@ -1089,5 +1168,7 @@ ZK_GLOBAL void k_bench_imad(uint32_t* __restrict__ data, size_t n, uint32_t iter
   }
   data[i] = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7;
 }
+
+#endif  // ZK_K_BENCH
 
 }  // namespace zk

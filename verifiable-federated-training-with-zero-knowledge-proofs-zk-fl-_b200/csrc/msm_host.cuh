@@ -1,0 +1,158 @@
+// Host side of the Pippenger pipeline, templated over the coordinate field; msm_g1.cu / msm_g2.cu instantiate it.
+#pragma once
+#include "host.h"
+
+static inline uint32_t affine_slots() { uint32_t K = env_u32("ZKFL_MSM_AFFINE_K", 64); return K < 1 ? 1 : (K > 4096 ? 4096 : K); }   // chunks per thread
+
+// bucket accumulation of one MSM (slot = which of the five buffer sets), on the main stream; uses the lists left by msm_sort(gen).
+// The fix-up of buckets cut by chunk borders is fused into level 1 of the batch reduction; only the paths that read completed
+// bucket arrays (latency variant of the reduction, batch-affine accumulation) still run k_msm_fixup.
+template <class F>
+int msm_accumulate(zkfl_ctx* c, const Affine<F>* bases, const MsmShape& s, int slot, const char* tag, int gen) {
+  size_t rows = (size_t)s.B * s.R;
+  TRY(c->buckets[slot].reserve(rows * s.nb * sizeof(Xyzz<F>)));
+  const uint32_t S = s.lsS ? (1u << s.lsS) : accumulate_chunk(), cpr = (s.cap + S - 1) / S;
+  TRY(c->head[slot].reserve(rows * cpr * sizeof(Xyzz<F>)));
+  TRY(c->tail[slot].reserve(rows * cpr * sizeof(Xyzz<F>)));
+  const uint32_t* offsets = c->offsets[gen].as<uint32_t>();
+  const uint32_t* counts = c->counts[gen].as<uint32_t>();
+  Xyzz<F>* head = c->head[slot].as<Xyzz<F>>();
+  Xyzz<F>* tail = c->tail[slot].as<Xyzz<F>>();
+  if (s.lsS) {
+    const uint32_t K = affine_slots();
+    const size_t n_groups = rows * (cpr >> 5);
+    if ((cpr >> 5) % K != 0 || rows >= 0xFFFFFFFFull) return fail(ZKFL_ERR_ARG, "batch-affine accumulation: bad list geometry");
+    TRY(c->aff_acc.reserve(n_groups * 32 * sizeof(Affine<F>)));
+    TRY(c->aff_pre.reserve(n_groups * 32 * sizeof(F)));
+    Stage st(c, tag);
+    ZK_LAUNCH(k_msm_accumulate_affine<F>, n_groups / K * 32, 128, c->stream, bases, c->sorted.as<uint32_t>(),
+              c->skey.as<uint16_t>(), offsets, counts, s, K, (uint32_t)rows,
+              c->aff_acc.as<Affine<F>>(), c->aff_pre.as<F>(), c->buckets[slot].as<Xyzz<F>>(), head, tail);
+  } else {
+    Stage st(c, tag);
+    ZK_LAUNCH(k_msm_accumulate_chunks<F>, rows * cpr, 128, c->stream, bases, c->sorted.as<uint32_t>(), c->skey.as<uint16_t>(),
+              offsets, counts, s, S, cpr, c->buckets[slot].as<Xyzz<F>>(), head, tail);
+  }
+  if (reduce_deep(s)) {
+    Stage st(c, "msm_fixup");
+    ZK_LAUNCH(k_msm_fixup<F>, rows * s.nb, 128, c->stream, offsets, counts, s, S, cpr, (const Xyzz<F>*)head, (const Xyzz<F>*)tail,
+              c->buckets[slot].as<Xyzz<F>>());
+  }
+  CU(cudaGetLastError());
+  return 0;
+}
+// bucket reduction sum_k (k+1) * B_k of one MSM on `stream` -> out[B]. Buffers must have been reserved (msm_reserve_reduce).
+template <class F>
+int msm_reduce(zkfl_ctx* c, const MsmShape& s, int slot, Xyzz<F>* out, cudaStream_t stream, const char* tag, int gen) {
+  size_t rows = (size_t)s.B * s.R;
+  ReducePlan p = reduce_plan(s);
+  Xyzz<F>* R1 = c->Rs[slot].as<Xyzz<F>>();
+  Xyzz<F>* T1 = c->Ts[slot].as<Xyzz<F>>();
+  Xyzz<F>* R2 = c->lvl2[slot].as<Xyzz<F>>();
+  Xyzz<F>* T2 = R2 + rows * p.N2;
+  Xyzz<F>* RT = T2 + rows * p.N2;
+  Stage st(c, tag, stream);
+  if (reduce_deep(s)) {
+    uint32_t lg = 0; while ((1u << lg) < s.nb) lg++;
+    const Xyzz<F>* main_in = c->buckets[slot].as<Xyzz<F>>();
+    uint32_t N = s.nb, n_pool = 0;
+    int pp = 0;
+    for (uint32_t done = 0; done < lg;) {
+      const uint32_t lgL = lg - done >= 3 ? 3 : lg - done;
+      Xyzz<F>* main_out = c->red_main[slot][pp].as<Xyzz<F>>();
+      Xyzz<F>* pool_out = c->red_pool[slot][pp].as<Xyzz<F>>();
+      const Xyzz<F>* pool_in = c->red_pool[slot][pp ^ 1].as<Xyzz<F>>();
+      ZK_LAUNCH(k_reduce_bits_level<F>, rows * (N >> lgL) * (1 + n_pool + lgL), 64, stream, main_in, pool_in, n_pool, rows, N, lgL,
+                main_out, pool_out);
+      main_in = main_out; N >>= lgL; n_pool += lgL; done += lgL; pp ^= 1;
+    }
+    ZK_LAUNCH(k_reduce_bits_final<F>, rows, 32, stream, main_in, (const Xyzz<F>*)c->red_pool[slot][pp ^ 1].as<Xyzz<F>>(), n_pool, rows,
+              c->win[slot].as<Xyzz<F>>());
+    ZK_LAUNCH(k_msm_combine<F>, s.B, 32, stream, c->win[slot].as<Xyzz<F>>(), s, out);
+    CU(cudaGetLastError());
+    return 0;
+  }
+  const uint32_t S = s.lsS ? (1u << s.lsS) : accumulate_chunk(), cpr = (s.cap + S - 1) / S;
+  ZK_LAUNCH(k_reduce_level1_fused<F>, rows * p.N1, 128, stream, (const Xyzz<F>*)c->buckets[slot].as<Xyzz<F>>(),
+            (const Xyzz<F>*)c->head[slot].as<Xyzz<F>>(), (const Xyzz<F>*)c->tail[slot].as<Xyzz<F>>(), c->offsets[gen].as<uint32_t>(),
+            c->counts[gen].as<uint32_t>(), rows, s.nb, p.L1, S, cpr, R1, T1);
+  ZK_LAUNCH(k_reduce_level<F>, rows * p.N2, 128, stream, (const Xyzz<F>*)R1, rows, p.N1, p.L2, R2, T2);
+  ZK_LAUNCH(k_reduce_level<F>, rows * p.N2, 128, stream, (const Xyzz<F>*)T1, rows, p.N1, p.L2, RT, (Xyzz<F>*)nullptr);
+  ZK_LAUNCH(k_reduce_final<F>, rows, 32, stream, (const Xyzz<F>*)R2, (const Xyzz<F>*)T2, (const Xyzz<F>*)RT, rows, p.N2, p.L1, p.L2,
+            c->win[slot].as<Xyzz<F>>());
+  ZK_LAUNCH(k_msm_combine<F>, s.B, 32, stream, c->win[slot].as<Xyzz<F>>(), s, out);
+  CU(cudaGetLastError());
+  return 0;
+}
+template <class F>
+int msm_run(zkfl_ctx* c, const Affine<F>* bases, const MsmShape& s, Xyzz<F>* out, const char* acc_tag, const char* red_tag) {
+  TRY(msm_accumulate<F>(c, bases, s, 0, acc_tag, 0));
+  TRY(msm_reserve_reduce(c, s, 0, sizeof(Xyzz<F>)));
+  return msm_reduce<F>(c, s, 0, out, c->stream, red_tag, 0);
+}
+
+template <class F>
+int msm_precompute_windows(zkfl_ctx* c, const Affine<F>* raw, uint32_t cnt, uint32_t cw, uint32_t W, Affine<F>* table) {
+  ZK_LAUNCH(k_precompute_windows<F>, cnt, 64, c->stream, raw, cnt, cw, W, table);
+  CU(cudaGetLastError());
+  return 0;
+}
+template <class F>
+int msm_fixed_base_table(zkfl_ctx* c, const Affine<F>& base, Affine<F>* tab) {
+  ZK_LAUNCH(k_fixed_base_table<F>, 32 * 256, 64, c->stream, base, tab);
+  CU(cudaGetLastError());
+  return 0;
+}
+template <class F>
+int msm_to_affine_canonical(zkfl_ctx* c, const Xyzz<F>* in, size_t n, Affine<F>* out) {
+  ZK_LAUNCH(k_to_affine_canonical<F>, n, n < 64 ? 32 : 64, c->stream, in, n, out);
+  CU(cudaGetLastError());
+  return 0;
+}
+template <class F>
+int msm_sum_partials(zkfl_ctx* c, const Affine<F>* parts, uint32_t nparts, size_t part_stride, size_t n, Xyzz<F>* out) {
+  ZK_LAUNCH(k_sum_partials<F>, n, 64, c->stream, parts, nparts, part_stride, (size_t)1, n, out);
+  CU(cudaGetLastError());
+  return 0;
+}
+template <class F>
+int msm_gen_mul(zkfl_ctx* c, const Affine<F>& gen, const uint8_t* scalars, size_t n, uint8_t* out) {
+  if (!c || !scalars || !out || n == 0) return fail(ZKFL_ERR_ARG, "bad argument");
+  for (size_t i = 0; i < n; i++) if (!fr_bytes_lt_mod(scalars + 32 * i)) return fail(ZKFL_ERR_ARG, "scalar not reduced mod r");
+  CU(cudaSetDevice(c->device));
+  DevBuf sc, pts;
+  TRY(sc.reserve(n * sizeof(Fr))); TRY(pts.reserve(n * sizeof(Affine<F>)));
+  CU(cudaMemcpyAsync(sc.p, scalars, n * sizeof(Fr), cudaMemcpyHostToDevice, c->stream));
+  ZK_LAUNCH(k_gen_mul<F>, n, 64, c->stream, gen, sc.as<Fr>(), n, pts.as<Affine<F>>());
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(out, pts.p, n * sizeof(Affine<F>), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+template <class F>
+int msm_point_scale(zkfl_ctx* c, const uint8_t* pts, const uint8_t* scalar, size_t n, uint8_t* out) {
+  if (!c || !pts || !scalar || !out || n == 0) return fail(ZKFL_ERR_ARG, "bad argument");
+  if (!fr_bytes_lt_mod(scalar)) return fail(ZKFL_ERR_ARG, "scalar not reduced mod r");
+  CU(cudaSetDevice(c->device));
+  DevBuf in, res;
+  TRY(in.reserve(n * sizeof(Affine<F>))); TRY(res.reserve(n * sizeof(Affine<F>)));
+  Fr k; memcpy(k.v, scalar, 32);
+  CU(cudaMemcpyAsync(in.p, pts, n * sizeof(Affine<F>), cudaMemcpyHostToDevice, c->stream));
+  ZK_LAUNCH(k_point_scale<F>, n, 64, c->stream, in.as<Affine<F>>(), k, n, res.as<Affine<F>>());
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(out, res.p, n * sizeof(Affine<F>), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+#define ZK_INSTANTIATE_MSM(F)                                                                                              \
+  template int msm_accumulate<F>(zkfl_ctx*, const Affine<F>*, const MsmShape&, int, const char*, int);                       \
+  template int msm_reduce<F>(zkfl_ctx*, const MsmShape&, int, Xyzz<F>*, cudaStream_t, const char*, int);                     \
+  template int msm_run<F>(zkfl_ctx*, const Affine<F>*, const MsmShape&, Xyzz<F>*, const char*, const char*);               \
+  template int msm_precompute_windows<F>(zkfl_ctx*, const Affine<F>*, uint32_t, uint32_t, uint32_t, Affine<F>*);           \
+  template int msm_fixed_base_table<F>(zkfl_ctx*, const Affine<F>&, Affine<F>*);                                           \
+  template int msm_to_affine_canonical<F>(zkfl_ctx*, const Xyzz<F>*, size_t, Affine<F>*);                                  \
+  template int msm_sum_partials<F>(zkfl_ctx*, const Affine<F>*, uint32_t, size_t, size_t, Xyzz<F>*);                       \
+  template int msm_gen_mul<F>(zkfl_ctx*, const Affine<F>&, const uint8_t*, size_t, uint8_t*);                              \
+  template int msm_point_scale<F>(zkfl_ctx*, const uint8_t*, const uint8_t*, size_t, uint8_t*);

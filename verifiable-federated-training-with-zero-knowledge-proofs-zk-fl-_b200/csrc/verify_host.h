@@ -11,15 +11,32 @@ using namespace zkp;
 
 static const PairingConsts& consts() { static const PairingConsts k = make_consts(); return k; }
 
+// ONE validation of a verification key for the host verifier and the device batch verifier: every coordinate reduced mod q,
+// every point (alpha, beta, gamma, delta, IC[0..l]) on its curve.  false -> both paths answer ZKFL_ERR_FORMAT.
+static bool vkey_well_formed(const uint8_t alpha1[64], const uint8_t beta2[128], const uint8_t gamma2[128], const uint8_t delta2[128],
+                             const uint8_t* ic, uint32_t l) {
+  const PairingConsts& k = consts();
+  uint32_t w[32];
+  auto coords_ok = [&](const uint8_t* p, int n) { memcpy(w, p, 32 * (size_t)n); for (int i = 0; i < n; i++) if (!canonical_lt(w + 8 * i, false)) return false; return true; };
+  if (!coords_ok(alpha1, 2) || !g1_on_curve(g1_from_canonical(w), k)) return false;
+  const uint8_t* g2s[3] = {beta2, gamma2, delta2};
+  for (int i = 0; i < 3; i++) if (!coords_ok(g2s[i], 4) || !g2_on_curve(g2_from_canonical(w), k)) return false;
+  for (uint32_t i = 0; i <= l; i++) if (!coords_ok(ic + 64 * (size_t)i, 2) || !g1_on_curve(g1_from_canonical(w), k)) return false;
+  return true;
+}
+
 // returns 1 = valid, 0 = invalid, negative = malformed input.  All points affine canonical little-endian.
 static int groth16_verify(const uint8_t alpha1[64], const uint8_t beta2[128], const uint8_t gamma2[128], const uint8_t delta2[128],
                           const uint8_t* ic /* (l+1) x 64 */, const uint8_t* publics /* l x 32 */, uint32_t l, const uint8_t proof[256]) {
   const PairingConsts& k = consts();
+  if (!vkey_well_formed(alpha1, beta2, gamma2, delta2, ic, l)) return -1;
   uint32_t pw[64], w[32];
   memcpy(pw, proof, 256);
   for (int i = 0; i < 8; i++) if (!canonical_lt(pw + 8 * i, false)) return 0;
   G1P A = g1_from_canonical(pw), C = g1_from_canonical(pw + 48);
   G2P Bp = g2_from_canonical(pw + 16);
+  // an all-zero proof point is the affine point (0, 0), which is not on the curve (snarkjs rejects it): malformed, not infinity
+  if (A.inf || C.inf || Bp.inf) return 0;
   if (!g1_on_curve(A, k) || !g1_on_curve(C, k) || !g2_on_curve(Bp, k)) return 0;
   memcpy(w, ic, 64);
   zk::G1Xyzz vkx = zk::G1Xyzz::from_affine(g1_to_affine(g1_from_canonical(w)));

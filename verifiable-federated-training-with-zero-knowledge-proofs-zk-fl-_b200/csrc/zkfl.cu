@@ -1,23 +1,13 @@
-// libzkfl.so host side: artefact parsing (.zkey / .r1cs / .zkwp), HBM residency, kernel orchestration
-// on one CUDA stream per context, and the C ABI declared in include/zkfl.h.
-#include "kernels.cuh"
-#include "verify_host.h"
-
-#include <atomic>
-#include <cstdio>
-#include <cstdlib>
-#include <map>
-#include <memory>
-#include <string>
-#include <vector>
-
-#include "../../include/zkfl.h"
+// libzkfl.so host side: artefact parsing (.zkey / .r1cs / .zkwp), HBM residency, orchestration of the proving
+// pipeline on one CUDA stream per context (side streams for the bucket reductions), and the C ABI declared in
+// include/zkfl.h.  Kernel families live in witness.cu, msm_g1.cu, msm_g2.cu, verify.cu (see host.h).
+#define ZK_K_FIN
+#define ZK_K_BENCH
+#include "host.h"
 
 #ifdef ZKFL_EMUL
 thread_local zk_emul_idx zk_emul_cur;
 #endif
-
-using namespace zk;
 
 // ------------------------------------------------------------------------------------ errors / counters
 static thread_local std::string g_err;
@@ -44,81 +34,8 @@ void debug_check(const char* name, cudaStream_t stream) {
 #endif
 }
 }  // namespace zkrt
-static int fail(int code, const std::string& msg) { g_err = msg; return code; }
-
-#define CU(expr)                                                                                     \
-  do {                                                                                               \
-    cudaError_t _e = (expr);                                                                         \
-    if (_e != cudaSuccess) return fail(ZKFL_ERR_CUDA, std::string(#expr) + ": " + zkrt::err_str(_e)); \
-  } while (0)
-#define TRY(expr)            \
-  do {                       \
-    int _r = (expr);         \
-    if (_r != 0) return _r;  \
-  } while (0)
-
-struct DevBuf {
-  void* p = nullptr;
-  size_t cap = 0;
-  int reserve(size_t bytes) {
-    if (bytes <= cap) return 0;
-    if (p) cudaFree(p);
-    p = nullptr; cap = 0;
-    // grow with headroom so alternating batch sizes do not thrash
-    cudaError_t e = cudaMalloc(&p, bytes);
-    if (e != cudaSuccess) { p = nullptr; return fail(ZKFL_ERR_NOMEM, "cudaMalloc(" + std::to_string(bytes) + ") failed"); }
-    cap = bytes;
-    return 0;
-  }
-  template <class T> T* as() const { return (T*)p; }
-  ~DevBuf() { if (p) cudaFree(p); }
-  DevBuf() = default;
-  DevBuf(const DevBuf&) = delete;
-  DevBuf& operator=(const DevBuf&) = delete;
-};
-
-struct ProfRec { std::string name; cudaEvent_t e0, e1; uint64_t launches; };
-struct ProfAgg { double ms = 0; uint64_t launches = 0; uint64_t calls = 0; };
-
-struct zkfl_ctx {
-  int device = 0;
-  cudaStream_t stream = nullptr;
-  bool prof = false;
-  std::vector<ProfRec> pending;
-  std::map<std::string, ProfAgg> agg;
-  std::vector<std::string> order;
-  // workspace (grow-only)
-  DevBuf w, abc, hsc, stage_in, stage_rs, aos;
-  DevBuf counts, offsets, cursors, chunk_sums, sorted, skey, head, tail;
-  DevBuf v_ic, v_pub, v_proofs, v_t, v_g1, v_g2, v_flags, v_f, v_halves, v_ok;   // batch verifier
-  DevBuf aff_acc, aff_pre;   // batch-affine accumulation: running affine sums and prefix products, [slot group][lane]
-  // five MSMs per proof batch (A, C, B1, H on G1; B2 on G2): own bucket / reduction buffers each, so the
-  // latency-bound bucket reduction of one MSM runs on `side` while the next MSM accumulates on `stream`
-  DevBuf buckets[5], Rs[5], Ts[5], lvl2[5], win[5];
-  DevBuf red_main[5][2], red_pool[5][2];   // ping-pong buffers of the latency variant of the bucket reduction
-  cudaStream_t side[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // one per MSM slot: the reductions are latency-bound and run concurrently
-  cudaEvent_t ev_acc[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}, ev_red[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-  DevBuf res_g1, res_g2, t_g1, t_g2, pis, var, proofs, pubs, bad;
-  DevBuf msm_sc, msm_out, mask_w, mask_wb, mask_h, part_out, part_in;
-  cudaEvent_t t0 = nullptr, t1 = nullptr, ev_join = nullptr;
-};
-
-struct Stage {
-  zkfl_ctx* c; size_t idx = (size_t)-1; uint64_t l0; cudaStream_t st;
-  Stage(zkfl_ctx* c_, const char* name, cudaStream_t stream = nullptr) : c(c_), st(stream ? stream : c_->stream) {
-    if (!c->prof) return;
-    ProfRec r; r.name = name; r.launches = 0;
-    cudaEventCreate(&r.e0); cudaEventCreate(&r.e1);
-    cudaEventRecord(r.e0, st);
-    l0 = g_launches.load();
-    c->pending.push_back(r); idx = c->pending.size() - 1;
-  }
-  ~Stage() {
-    if (idx == (size_t)-1) return;
-    cudaEventRecord(c->pending[idx].e1, st);
-    c->pending[idx].launches = g_launches.load() - l0;
-  }
-};
+int zk_fail(int code, const std::string& msg) { g_err = msg; return code; }
+uint64_t zk_launches_now() { return g_launches.load(); }
 
 // ------------------------------------------------------------------------------------ host field helpers
 static Fr fr_from_bytes_canonical(const uint8_t* p) { Fr r; memcpy(r.v, p, 32); return r; }
@@ -137,15 +54,14 @@ static Fr fr_root_of_unity(int power) {  // ffjavascript: nqr = 5, w[28] = 5^((r
   for (int i = 28; i > power; i--) w = w.sqr();
   return w;
 }
-static bool fr_bytes_lt_mod(const uint8_t* p) {
+bool fr_bytes_lt_mod(const uint8_t* p) {
   uint32_t v[8]; memcpy(v, p, 32);
   for (int i = 7; i >= 0; i--) { if (v[i] < FrP::mod(i)) return true; if (v[i] > FrP::mod(i)) return false; }
   return false;
 }
 
 // ------------------------------------------------------------------------------------ iden3 binfile
-struct Sec { const uint8_t* p; uint64_t len; };
-static int parse_sections(const uint8_t* d, size_t len, const char* magic, std::map<uint32_t, Sec>& out) {
+int parse_sections(const uint8_t* d, size_t len, const char* magic, std::map<uint32_t, Sec>& out) {
   if (!d || len < 12 || memcmp(d, magic, 4)) return fail(ZKFL_ERR_FORMAT, std::string("bad magic, expected ") + magic);
   uint32_t n; memcpy(&n, d + 8, 4);
   size_t p = 12;
@@ -159,28 +75,6 @@ static int parse_sections(const uint8_t* d, size_t len, const char* magic, std::
   return 0;
 }
 
-template <class T>
-static int upload(zkfl_ctx* c, DevBuf& buf, const T* host, size_t count) {
-  TRY(buf.reserve(count ? count * sizeof(T) : 16));
-  if (count) CU(cudaMemcpyAsync(buf.p, host, count * sizeof(T), cudaMemcpyHostToDevice, c->stream));
-  CU(cudaStreamSynchronize(c->stream));
-  return 0;
-}
-
-struct CsrHost {
-  std::vector<uint32_t> row_off, wire;
-  std::vector<Fr> coef;
-};
-struct CsrBufs {
-  DevBuf row_off, wire, coef;
-  CsrDev dev() const { CsrDev d; d.row_off = row_off.as<uint32_t>(); d.wire = wire.as<uint32_t>(); d.coef = coef.as<Fr>(); return d; }
-};
-static int upload_csr(zkfl_ctx* c, const CsrHost& h, CsrBufs& b) {
-  TRY(upload(c, b.row_off, h.row_off.data(), h.row_off.size()));
-  TRY(upload(c, b.wire, h.wire.data(), h.wire.size()));
-  TRY(upload(c, b.coef, h.coef.data(), h.coef.size()));
-  return 0;
-}
 // builds CSR from COO triples (row, wire, coef) with counting sort by row
 static void coo_to_csr(uint32_t n_rows, const std::vector<uint32_t>& rows, const std::vector<uint32_t>& wires,
                        const std::vector<Fr>& coefs, CsrHost& out) {
@@ -192,197 +86,6 @@ static void coo_to_csr(uint32_t n_rows, const std::vector<uint32_t>& rows, const
   for (size_t i = 0; i < rows.size(); i++) { uint32_t p = cur[rows[i]]++; out.wire[p] = wires[i]; out.coef[p] = coefs[i]; }
 }
 
-// ------------------------------------------------------------------------------------ handles
-struct zkfl_circuit {
-  zkfl_ctx* ctx;
-  uint32_t n_wires, n_public, n_inputs, n_ops;
-  DevBuf ops, lc_off, lc_wire, lc_coef, pos_in, pconst;
-  std::vector<uint32_t> level_off;  // ops [level_off[k], level_off[k+1]) form dependency level k
-  ProgramDev dev;
-};
-struct zkfl_r1cs {
-  zkfl_ctx* ctx;
-  uint32_t n_wires, n_constraints;
-  CsrBufs A, B, C;
-};
-struct zkfl_zkey {
-  zkfl_ctx* ctx;
-  uint32_t n_vars, n_public, domain, log_n;
-  CsrBufs A, B;
-  DevBuf pA, pB1, pB2, pC, pH, skipB, tw_fwd, tw_inv, coset, tab_d1, tab_d2;
-  uint32_t c_w = 0, c_h = 0;  // window sizes the precomputed tables were built for
-  VkDev vk;
-};
-struct MsmBases {
-  zkfl_ctx* ctx; int group; size_t n; DevBuf pts;
-};
-
-// ------------------------------------------------------------------------------------ MSM pipeline
-static uint32_t env_u32(const char* name, uint32_t dflt) {
-  const char* v = getenv(name);
-  return v && *v ? (uint32_t)strtoul(v, nullptr, 10) : dflt;
-}
-static uint32_t accumulate_chunk() { uint32_t S = env_u32("ZKFL_MSM_CHUNK", 32); return S < 4 ? 4 : S; }
-static uint32_t affine_slots() { uint32_t K = env_u32("ZKFL_MSM_AFFINE_K", 64); return K < 1 ? 1 : (K > 4096 ? 4096 : K); }   // chunks per thread
-// shared = all windows of a proof accumulate into ONE bucket set (bases table precomputed with the window shifts)
-static MsmShape msm_shape(uint32_t m, uint32_t B, bool shared, uint32_t force_c = 0) {
-  uint32_t best_c = 4; double best = 1e300;
-  for (uint32_t c = 4; c <= 16; c++) {
-    double W = 254 / c + 1, nb = (double)(1u << (c - 1));
-    double cost = shared ? W * (double)m + 2.6 * nb : W * ((double)m + 2.6 * nb);
-    if (cost < best) { best = cost; best_c = c; }
-  }
-  uint32_t c = force_c ? force_c : env_u32(shared ? "ZKFL_MSM_C_SHARED" : "ZKFL_MSM_C", best_c);
-  if (c < 2) c = 2;
-  if (c > 16) c = 16;
-  MsmShape s; s.m = m; s.B = B; s.c = c; s.W = 254 / c + 1; s.nb = 1u << (c - 1);
-  s.R = shared ? 1 : s.W;
-  s.cap = shared ? m * s.W : m;
-  s.lsS = 0;
-  // Batch-affine accumulation (k_msm_accumulate_affine): OPT-IN.  Measured on B200 at 1024 sgd_verified proofs it executes
-  // fewer instructions per addition than the XYZZ chunk kernel (2390 vs ~2600) but runs at 22 % FMA-pipe utilisation
-  // against 46 %: 130 registers, long-running warps (tail effect) and the serial latency of the shared inversion leave two
-  // warps per scheduler on average (profiles/r01_ncu_full_k_msm_accumulate_affine.csv), so the XYZZ kernel stays the default.
-  // ZKFL_MSM_AFFINE = 0 / unset: never, 1: always, 2: by size (needs K*S sorted entries per thread to fill the GPU).
-  const uint32_t mode = env_u32("ZKFL_MSM_AFFINE", 0);
-  uint32_t S = accumulate_chunk(), ls = 0;
-  while ((1u << ls) < S) ls++;
-  const double threads = (double)B * s.R * s.cap / ((double)(1u << ls) * affine_slots());
-  if (mode == 1 || (mode != 0 && shared && threads >= 148.0 * 512.0)) {
-    s.lsS = ls;
-    const uint32_t unit = (32u << ls) * affine_slots();   // a warp owns K groups of 32 chunks of ONE row
-    s.cap = (s.cap + unit - 1) / unit * unit;
-  }
-  return s;
-}
-// three-level reduction tree over nb = L1 * L2 * N2 buckets
-struct ReducePlan { uint32_t L1, L2, N1, N2; };
-static ReducePlan reduce_plan(const MsmShape& s) {
-  uint32_t lg = 0; while ((1u << lg) < s.nb) lg++;
-  uint32_t l1 = (lg + 2) / 3, l2 = (lg - l1 + 1) / 2;
-  ReducePlan p; p.L1 = 1u << l1; p.L2 = 1u << l2; p.N1 = s.nb >> l1; p.N2 = p.N1 >> l2;
-  return p;
-}
-
-static int msm_sort(zkfl_ctx* c, const Fr* scalars, const uint8_t* skip, const MsmShape& s) {
-  size_t rows = (size_t)s.B * s.R;
-  uint32_t nchunk = (s.nb + ZK_SCAN_CHUNK - 1) / ZK_SCAN_CHUNK;
-  TRY(c->counts.reserve(rows * s.nb * 4));
-  TRY(c->offsets.reserve(rows * s.nb * 4));
-  TRY(c->cursors.reserve(rows * s.nb * 4));
-  TRY(c->chunk_sums.reserve(rows * nchunk * 4));
-  TRY(c->sorted.reserve(rows * s.cap * 4));
-  TRY(c->skey.reserve(rows * s.cap * 2));
-  CU(cudaMemsetAsync(c->counts.p, 0, rows * s.nb * 4, c->stream));
-  ZK_LAUNCH(k_msm_count, (size_t)s.m * s.B, 256, c->stream, scalars, skip, s, c->counts.as<uint32_t>());
-  ZK_LAUNCH(k_msm_scan_chunks, rows * nchunk, 128, c->stream, c->counts.as<uint32_t>(), s, c->chunk_sums.as<uint32_t>());
-  ZK_LAUNCH(k_msm_scan_write, rows * nchunk, 128, c->stream, c->counts.as<uint32_t>(), c->chunk_sums.as<uint32_t>(), s,
-            c->offsets.as<uint32_t>(), c->cursors.as<uint32_t>());
-  ZK_LAUNCH(k_msm_scatter, (size_t)s.m * s.B, 256, c->stream, scalars, skip, s, c->cursors.as<uint32_t>(), c->sorted.as<uint32_t>(),
-            c->skey.as<uint16_t>());
-  CU(cudaGetLastError());
-  return 0;
-}
-// bucket accumulation of one MSM (slot = which of the five buffer sets), on the main stream; uses the lists left by msm_sort
-template <class F>
-static int msm_accumulate(zkfl_ctx* c, const Affine<F>* bases, const MsmShape& s, int slot, const char* tag) {
-  size_t rows = (size_t)s.B * s.R;
-  TRY(c->buckets[slot].reserve(rows * s.nb * sizeof(Xyzz<F>)));
-  const uint32_t S = s.lsS ? (1u << s.lsS) : accumulate_chunk(), cpr = (s.cap + S - 1) / S;
-  TRY(c->head.reserve(rows * cpr * sizeof(Xyzz<F>)));
-  TRY(c->tail.reserve(rows * cpr * sizeof(Xyzz<F>)));
-  if (s.lsS) {
-    const uint32_t K = affine_slots();
-    const size_t n_groups = rows * (cpr >> 5);
-    if ((cpr >> 5) % K != 0 || rows >= 0xFFFFFFFFull) return fail(ZKFL_ERR_ARG, "batch-affine accumulation: bad list geometry");
-    TRY(c->aff_acc.reserve(n_groups * 32 * sizeof(Affine<F>)));
-    TRY(c->aff_pre.reserve(n_groups * 32 * sizeof(F)));
-    Stage st(c, tag);
-    ZK_LAUNCH(k_msm_accumulate_affine<F>, n_groups / K * 32, 128, c->stream, bases, c->sorted.as<uint32_t>(),
-              c->skey.as<uint16_t>(), c->offsets.as<uint32_t>(), c->counts.as<uint32_t>(), s, K, (uint32_t)rows,
-              c->aff_acc.as<Affine<F>>(), c->aff_pre.as<F>(), c->buckets[slot].as<Xyzz<F>>(), c->head.as<Xyzz<F>>(),
-              c->tail.as<Xyzz<F>>());
-    ZK_LAUNCH(k_msm_fixup<F>, rows * s.nb, 128, c->stream, c->offsets.as<uint32_t>(), c->counts.as<uint32_t>(), s, S, cpr,
-              c->head.as<Xyzz<F>>(), c->tail.as<Xyzz<F>>(), c->buckets[slot].as<Xyzz<F>>());
-    CU(cudaGetLastError());
-    return 0;
-  }
-  Stage st(c, tag);
-  ZK_LAUNCH(k_msm_accumulate_chunks<F>, rows * cpr, 128, c->stream, bases, c->sorted.as<uint32_t>(), c->skey.as<uint16_t>(),
-            c->offsets.as<uint32_t>(), c->counts.as<uint32_t>(), s, S, cpr, c->buckets[slot].as<Xyzz<F>>(), c->head.as<Xyzz<F>>(),
-            c->tail.as<Xyzz<F>>());
-  ZK_LAUNCH(k_msm_fixup<F>, rows * s.nb, 128, c->stream, c->offsets.as<uint32_t>(), c->counts.as<uint32_t>(), s, S, cpr,
-            c->head.as<Xyzz<F>>(), c->tail.as<Xyzz<F>>(), c->buckets[slot].as<Xyzz<F>>());
-  CU(cudaGetLastError());
-  return 0;
-}
-// few rows: the bit-decomposed tree of plain sums (k_reduce_bits_level) instead of the three-level running sums
-static bool reduce_deep(const MsmShape& s) {
-  const uint32_t mode = env_u32("ZKFL_REDUCE_DEEP", 2);   // 0 never, 1 always, 2 by size
-  return mode == 1 || (mode == 2 && (size_t)s.B * s.R <= 32 && s.nb >= 64);
-}
-static int msm_reserve_reduce(zkfl_ctx* c, const MsmShape& s, int slot, size_t elem) {
-  size_t rows = (size_t)s.B * s.R;
-  ReducePlan p = reduce_plan(s);
-  if (reduce_deep(s)) {
-    for (int k = 0; k < 2; k++) {
-      TRY(c->red_main[slot][k].reserve(rows * (s.nb / 2) * elem));
-      TRY(c->red_pool[slot][k].reserve(rows * s.nb * elem));   // <= 3/8 + 6/64 + ... of nb per row, with slack for small fan-ins
-    }
-  }
-  TRY(c->Rs[slot].reserve(rows * p.N1 * elem));
-  TRY(c->Ts[slot].reserve(rows * p.N1 * elem));
-  TRY(c->lvl2[slot].reserve(3 * rows * p.N2 * elem));
-  TRY(c->win[slot].reserve(rows * elem));
-  return 0;
-}
-// bucket reduction sum_k (k+1) * B_k of one MSM on `stream` -> out[B]. Buffers must have been reserved (msm_reserve_reduce).
-template <class F>
-static int msm_reduce(zkfl_ctx* c, const MsmShape& s, int slot, Xyzz<F>* out, cudaStream_t stream, const char* tag) {
-  size_t rows = (size_t)s.B * s.R;
-  ReducePlan p = reduce_plan(s);
-  Xyzz<F>* R1 = c->Rs[slot].as<Xyzz<F>>();
-  Xyzz<F>* T1 = c->Ts[slot].as<Xyzz<F>>();
-  Xyzz<F>* R2 = c->lvl2[slot].as<Xyzz<F>>();
-  Xyzz<F>* T2 = R2 + rows * p.N2;
-  Xyzz<F>* RT = T2 + rows * p.N2;
-  Stage st(c, tag, stream);
-  if (reduce_deep(s)) {
-    uint32_t lg = 0; while ((1u << lg) < s.nb) lg++;
-    const Xyzz<F>* main_in = c->buckets[slot].as<Xyzz<F>>();
-    uint32_t N = s.nb, n_pool = 0;
-    int pp = 0;
-    for (uint32_t done = 0; done < lg;) {
-      const uint32_t lgL = lg - done >= 3 ? 3 : lg - done;
-      Xyzz<F>* main_out = c->red_main[slot][pp].as<Xyzz<F>>();
-      Xyzz<F>* pool_out = c->red_pool[slot][pp].as<Xyzz<F>>();
-      const Xyzz<F>* pool_in = c->red_pool[slot][pp ^ 1].as<Xyzz<F>>();
-      ZK_LAUNCH(k_reduce_bits_level<F>, rows * (N >> lgL) * (1 + n_pool + lgL), 64, stream, main_in, pool_in, n_pool, rows, N, lgL,
-                main_out, pool_out);
-      main_in = main_out; N >>= lgL; n_pool += lgL; done += lgL; pp ^= 1;
-    }
-    ZK_LAUNCH(k_reduce_bits_final<F>, rows, 32, stream, main_in, (const Xyzz<F>*)c->red_pool[slot][pp ^ 1].as<Xyzz<F>>(), n_pool, rows,
-              c->win[slot].as<Xyzz<F>>());
-    ZK_LAUNCH(k_msm_combine<F>, s.B, 32, stream, c->win[slot].as<Xyzz<F>>(), s, out);
-    CU(cudaGetLastError());
-    return 0;
-  }
-  ZK_LAUNCH(k_reduce_level<F>, rows * p.N1, 64, stream, c->buckets[slot].as<Xyzz<F>>(), rows, s.nb, p.L1, R1, T1);
-  ZK_LAUNCH(k_reduce_level<F>, rows * p.N2, 64, stream, (const Xyzz<F>*)R1, rows, p.N1, p.L2, R2, T2);
-  ZK_LAUNCH(k_reduce_level<F>, rows * p.N2, 64, stream, (const Xyzz<F>*)T1, rows, p.N1, p.L2, RT, (Xyzz<F>*)nullptr);
-  ZK_LAUNCH(k_reduce_final<F>, rows, 32, stream, (const Xyzz<F>*)R2, (const Xyzz<F>*)T2, (const Xyzz<F>*)RT, rows, p.N2, p.L1, p.L2,
-            c->win[slot].as<Xyzz<F>>());
-  ZK_LAUNCH(k_msm_combine<F>, s.B, 32, stream, c->win[slot].as<Xyzz<F>>(), s, out);
-  CU(cudaGetLastError());
-  return 0;
-}
-template <class F>
-static int msm_run(zkfl_ctx* c, const Affine<F>* bases, const MsmShape& s, Xyzz<F>* out, const char* acc_tag, const char* red_tag) {
-  TRY(msm_accumulate<F>(c, bases, s, 0, acc_tag));
-  TRY(msm_reserve_reduce(c, s, 0, sizeof(Xyzz<F>)));
-  return msm_reduce<F>(c, s, 0, out, c->stream, red_tag);
-}
-
 // ------------------------------------------------------------------------------------ prove pipeline (witness in c->w)
 static int finalize_from_sums(zkfl_ctx* c, const zkfl_zkey* z, const Fr* rs_dev, uint32_t B);
 // part / nparts: this context handles the point range [part*m/nparts, (part+1)*m/nparts) of every MSM (nparts == 1: all).
@@ -391,38 +94,9 @@ static int prove_from_device_witness(zkfl_ctx* c, const zkfl_zkey* z, const Fr* 
                                      uint32_t nparts = 1, bool finalize = true) {
   const uint32_t n = z->domain, m = z->n_vars;
   Fr* w = c->w.as<Fr>();
-  TRY(c->abc.reserve(3 * (size_t)n * B * sizeof(Fr)));
-  TRY(c->hsc.reserve((size_t)n * B * sizeof(Fr)));
+  TRY(run_h_poly(c, z, B));
   TRY(c->res_g1.reserve(4 * (size_t)B * sizeof(G1Xyzz)));
   TRY(c->res_g2.reserve((size_t)B * sizeof(G2Xyzz)));
-  Fr* abc = c->abc.as<Fr>();
-  {
-    Stage st(c, "build_abc");
-    ZK_LAUNCH(k_build_abc, (size_t)n * B, 128, c->stream, z->A.dev(), z->B.dev(), w, abc, n, B);
-  }
-  {
-    Stage st(c, "ntt");
-    // inverse transform (DIF, natural -> bit-reversed), 3 stages per pass; the last pass also applies n^-1 * w_2n^bitrev(p)
-    auto radix = [&](int K, uint32_t half, int dif, const Fr* twd, const Fr* scale) {
-      size_t threads = (size_t)3 * (n >> K) * B;
-      if (K == 3) ZK_LAUNCH(k_ntt_radix<3>, threads, 128, c->stream, abc, twd, scale, n, B, 3u, half, dif);
-      else if (K == 2) ZK_LAUNCH(k_ntt_radix<2>, threads, 128, c->stream, abc, twd, scale, n, B, 3u, half, dif);
-      else ZK_LAUNCH(k_ntt_radix<1>, threads, 256, c->stream, abc, twd, scale, n, B, 3u, half, dif);
-    };
-    const int lg = (int)z->log_n;
-    for (int done = 0; done < lg;) {   // DIF: stage t has half = n >> (t + 1)
-      int K = lg - done >= 3 ? 3 : lg - done;
-      bool last = done + K == lg;
-      radix(K, n >> (done + 1), 1, z->tw_inv.as<Fr>(), last ? z->coset.as<Fr>() : nullptr);
-      done += K;
-    }
-    for (int done = 0; done < lg;) {   // DIT: stage t has half = 1 << t
-      int K = lg - done >= 3 ? 3 : lg - done;
-      radix(K, 1u << done, 0, z->tw_fwd.as<Fr>(), nullptr);
-      done += K;
-    }
-    ZK_LAUNCH(k_join_abc, (size_t)n * B, 256, c->stream, abc, c->hsc.as<Fr>(), n, B);
-  }
   G1Xyzz* r1 = c->res_g1.as<G1Xyzz>();
   G2Xyzz* r2 = c->res_g2.as<G2Xyzz>();
   MsmShape sw = msm_shape(m, B, true, z->c_w);
@@ -444,38 +118,38 @@ static int prove_from_device_witness(zkfl_ctx* c, const zkfl_zkey* z, const Fr* 
     TRY(c->mask_w.reserve(m)); TRY(c->mask_wb.reserve(m)); TRY(c->mask_h.reserve(n));
     uint32_t lo = (uint32_t)((uint64_t)m * part / nparts), hi = (uint32_t)((uint64_t)m * (part + 1) / nparts);
     uint32_t hlo = (uint32_t)((uint64_t)n * part / nparts), hhi = (uint32_t)((uint64_t)n * (part + 1) / nparts);
-    ZK_LAUNCH(k_range_mask, m, 256, c->stream, (const uint8_t*)nullptr, m, lo, hi, c->mask_w.as<uint8_t>());
-    ZK_LAUNCH(k_range_mask, m, 256, c->stream, z->skipB.as<uint8_t>(), m, lo, hi, c->mask_wb.as<uint8_t>());
-    ZK_LAUNCH(k_range_mask, n, 256, c->stream, (const uint8_t*)nullptr, n, hlo, hhi, c->mask_h.as<uint8_t>());
+    TRY(msm_range_mask(c, nullptr, m, lo, hi, c->mask_w.as<uint8_t>()));
+    TRY(msm_range_mask(c, z->skipB.as<uint8_t>(), m, lo, hi, c->mask_wb.as<uint8_t>()));
+    TRY(msm_range_mask(c, nullptr, n, hlo, hhi, c->mask_h.as<uint8_t>()));
     skip_w = c->mask_w.as<uint8_t>(); skip_wb = c->mask_wb.as<uint8_t>(); skip_h = c->mask_h.as<uint8_t>();
   }
-  { Stage st(c, "msm_sort_w"); TRY(msm_sort(c, w, skip_w, sw)); }
-  TRY(msm_accumulate<Fq>(c, z->pA.as<G1Affine>(), sw, 0, "msm_acc_g1"));
+  { Stage st(c, "msm_sort_w"); TRY(msm_sort(c, w, skip_w, sw, 0)); }
+  TRY(msm_accumulate<Fq>(c, z->pA.as<G1Affine>(), sw, 0, "msm_acc_g1", 0));
   CU(cudaEventRecord(c->ev_acc[0], c->stream));
   CU(cudaStreamWaitEvent(c->side[0], c->ev_acc[0], 0));
-  TRY(msm_reduce<Fq>(c, sw, 0, r1, c->side[0], "msm_reduce_g1"));
+  TRY(msm_reduce<Fq>(c, sw, 0, r1, c->side[0], "msm_reduce_g1", 0));
   CU(cudaEventRecord(c->ev_red[0], c->side[0]));
-  TRY(msm_accumulate<Fq>(c, z->pC.as<G1Affine>(), sw, 1, "msm_acc_g1"));
+  TRY(msm_accumulate<Fq>(c, z->pC.as<G1Affine>(), sw, 1, "msm_acc_g1", 0));
   CU(cudaEventRecord(c->ev_acc[1], c->stream));
   CU(cudaStreamWaitEvent(c->side[1], c->ev_acc[1], 0));
-  TRY(msm_reduce<Fq>(c, sw, 1, r1 + 2 * (size_t)B, c->side[1], "msm_reduce_g1"));
+  TRY(msm_reduce<Fq>(c, sw, 1, r1 + 2 * (size_t)B, c->side[1], "msm_reduce_g1", 0));
   CU(cudaEventRecord(c->ev_red[1], c->side[1]));
-  { Stage st(c, "msm_sort_w"); TRY(msm_sort(c, w, skip_wb, sw)); }
-  TRY(msm_accumulate<Fq>(c, z->pB1.as<G1Affine>(), sw, 2, "msm_acc_g1"));
+  { Stage st(c, "msm_sort_w"); TRY(msm_sort(c, w, skip_wb, sw, 1)); }
+  TRY(msm_accumulate<Fq>(c, z->pB1.as<G1Affine>(), sw, 2, "msm_acc_g1", 1));
   CU(cudaEventRecord(c->ev_acc[2], c->stream));
   CU(cudaStreamWaitEvent(c->side[2], c->ev_acc[2], 0));
-  TRY(msm_reduce<Fq>(c, sw, 2, r1 + B, c->side[2], "msm_reduce_g1"));
+  TRY(msm_reduce<Fq>(c, sw, 2, r1 + B, c->side[2], "msm_reduce_g1", 1));
   CU(cudaEventRecord(c->ev_red[2], c->side[2]));
-  TRY(msm_accumulate<Fq2>(c, z->pB2.as<G2Affine>(), sw, 4, "msm_acc_g2"));
+  TRY(msm_accumulate<Fq2>(c, z->pB2.as<G2Affine>(), sw, 4, "msm_acc_g2", 1));
   CU(cudaEventRecord(c->ev_acc[4], c->stream));
   CU(cudaStreamWaitEvent(c->side[4], c->ev_acc[4], 0));
-  TRY(msm_reduce<Fq2>(c, sw, 4, r2, c->side[4], "msm_reduce_g2"));
+  TRY(msm_reduce<Fq2>(c, sw, 4, r2, c->side[4], "msm_reduce_g2", 1));
   CU(cudaEventRecord(c->ev_red[4], c->side[4]));
-  { Stage st(c, "msm_sort_h"); TRY(msm_sort(c, c->hsc.as<Fr>(), skip_h, sh)); }
-  TRY(msm_accumulate<Fq>(c, z->pH.as<G1Affine>(), sh, 3, "msm_acc_g1"));
+  { Stage st(c, "msm_sort_h"); TRY(msm_sort(c, c->hsc.as<Fr>(), skip_h, sh, 2)); }
+  TRY(msm_accumulate<Fq>(c, z->pH.as<G1Affine>(), sh, 3, "msm_acc_g1", 2));
   CU(cudaEventRecord(c->ev_acc[3], c->stream));
   CU(cudaStreamWaitEvent(c->side[3], c->ev_acc[3], 0));
-  TRY(msm_reduce<Fq>(c, sh, 3, r1 + 3 * (size_t)B, c->side[3], "msm_reduce_g1"));
+  TRY(msm_reduce<Fq>(c, sh, 3, r1 + 3 * (size_t)B, c->side[3], "msm_reduce_g1", 2));
   CU(cudaEventRecord(c->ev_red[3], c->side[3]));
   for (int i = 0; i < 5; i++) CU(cudaStreamWaitEvent(c->stream, c->ev_red[i], 0));
   if (!finalize) return 0;
@@ -527,53 +201,14 @@ static int stage_rs(zkfl_ctx* c, const uint8_t* rs, int B) {
   return 0;
 }
 
-static int run_witness(zkfl_ctx* c, const zkfl_circuit* circ, const uint8_t* inputs_host, uint32_t B) {
-  Stage st(c, "witness");
-  TRY(c->w.reserve((size_t)circ->n_wires * B * sizeof(Fr)));
-  if (inputs_host) {
-    TRY(c->stage_in.reserve((size_t)circ->n_inputs * B * sizeof(Fr)));
-    CU(cudaMemcpyAsync(c->stage_in.p, inputs_host, (size_t)circ->n_inputs * B * sizeof(Fr), cudaMemcpyHostToDevice, c->stream));
-  }
-  ZK_LAUNCH(k_aos_to_soa, (size_t)circ->n_inputs * B, 256, c->stream, c->stage_in.as<Fr>(), c->w.as<Fr>(), circ->n_inputs, B, 1u);
-  ZK_LAUNCH(k_witness_init, B, 128, c->stream, c->w.as<Fr>(), B);
-  for (size_t k = 0; k + 1 < circ->level_off.size(); k++) {
-    uint32_t lo = circ->level_off[k], hi = circ->level_off[k + 1];
-#ifndef ZKFL_EMUL
-    // few instances: one warp per (op, instance), Poseidon state across the lanes (ZKFL_WITNESS_COOP = 0 never, 1 always)
-    const uint32_t coop = env_u32("ZKFL_WITNESS_COOP", 2);
-    if (coop == 1 || (coop == 2 && B <= 32)) {
-      ZK_LAUNCH(k_witness_level_coop, (size_t)(hi - lo) * B * 32, 128, c->stream, circ->dev, c->w.as<Fr>(), B, lo, hi);
-      continue;
-    }
-#endif
-    ZK_LAUNCH(k_witness_level, (size_t)(hi - lo) * B, 64, c->stream, circ->dev, c->w.as<Fr>(), B, lo, hi);
-  }
-  CU(cudaGetLastError());
-  return 0;
-}
-
 static int fetch_publics(zkfl_ctx* c, uint32_t n_public, uint32_t B, uint8_t* publics_out) {
   if (!publics_out || !n_public) return 0;
   TRY(c->pubs.reserve((size_t)n_public * B * sizeof(Fr)));
-  ZK_LAUNCH(k_soa_to_aos, (size_t)n_public * B, 256, c->stream, c->w.as<Fr>() + B, c->pubs.as<Fr>(), n_public, B);
+  TRY(zk_soa_to_aos(c, c->w.as<Fr>() + B, c->pubs.as<Fr>(), n_public, B));
   CU(cudaMemcpyAsync(publics_out, c->pubs.p, (size_t)n_public * B * sizeof(Fr), cudaMemcpyDeviceToHost, c->stream));
   return 0;
 }
 
-static int check_r1cs_device(zkfl_ctx* c, const zkfl_r1cs* r, uint32_t B, uint32_t* first_bad) {
-  Stage st(c, "r1cs_check");
-  TRY(c->bad.reserve((size_t)B * 4));
-  CU(cudaMemsetAsync(c->bad.p, 0xFF, (size_t)B * 4, c->stream));
-  ZK_LAUNCH(k_r1cs_check, (size_t)r->n_constraints * B, 128, c->stream, r->A.dev(), r->B.dev(), r->C.dev(), c->w.as<Fr>(),
-            r->n_constraints, B, c->bad.as<uint32_t>());
-  std::vector<uint32_t> host(B);
-  CU(cudaMemcpyAsync(host.data(), c->bad.p, (size_t)B * 4, cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaStreamSynchronize(c->stream));
-  int bad = 0;
-  for (uint32_t b = 0; b < B; b++) { if (first_bad) first_bad[b] = host[b]; if (host[b] != 0xFFFFFFFFu) bad++; }
-  if (bad) return fail(ZKFL_ERR_ASSERT, "Assert Failed: " + std::to_string(bad) + " of " + std::to_string(B) + " witnesses violate a constraint");
-  return 0;
-}
 
 // ------------------------------------------------------------------------------------ C ABI
 extern "C" {
@@ -615,6 +250,7 @@ void zkfl_ctx_free(zkfl_ctx* c) {
   for (auto& r : c->pending) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
   if (c->t0) { cudaEventDestroy(c->t0); cudaEventDestroy(c->t1); }
   if (c->ev_join) cudaEventDestroy(c->ev_join);
+  if (c->chk_host) cudaFreeHost(c->chk_host);
   for (int i = 0; i < 5; i++) {
     if (!c->side[i]) continue;
     cudaStreamSynchronize(c->side[i]);
@@ -712,12 +348,32 @@ int zkfl_circuit_load(zkfl_ctx* c, const uint8_t* d, size_t len, zkfl_circuit** 
   if (k->level_off.front() != 0 || k->level_off.back() != k->n_ops) return fail(ZKFL_ERR_FORMAT, "zkwp: bad level schedule");
   for (size_t i = 0; i + 1 < k->level_off.size(); i++)
     if (k->level_off[i] > k->level_off[i + 1]) return fail(ZKFL_ERR_FORMAT, "zkwp: bad level schedule");
-  // validate ops reference existing widths / wires
+  // A .zkwp comes from disk (it stands where circom's .wasm stood): every index and extent is checked here, so a malformed
+  // program is rejected at load time and can never make a kernel read or write outside its buffers.
+  if ((uint64_t)k->n_inputs + 1 > k->n_wires || k->n_public > k->n_inputs) return fail(ZKFL_ERR_FORMAT, "zkwp: bad header counts");
+  const uint32_t* lc_off = (const uint32_t*)S[3].p;
+  const uint32_t* lc_wire = (const uint32_t*)S[4].p;
+  const uint32_t* pos_in = (const uint32_t*)S[6].p;
+  if (lc_off[0] != 0 || lc_off[n_lcs] != n_terms) return fail(ZKFL_ERR_FORMAT, "zkwp: bad linear-combination offsets");
+  for (uint32_t i = 0; i < n_lcs; i++) if (lc_off[i] > lc_off[i + 1]) return fail(ZKFL_ERR_FORMAT, "zkwp: bad linear-combination offsets");
+  for (uint32_t i = 0; i < n_terms; i++) if (lc_wire[i] >= k->n_wires) return fail(ZKFL_ERR_FORMAT, "zkwp: term wire out of range");
+  for (uint32_t i = 0; i < n_pos; i++) if (pos_in[i] >= k->n_wires) return fail(ZKFL_ERR_FORMAT, "zkwp: poseidon input wire out of range");
   const uint32_t* ops = (const uint32_t*)S[2].p;
   for (uint32_t o = 0; o < k->n_ops; o++) {
     const uint32_t* op = ops + 5 * (size_t)o;
-    if (op[0] < 1 || op[0] > 4 || op[1] >= k->n_wires) return fail(ZKFL_ERR_FORMAT, "zkwp: bad op");
-    if (op[0] == 4 && (op[2] > 17 || !k->dev.pk[op[2]].C)) return fail(ZKFL_ERR_FORMAT, "zkwp: poseidon width without constants");
+    const uint32_t code = op[0], dst = op[1];
+    uint64_t n_out = 1;
+    if (code < 1 || code > 4) return fail(ZKFL_ERR_FORMAT, "zkwp: bad op code");
+    if (code <= 3 && op[2] >= n_lcs) return fail(ZKFL_ERR_FORMAT, "zkwp: linear combination out of range");
+    if (code == 2 && (op[3] >= n_lcs || (op[4] != 0xFFFFFFFFu && op[4] >= n_lcs))) return fail(ZKFL_ERR_FORMAT, "zkwp: linear combination out of range");
+    if (code == 3) { if (op[3] > 254) return fail(ZKFL_ERR_FORMAT, "zkwp: bit decomposition wider than the field"); n_out = op[3]; }
+    if (code == 4) {
+      const uint32_t t = op[2];
+      if (t < 2 || t > 17 || !k->dev.pk[t].C) return fail(ZKFL_ERR_FORMAT, "zkwp: poseidon width without constants");
+      if ((uint64_t)op[3] + (t - 1) > n_pos) return fail(ZKFL_ERR_FORMAT, "zkwp: poseidon input list out of range");
+      n_out = 3ull * (8ull * t + k->dev.pk[t].rp) + 1;   // x^2, x^4, x^5 per S-box, then the output
+    }
+    if (dst <= k->n_inputs || (uint64_t)dst + n_out > k->n_wires) return fail(ZKFL_ERR_FORMAT, "zkwp: op output out of range");
   }
   *out = k.release();
   return 0;
@@ -823,9 +479,8 @@ int zkfl_zkey_load(zkfl_ctx* c, const uint8_t* d, size_t len, zkfl_zkey** out) {
     TRY(upload(c, raw, pts, bytes));
     uint32_t W = 254 / cw + 1;
     TRY(out.reserve((size_t)W * bytes));
-    if (g2) ZK_LAUNCH(k_precompute_windows<Fq2>, cnt, 64, c->stream, raw.as<G2Affine>(), cnt, cw, W, out.as<G2Affine>());
-    else ZK_LAUNCH(k_precompute_windows<Fq>, cnt, 64, c->stream, raw.as<G1Affine>(), cnt, cw, W, out.as<G1Affine>());
-    CU(cudaGetLastError());
+    if (g2) TRY(msm_precompute_windows<Fq2>(c, raw.as<G2Affine>(), cnt, cw, W, out.as<G2Affine>()));
+    else TRY(msm_precompute_windows<Fq>(c, raw.as<G1Affine>(), cnt, cw, W, out.as<G1Affine>()));
     CU(cudaStreamSynchronize(c->stream));
     return 0;
   };
@@ -835,9 +490,8 @@ int zkfl_zkey_load(zkfl_ctx* c, const uint8_t* d, size_t len, zkfl_zkey** out) {
   TRY(build_table(S[9].p, S[9].len, n, z->c_h, false, z->pH));
   TRY(z->tab_d1.reserve(32 * 256 * sizeof(G1Affine)));
   TRY(z->tab_d2.reserve(32 * 256 * sizeof(G2Affine)));
-  ZK_LAUNCH(k_fixed_base_table<Fq>, 32 * 256, 64, c->stream, z->vk.delta1, z->tab_d1.as<G1Affine>());
-  ZK_LAUNCH(k_fixed_base_table<Fq2>, 32 * 256, 64, c->stream, z->vk.delta2, z->tab_d2.as<G2Affine>());
-  CU(cudaGetLastError());
+  TRY(msm_fixed_base_table<Fq>(c, z->vk.delta1, z->tab_d1.as<G1Affine>()));
+  TRY(msm_fixed_base_table<Fq2>(c, z->vk.delta2, z->tab_d2.as<G2Affine>()));
   CU(cudaStreamSynchronize(c->stream));
   {  // wires without a B-query point (absent from the B matrix): dropped when sorting for the B1 / B2 MSMs
     std::vector<uint8_t> skip(m, 0);
@@ -888,7 +542,7 @@ int zkfl_wtns_calculate_batch(zkfl_ctx* c, const zkfl_circuit* k, const zkfl_r1c
   TRY(run_witness(c, k, inputs, (uint32_t)B));
   if (wtns_out) {
     TRY(c->aos.reserve((size_t)k->n_wires * B * sizeof(Fr)));
-    ZK_LAUNCH(k_soa_to_aos, (size_t)k->n_wires * B, 256, c->stream, c->w.as<Fr>(), c->aos.as<Fr>(), k->n_wires, (uint32_t)B);
+    TRY(zk_soa_to_aos(c, c->w.as<Fr>(), c->aos.as<Fr>(), k->n_wires, (uint32_t)B));
     CU(cudaMemcpyAsync(wtns_out, c->aos.p, (size_t)k->n_wires * B * sizeof(Fr), cudaMemcpyDeviceToHost, c->stream));
   }
   int rc = 0;
@@ -908,8 +562,7 @@ int zkfl_wtns_eval_wires(zkfl_ctx* c, const zkfl_circuit* k, const uint8_t* inpu
   TRY(c->bad.reserve((size_t)n_sel * 4));
   TRY(c->aos.reserve((size_t)n_sel * B * sizeof(Fr)));
   CU(cudaMemcpyAsync(c->bad.p, wires, (size_t)n_sel * 4, cudaMemcpyHostToDevice, c->stream));
-  ZK_LAUNCH(k_gather_wires, (size_t)n_sel * B, 256, c->stream, c->w.as<Fr>(), c->bad.as<uint32_t>(), n_sel, (uint32_t)B, c->aos.as<Fr>());
-  CU(cudaGetLastError());
+  TRY(zk_gather_wires(c, c->w.as<Fr>(), c->bad.as<uint32_t>(), n_sel, (uint32_t)B, c->aos.as<Fr>()));
   CU(cudaMemcpyAsync(out, c->aos.p, (size_t)n_sel * B * sizeof(Fr), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   return 0;
@@ -920,7 +573,7 @@ int zkfl_r1cs_check_batch(zkfl_ctx* c, const zkfl_r1cs* r, const uint8_t* wtns, 
   size_t cnt = (size_t)r->n_wires * B;
   TRY(c->aos.reserve(cnt * sizeof(Fr))); TRY(c->w.reserve(cnt * sizeof(Fr)));
   CU(cudaMemcpyAsync(c->aos.p, wtns, cnt * sizeof(Fr), cudaMemcpyDefault, c->stream));   // pageable, pinned or device memory
-  ZK_LAUNCH(k_aos_to_soa, cnt, 256, c->stream, c->aos.as<Fr>(), c->w.as<Fr>(), r->n_wires, (uint32_t)B, 0u);
+  TRY(zk_aos_to_soa(c, c->aos.as<Fr>(), c->w.as<Fr>(), r->n_wires, (uint32_t)B, 0u));
   return check_r1cs_device(c, r, (uint32_t)B, first_bad);
 }
 
@@ -935,30 +588,46 @@ int zkfl_groth16_prove_batch(zkfl_ctx* c, const zkfl_zkey* z, const uint8_t* wtn
     Stage st(c, "upload_wtns");
     TRY(c->aos.reserve(cnt * sizeof(Fr))); TRY(c->w.reserve(cnt * sizeof(Fr)));
     CU(cudaMemcpyAsync(c->aos.p, wtns, cnt * sizeof(Fr), cudaMemcpyDefault, c->stream));   // pageable, pinned or device memory
-    ZK_LAUNCH(k_aos_to_soa, cnt, 256, c->stream, c->aos.as<Fr>(), c->w.as<Fr>(), z->n_vars, (uint32_t)B, 0u);
+    TRY(zk_aos_to_soa(c, c->aos.as<Fr>(), c->w.as<Fr>(), z->n_vars, (uint32_t)B, 0u));
+    TRY(check_wtns_launch(c, z->n_vars, (uint32_t)B));   // snarkjs reads the .wtns through its field class: reduced values, w[0] = 1
   }
   TRY(prove_from_device_witness(c, z, c->stage_rs.as<Fr>(), (uint32_t)B));
   CU(cudaMemcpyAsync(proofs_out, c->proofs.p, (size_t)B * 256, cudaMemcpyDeviceToHost, c->stream));
   TRY(fetch_publics(c, z->n_public, (uint32_t)B, publics_out));
   CU(cudaStreamSynchronize(c->stream));
+  return checks_result(c, nullptr);
+}
+static int validate_inputs(const uint8_t* inputs, size_t count) {
+  for (size_t i = 0; i < count; i++)
+    if (!fr_bytes_lt_mod(inputs + 32 * i)) return fail(ZKFL_ERR_ARG, "input not reduced mod r");
   return 0;
 }
-int zkfl_groth16_full_prove_batch(zkfl_ctx* c, const zkfl_circuit* k, const zkfl_zkey* z, const uint8_t* inputs,
-                                  const uint8_t* rs, int B, uint8_t* proofs_out, uint8_t* publics_out) {
+// circom's witness calculator aborts at the first failing `===`, so `fullProve` never proves an unsatisfied witness.  With
+// r1cs != NULL the constraint check runs on the HBM-resident witness inside the same stream-ordered pass (no second witness
+// run, no copy of the witness to the host); its verdict is read after the final synchronisation: any violation -> the proofs
+// are NOT returned (buffers zeroed), ZKFL_ERR_ASSERT, first_bad[b] = first violated row or 0xFFFFFFFF.
+int zkfl_groth16_full_prove_batch(zkfl_ctx* c, const zkfl_circuit* k, const zkfl_zkey* z, const zkfl_r1cs* r, const uint8_t* inputs,
+                                  const uint8_t* rs, int B, uint8_t* proofs_out, uint8_t* publics_out, uint32_t* first_bad) {
   if (!c || !k || !z || !inputs || !proofs_out || B <= 0) return fail(ZKFL_ERR_ARG, "bad argument");
   if (k->n_wires != z->n_vars || k->n_public != z->n_public) return fail(ZKFL_ERR_ARG, "circuit and zkey do not match");
+  if (r && r->n_wires != k->n_wires) return fail(ZKFL_ERR_ARG, "r1cs does not match circuit");
+  TRY(validate_inputs(inputs, (size_t)B * k->n_inputs));
   CU(cudaSetDevice(c->device));
   TRY(stage_rs(c, rs, B));
   TRY(run_witness(c, k, inputs, (uint32_t)B));
+  if (r) TRY(check_r1cs_launch(c, r, (uint32_t)B));
   TRY(prove_from_device_witness(c, z, c->stage_rs.as<Fr>(), (uint32_t)B));
   CU(cudaMemcpyAsync(proofs_out, c->proofs.p, (size_t)B * 256, cudaMemcpyDeviceToHost, c->stream));
   TRY(fetch_publics(c, z->n_public, (uint32_t)B, publics_out));
   CU(cudaStreamSynchronize(c->stream));
-  return 0;
+  int rc = checks_result(c, first_bad);
+  if (rc) memset(proofs_out, 0, (size_t)B * 256);
+  return rc;
 }
 int zkfl_full_prove_stage(zkfl_ctx* c, const zkfl_circuit* k, const zkfl_zkey* z, const uint8_t* inputs, const uint8_t* rs, int B) {
   if (!c || !k || !z || !inputs || B <= 0) return fail(ZKFL_ERR_ARG, "bad argument");
   if (k->n_wires != z->n_vars) return fail(ZKFL_ERR_ARG, "circuit and zkey do not match");
+  TRY(validate_inputs(inputs, (size_t)B * k->n_inputs));
   CU(cudaSetDevice(c->device));
   TRY(stage_rs(c, rs, B));
   TRY(c->stage_in.reserve((size_t)k->n_inputs * B * sizeof(Fr)));
@@ -966,19 +635,23 @@ int zkfl_full_prove_stage(zkfl_ctx* c, const zkfl_circuit* k, const zkfl_zkey* z
   CU(cudaStreamSynchronize(c->stream));
   return 0;
 }
-int zkfl_full_prove_run(zkfl_ctx* c, const zkfl_circuit* k, const zkfl_zkey* z, int B) {
+int zkfl_full_prove_run(zkfl_ctx* c, const zkfl_circuit* k, const zkfl_zkey* z, const zkfl_r1cs* r, int B) {
   if (!c || !k || !z || B <= 0) return fail(ZKFL_ERR_ARG, "bad argument");
+  if (r && r->n_wires != k->n_wires) return fail(ZKFL_ERR_ARG, "r1cs does not match circuit");
   CU(cudaSetDevice(c->device));
   TRY(run_witness(c, k, nullptr, (uint32_t)B));
+  if (r) TRY(check_r1cs_launch(c, r, (uint32_t)B));
   TRY(prove_from_device_witness(c, z, c->stage_rs.as<Fr>(), (uint32_t)B));
-  return 0;  // asynchronous: the caller brackets with its own events / zkfl_full_prove_fetch
+  return 0;  // asynchronous: the caller brackets with its own events / zkfl_full_prove_fetch (which reports the check)
 }
-int zkfl_full_prove_fetch(zkfl_ctx* c, int B, uint8_t* proofs_out) {
+int zkfl_full_prove_fetch(zkfl_ctx* c, int B, uint8_t* proofs_out, uint32_t* first_bad) {
   if (!c || B <= 0) return fail(ZKFL_ERR_ARG, "bad argument");
   CU(cudaSetDevice(c->device));
   if (proofs_out) CU(cudaMemcpyAsync(proofs_out, c->proofs.p, (size_t)B * 256, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
-  return 0;
+  int rc = checks_result(c, first_bad);
+  if (rc && proofs_out) memset(proofs_out, 0, (size_t)B * 256);
+  return rc;
 }
 
 // ---- single large proof split over several GPUs: per-rank MSM partials, then gather + add + blind
@@ -989,17 +662,17 @@ int zkfl_groth16_msm_partials(zkfl_ctx* c, const zkfl_zkey* z, const uint8_t* wt
   size_t cnt = (size_t)z->n_vars * B;
   TRY(c->aos.reserve(cnt * sizeof(Fr))); TRY(c->w.reserve(cnt * sizeof(Fr)));
   CU(cudaMemcpyAsync(c->aos.p, wtns, cnt * sizeof(Fr), cudaMemcpyDefault, c->stream));   // pageable, pinned or device memory
-  ZK_LAUNCH(k_aos_to_soa, cnt, 256, c->stream, c->aos.as<Fr>(), c->w.as<Fr>(), z->n_vars, (uint32_t)B, 0u);
+  TRY(zk_aos_to_soa(c, c->aos.as<Fr>(), c->w.as<Fr>(), z->n_vars, (uint32_t)B, 0u));
+  TRY(check_wtns_launch(c, z->n_vars, (uint32_t)B));
   TRY(prove_from_device_witness(c, z, nullptr, (uint32_t)B, part, nparts, false));
   // layout per proof b: A | B1 | C | H (64 B each, affine canonical) | B2 (128 B)  -> stored as [5 blocks][B]
   TRY(c->part_out.reserve((size_t)B * 384));
   uint8_t* o = c->part_out.as<uint8_t>();
-  ZK_LAUNCH(k_to_affine_canonical<Fq>, (size_t)4 * B, 64, c->stream, c->res_g1.as<G1Xyzz>(), (size_t)4 * B, (G1Affine*)o);
-  ZK_LAUNCH(k_to_affine_canonical<Fq2>, (size_t)B, 64, c->stream, c->res_g2.as<G2Xyzz>(), (size_t)B, (G2Affine*)(o + (size_t)B * 256));
-  CU(cudaGetLastError());
+  TRY(msm_to_affine_canonical<Fq>(c, c->res_g1.as<G1Xyzz>(), (size_t)4 * B, (G1Affine*)o));
+  TRY(msm_to_affine_canonical<Fq2>(c, c->res_g2.as<G2Xyzz>(), (size_t)B, (G2Affine*)(o + (size_t)B * 256)));
   CU(cudaMemcpyAsync(partials_out, o, (size_t)B * 384, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
-  return 0;
+  return checks_result(c, nullptr);
 }
 int zkfl_groth16_finalize(zkfl_ctx* c, const zkfl_zkey* z, const uint8_t* partials, uint32_t nparts, const uint8_t* rs, int B,
                           uint8_t* proofs_out) {
@@ -1012,10 +685,8 @@ int zkfl_groth16_finalize(zkfl_ctx* c, const zkfl_zkey* z, const uint8_t* partia
   TRY(c->res_g2.reserve((size_t)B * sizeof(G2Xyzz)));
   CU(cudaMemcpyAsync(c->part_in.p, partials, per * nparts, cudaMemcpyHostToDevice, c->stream));
   const uint8_t* in = c->part_in.as<uint8_t>();
-  ZK_LAUNCH(k_sum_partials<Fq>, (size_t)4 * B, 64, c->stream, (const G1Affine*)in, nparts, per / sizeof(G1Affine), (size_t)1, (size_t)4 * B,
-            c->res_g1.as<G1Xyzz>());
-  ZK_LAUNCH(k_sum_partials<Fq2>, (size_t)B, 64, c->stream, (const G2Affine*)(in + (size_t)B * 256), nparts, per / sizeof(G2Affine), (size_t)1,
-            (size_t)B, c->res_g2.as<G2Xyzz>());
+  TRY(msm_sum_partials<Fq>(c, (const G1Affine*)in, nparts, per / sizeof(G1Affine), (size_t)4 * B, c->res_g1.as<G1Xyzz>()));
+  TRY(msm_sum_partials<Fq2>(c, (const G2Affine*)(in + (size_t)B * 256), nparts, per / sizeof(G2Affine), (size_t)B, c->res_g2.as<G2Xyzz>()));
   TRY(finalize_from_sums(c, z, c->stage_rs.as<Fr>(), (uint32_t)B));
   CU(cudaMemcpyAsync(proofs_out, c->proofs.p, (size_t)B * 256, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
@@ -1045,10 +716,10 @@ int zkfl_msm_run(zkfl_ctx* c, void* handle, const uint8_t* scalars, size_t n, ui
   uint8_t* o = c->msm_out.as<uint8_t>();
   if (b->group == 1) {
     TRY(msm_run<Fq>(c, b->pts.as<G1Affine>(), s, (G1Xyzz*)o, "msm_acc_g1", "msm_reduce_g1"));
-    ZK_LAUNCH(k_to_affine_canonical<Fq>, 1, 32, c->stream, (const G1Xyzz*)o, (size_t)1, (G1Affine*)(o + sizeof(G2Xyzz)));
+    TRY(msm_to_affine_canonical<Fq>(c, (const G1Xyzz*)o, (size_t)1, (G1Affine*)(o + sizeof(G2Xyzz))));
   } else {
     TRY(msm_run<Fq2>(c, b->pts.as<G2Affine>(), s, (G2Xyzz*)o, "msm_acc_g2", "msm_reduce_g2"));
-    ZK_LAUNCH(k_to_affine_canonical<Fq2>, 1, 32, c->stream, (const G2Xyzz*)o, (size_t)1, (G2Affine*)(o + sizeof(G2Xyzz)));
+    TRY(msm_to_affine_canonical<Fq2>(c, (const G2Xyzz*)o, (size_t)1, (G2Affine*)(o + sizeof(G2Xyzz))));
   }
   if (out) {
     CU(cudaMemcpyAsync(out, o + sizeof(G2Xyzz), b->group == 1 ? 64 : 128, cudaMemcpyDeviceToHost, c->stream));
@@ -1069,26 +740,12 @@ int zkfl_g2_msm(zkfl_ctx* c, const uint8_t* bases, const uint8_t* scalars, size_
 
 // ---- setup support
 }  // extern "C"
-template <class F>
-static int gen_mul(zkfl_ctx* c, const Affine<F>& gen, const uint8_t* scalars, size_t n, uint8_t* out) {
-  if (!c || !scalars || !out || n == 0) return fail(ZKFL_ERR_ARG, "bad argument");
-  for (size_t i = 0; i < n; i++) if (!fr_bytes_lt_mod(scalars + 32 * i)) return fail(ZKFL_ERR_ARG, "scalar not reduced mod r");
-  CU(cudaSetDevice(c->device));
-  DevBuf sc, pts;
-  TRY(sc.reserve(n * sizeof(Fr))); TRY(pts.reserve(n * sizeof(Affine<F>)));
-  CU(cudaMemcpyAsync(sc.p, scalars, n * sizeof(Fr), cudaMemcpyHostToDevice, c->stream));
-  ZK_LAUNCH(k_gen_mul<F>, n, 64, c->stream, gen, sc.as<Fr>(), n, pts.as<Affine<F>>());
-  CU(cudaGetLastError());
-  CU(cudaMemcpyAsync(out, pts.p, n * sizeof(Affine<F>), cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaStreamSynchronize(c->stream));
-  return 0;
-}
 static Fq fq_small(uint32_t v) { Fq r = Fq::zero(); r.v[0] = v; return r.to_mont(); }
 static Fq fq_words(const uint32_t (&w)[8]) { Fq r; for (int i = 0; i < 8; i++) r.v[i] = w[i]; return r.to_mont(); }
 extern "C" {
 int zkfl_g1_mul_generator(zkfl_ctx* c, const uint8_t* scalars, size_t n, uint8_t* out) {
   G1Affine g; g.x = fq_small(1); g.y = fq_small(2);
-  return gen_mul<Fq>(c, g, scalars, n, out);
+  return msm_gen_mul<Fq>(c, g, scalars, n, out);
 }
 int zkfl_g2_mul_generator(zkfl_ctx* c, const uint8_t* scalars, size_t n, uint8_t* out) {
   static const uint32_t X0[8] = {0xd992f6edu, 0x46debd5cu, 0xf75edaddu, 0x674322d4u, 0x5e5c4479u, 0x426a0066u, 0x121f1e76u, 0x1800deefu};
@@ -1096,78 +753,12 @@ int zkfl_g2_mul_generator(zkfl_ctx* c, const uint8_t* scalars, size_t n, uint8_t
   static const uint32_t Y0[8] = {0x66fa7daau, 0x4ce6cc01u, 0x0c43d37bu, 0xe3d1e769u, 0x8dcb408fu, 0x4aab7180u, 0xdb8c6debu, 0x12c85ea5u};
   static const uint32_t Y1[8] = {0xd122975bu, 0x55acdadcu, 0x70b38ef3u, 0xbc4b3133u, 0x690c3395u, 0xec9e99adu, 0x585ff075u, 0x090689d0u};
   G2Affine g; g.x.a = fq_words(X0); g.x.b = fq_words(X1); g.y.a = fq_words(Y0); g.y.b = fq_words(Y1);
-  return gen_mul<Fq2>(c, g, scalars, n, out);
+  return msm_gen_mul<Fq2>(c, g, scalars, n, out);
 }
 
-int zkfl_groth16_verify(const uint8_t* alpha1, const uint8_t* beta2, const uint8_t* gamma2, const uint8_t* delta2, const uint8_t* ic,
-                        const uint8_t* publics, uint32_t n_public, const uint8_t* proof, int* ok) {
-  if (!alpha1 || !beta2 || !gamma2 || !delta2 || !ic || (!publics && n_public) || !proof || !ok) return fail(ZKFL_ERR_ARG, "bad argument");
-  int r = zkv::groth16_verify(alpha1, beta2, gamma2, delta2, ic, publics, n_public, proof);
-  if (r < 0) return fail(ZKFL_ERR_FORMAT, "malformed verification input");
-  *ok = r;
-  return 0;
-}
-int zkfl_groth16_verify_batch(zkfl_ctx* c, const uint8_t* alpha1, const uint8_t* beta2, const uint8_t* gamma2, const uint8_t* delta2,
-                              const uint8_t* ic, uint32_t n_public, const uint8_t* publics, const uint8_t* proofs, int B, int32_t* ok) {
-  if (!c || !alpha1 || !beta2 || !gamma2 || !delta2 || !ic || (!publics && n_public) || !proofs || !ok || B < 0)
-    return fail(ZKFL_ERR_ARG, "bad argument");
-  if (B == 0) return 0;
-  CU(cudaSetDevice(c->device));
-  const zkp::PairingConsts& k = zkv::consts();
-  // verification key: decoded on the host (a handful of points), IC as Montgomery affine on the device
-  uint32_t w[32];
-  memcpy(w, alpha1, 64); const zkp::G1P alpha = zkp::g1_from_canonical(w);
-  memcpy(w, beta2, 128); const zkp::G2P beta = zkp::g2_from_canonical(w);
-  memcpy(w, gamma2, 128); const zkp::G2P gamma = zkp::g2_from_canonical(w);
-  memcpy(w, delta2, 128); const zkp::G2P delta = zkp::g2_from_canonical(w);
-  if (!zkp::g1_on_curve(alpha, k) || !zkp::g2_on_curve(beta, k) || !zkp::g2_on_curve(gamma, k) || !zkp::g2_on_curve(delta, k))
-    return fail(ZKFL_ERR_FORMAT, "verification key point not on the curve");
-  std::vector<G1Affine> ic_m(n_public + 1);
-  for (uint32_t i = 0; i <= n_public; i++) {
-    memcpy(w, ic + 64 * (size_t)i, 64);
-    const zkp::G1P p = zkp::g1_from_canonical(w);
-    if (!zkp::g1_on_curve(p, k)) return fail(ZKFL_ERR_FORMAT, "verification key IC point not on the curve");
-    ic_m[i] = zkp::g1_to_affine(p);
-  }
-  const uint32_t l = n_public, Bu = (uint32_t)B;
-  TRY(c->v_ic.reserve(ic_m.size() * sizeof(G1Affine)));
-  TRY(c->v_pub.reserve((size_t)Bu * (l ? l : 1) * sizeof(Fr)));
-  TRY(c->v_proofs.reserve((size_t)Bu * 256));
-  TRY(c->v_t.reserve((size_t)Bu * (l ? l : 1) * sizeof(G1Xyzz)));
-  TRY(c->v_g1.reserve((size_t)Bu * 3 * sizeof(zkp::G1P)));
-  TRY(c->v_g2.reserve((size_t)Bu * sizeof(zkp::G2P)));
-  TRY(c->v_flags.reserve((size_t)Bu * 4));
-  TRY(c->v_f.reserve(((size_t)3 * Bu + 1) * sizeof(zkp::F12)));
-  TRY(c->v_halves.reserve((size_t)2 * Bu * sizeof(zkp::F12)));
-  TRY(c->v_ok.reserve((size_t)Bu * 4));
-  CU(cudaMemcpyAsync(c->v_ic.p, ic_m.data(), ic_m.size() * sizeof(G1Affine), cudaMemcpyHostToDevice, c->stream));
-  if (l) CU(cudaMemcpyAsync(c->v_pub.p, publics, (size_t)Bu * l * 32, cudaMemcpyHostToDevice, c->stream));
-  CU(cudaMemcpyAsync(c->v_proofs.p, proofs, (size_t)Bu * 256, cudaMemcpyHostToDevice, c->stream));
-  {
-    Stage st(c, "verify_prepare");
-    ZK_LAUNCH(k_vfy_ic_mul, (size_t)Bu * l, 64, c->stream, c->v_ic.as<G1Affine>(), c->v_pub.as<Fr>(), l, Bu, c->v_t.as<G1Xyzz>());
-    ZK_LAUNCH(k_vfy_prepare, Bu, 32, c->stream, k, c->v_ic.as<G1Affine>(), c->v_pub.as<Fr>(), l, Bu, c->v_proofs.as<uint32_t>(),
-              c->v_t.as<G1Xyzz>(), c->v_g1.as<zkp::G1P>(), c->v_g2.as<zkp::G2P>(), c->v_flags.as<uint32_t>());
-  }
-  {
-    Stage st(c, "verify_miller");
-    ZK_LAUNCH(k_vfy_miller, (size_t)3 * Bu + 1, 32, c->stream, k, beta, gamma, delta, alpha, c->v_g1.as<zkp::G1P>(),
-              c->v_g2.as<zkp::G2P>(), Bu, c->v_f.as<zkp::F12>(), c->v_flags.as<uint32_t>(), (int)env_u32("ZKFL_VERIFY_FLAT", 0));
-  }
-  if (!env_u32("ZKFL_VERIFY_FLAT", 0)) {
-    Stage st(c, "verify_final_exp");
-    ZK_LAUNCH(k_vfy_final_tower, Bu, 32, c->stream, k, c->v_f.as<zkp::F12>(), c->v_flags.as<uint32_t>(), Bu, c->v_ok.as<int32_t>());
-  } else {   // cross-check knob: the inversion-free two-power form in the flat basis
-    Stage st(c, "verify_final_exp");
-    ZK_LAUNCH(k_vfy_final, ((size_t)Bu + 31) / 32 * 64, 64, c->stream, k, c->v_f.as<zkp::F12>(), c->v_flags.as<uint32_t>(), Bu,
-              c->v_halves.as<zkp::F12>());
-    ZK_LAUNCH(k_vfy_compare, Bu, 64, c->stream, c->v_halves.as<zkp::F12>(), c->v_flags.as<uint32_t>(), Bu, c->v_ok.as<int32_t>());
-  }
-  CU(cudaGetLastError());
-  CU(cudaMemcpyAsync(ok, c->v_ok.p, (size_t)Bu * 4, cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaStreamSynchronize(c->stream));
-  return 0;
-}
+// `zkey contribute`: every point of a section times one scalar
+int zkfl_g1_scale_points(zkfl_ctx* c, const uint8_t* pts, size_t n, const uint8_t scalar[32], uint8_t* out) { return msm_point_scale<Fq>(c, pts, scalar, n, out); }
+int zkfl_g2_scale_points(zkfl_ctx* c, const uint8_t* pts, size_t n, const uint8_t scalar[32], uint8_t* out) { return msm_point_scale<Fq2>(c, pts, scalar, n, out); }
 // ---- single-proof forms of SURVEY 8b's list (one snarkjs / witness-calculator process each in the reference): B = 1 of the batch
 int zkfl_wtns_calculate(zkfl_ctx* c, const zkfl_circuit* k, const zkfl_r1cs* r, const uint8_t* inputs, uint8_t* wtns_out, uint32_t* first_bad) {
   return zkfl_wtns_calculate_batch(c, k, r, inputs, 1, wtns_out, first_bad);
@@ -1182,10 +773,10 @@ int zkfl_groth16_prove(zkfl_ctx* c, const zkfl_zkey* z, const uint8_t* wtns, con
   uint8_t rs[64];
   return zkfl_groth16_prove_batch(c, z, wtns, join_rs(r, s, rs), 1, proof_out, public_out);
 }
-int zkfl_groth16_full_prove(zkfl_ctx* c, const zkfl_circuit* k, const zkfl_zkey* z, const uint8_t* inputs, const uint8_t* r, const uint8_t* s,
-                            uint8_t proof_out[256], uint8_t* public_out) {
+int zkfl_groth16_full_prove(zkfl_ctx* c, const zkfl_circuit* k, const zkfl_zkey* z, const zkfl_r1cs* r1cs, const uint8_t* inputs,
+                            const uint8_t* r, const uint8_t* s, uint8_t proof_out[256], uint8_t* public_out) {
   uint8_t rs[64];
-  return zkfl_groth16_full_prove_batch(c, k, z, inputs, join_rs(r, s, rs), 1, proof_out, public_out);
+  return zkfl_groth16_full_prove_batch(c, k, z, r1cs, inputs, join_rs(r, s, rs), 1, proof_out, public_out, nullptr);
 }
 // ---- snarkjs JSON shapes (proof.json / public.json) from the binary encodings; host code
 static std::string dec_from_le32(const uint8_t* p) {
@@ -1220,19 +811,6 @@ int zkfl_public_to_json(const uint8_t* publics, uint32_t n_public, char* buf, si
   for (uint32_t i = 0; i < n_public; i++) j += (i ? ", \"" : "\"") + dec_from_le32(publics + 32 * (size_t)i) + "\"";
   j += "]";
   return put_json(j, buf, cap);
-}
-int zkfl_debug_pairing_selftest(void) { return zkv::pairing_selftest(); }
-// dev / test hook: copies a named workspace buffer of the batch verifier to the host (intermediate values of the last call)
-int zkfl_debug_read(zkfl_ctx* c, const char* name, void* out, size_t bytes) {
-  if (!c || !name || !out) return fail(ZKFL_ERR_ARG, "bad argument");
-  const std::string n(name);
-  const DevBuf* b = n == "v_f" ? &c->v_f : n == "v_halves" ? &c->v_halves : n == "v_flags" ? &c->v_flags : n == "v_g1" ? &c->v_g1
-                  : n == "v_g2" ? &c->v_g2 : n == "v_t" ? &c->v_t : nullptr;
-  if (!b || bytes > b->cap) return fail(ZKFL_ERR_ARG, "unknown buffer or size");
-  CU(cudaSetDevice(c->device));
-  CU(cudaMemcpyAsync(out, b->p, bytes, cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaStreamSynchronize(c->stream));
-  return 0;
 }
 // makes `c`'s stream wait for everything queued so far on `other`'s stream (two contexts on one GPU working on
 // half-batches concurrently: join before the end-of-step timestamp)

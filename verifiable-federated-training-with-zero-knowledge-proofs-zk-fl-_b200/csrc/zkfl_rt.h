@@ -13,11 +13,13 @@
 #define ZK_HD __host__ __device__ __forceinline__
 #define ZK_D __device__ __forceinline__
 #define ZK_HD_NOINLINE __host__ __device__ __noinline__
-#define ZK_GLOBAL __global__
+// kernels have internal linkage: kernels.cuh is included by several .cu files and each compiles only the kernels it launches
+#define ZK_GLOBAL static __global__
 #define ZK_UNROLL _Pragma("unroll")
 #define ZK_NOUNROLL _Pragma("unroll 1")
 #define ZK_TID ((size_t)blockIdx.x * blockDim.x + threadIdx.x)
 #define ZK_ATOMIC_ADD(p, v) atomicAdd((p), (v))
+#define ZK_ATOMIC_OR(p, v) atomicOr((p), (v))
 #define ZK_LDG(p) __ldg(p)
 
 namespace zkrt {
@@ -54,6 +56,7 @@ struct zk_emul_idx { size_t tid; };
 extern thread_local zk_emul_idx zk_emul_cur;
 #define ZK_TID (zk_emul_cur.tid)
 #define ZK_ATOMIC_ADD(p, v) __atomic_fetch_add((p), (v), __ATOMIC_RELAXED)
+#define ZK_ATOMIC_OR(p, v) __atomic_fetch_or((p), (v), __ATOMIC_RELAXED)
 #define ZK_LDG(p) (*(p))
 
 typedef int cudaError_t;

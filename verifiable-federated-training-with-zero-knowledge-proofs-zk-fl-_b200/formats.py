@@ -100,6 +100,15 @@ def proof_bytes_to_json(p: bytes) -> dict:
 
 
 def proof_json_to_bytes(j: dict) -> bytes:
+    """proof.json -> 256 bytes.  snarkjs reads the points as projective triples with z = 1 (`["1","0"]` in G2) and only proves
+    / verifies `groth16` over `bn128`: anything else is malformed here (ValueError), not silently reinterpreted."""
+    if j.get("protocol", "groth16") != "groth16" or j.get("curve", "bn128") not in ("bn128", "bn254"):
+        raise ValueError("proof.json: not a groth16 proof over bn128")
+    for key in ("pi_a", "pi_c"):
+        if len(j[key]) != 3 or str(j[key][2]) != "1":
+            raise ValueError(f"proof.json: {key} is not an affine point (z != 1)")
+    if len(j["pi_b"]) != 3 or [str(v) for v in j["pi_b"][2]] != ["1", "0"]:
+        raise ValueError("proof.json: pi_b is not an affine point (z != 1)")
     vals = [j["pi_a"][0], j["pi_a"][1], j["pi_b"][0][0], j["pi_b"][0][1], j["pi_b"][1][0], j["pi_b"][1][1],
             j["pi_c"][0], j["pi_c"][1]]
     return b"".join(int(x).to_bytes(32, "little") for x in vals)

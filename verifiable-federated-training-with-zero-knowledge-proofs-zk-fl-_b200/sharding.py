@@ -61,10 +61,31 @@ def prove_independent(prover, circuit, zkey, inputs: list, rs: list | None = Non
     return out_p, out_q
 
 
+def _shared_rs(rs, B: int):
+    """the blinding scalars must be the SAME on every rank (all ranks assemble the same proof): rank 0's choice -- the caller's
+    or fresh CSPRNG draws -- is broadcast."""
+    import secrets
+    from .formats import FR
+    rank = dist.get_rank()
+    if rank == 0:
+        vals = rs if rs is not None else [(secrets.randbelow(FR), secrets.randbelow(FR)) for _ in range(B)]
+        raw = b"".join(int(r).to_bytes(32, "little") + int(s).to_bytes(32, "little") for r, s in vals)
+        t = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(_device())
+    else:
+        t = torch.zeros(64 * B, dtype=torch.uint8, device=_device())
+    dist.broadcast(t, src=0)
+    raw = bytes(t.cpu().numpy().tobytes())
+    return [(int.from_bytes(raw[64 * b:64 * b + 32], "little"), int.from_bytes(raw[64 * b + 32:64 * b + 64], "little")) for b in range(B)]
+
+
 def prove_split(prover, zkey, wtns: list[bytes], rs: list | None):
-    """One (or a few) large proofs with every MSM split by point range over the ranks. Every rank returns the proofs."""
+    """One (or a few) large proofs with every MSM split by point range over the ranks. Every rank returns the SAME proofs
+    (rs=None: rank 0 draws r, s and broadcasts them)."""
     world, rank = dist.get_world_size(), dist.get_rank()
     B = len(wtns) if isinstance(wtns, (list, tuple)) else (wtns.numel() * wtns.element_size() if hasattr(wtns, "data_ptr") else len(wtns)) // (32 * zkey.n_vars)
+    if hasattr(wtns, "is_cuda") and wtns.is_cuda:
+        torch.cuda.current_stream(wtns.device).synchronize()   # the library copies on its own stream: the producer must be done
+    rs = _shared_rs(rs, B)
     part = prover.msm_partials(zkey, wtns, rank, world)
     mine = torch.frombuffer(bytearray(part), dtype=torch.uint8).to(_device())
     allp = [torch.zeros_like(mine) for _ in range(world)]

@@ -20,15 +20,17 @@ from .circuits.poseidon_params import FR
 LEARNING_RATE = 0.01  # full_system_simulation.mjs:52
 
 
-def _setup(prover, name, cache):
+def _setup(prover, name, cache, setup_seed: bytes | None = None):
+    """per-circuit setup; the toxic waste is OS randomness unless a test passes `setup_seed` (reproducible, forgeable)"""
     if name not in cache:
         cc = build_circuit(name)
-        zk = prover.new_zkey(cc, b"zkfl-round-" + name.encode())
+        zk = prover.new_zkey(cc, None if setup_seed is None else setup_seed + name.encode())
         cache[name] = (prover.load_circuit(cc), prover.load_zkey(zk), formats.export_verification_key(zk))
     return cache[name]
 
 
-def run_round(prover, n_clients: int = 3, seed: int = 12345, weights=None, verify: bool = True, cache: dict | None = None) -> dict:
+def run_round(prover, n_clients: int = 3, seed: int = 12345, weights=None, verify: bool = True, cache: dict | None = None,
+              setup_seed: bytes | None = None) -> dict:
     assert n_clients % 3 == 0, "clients come in federations of three (NUM_PEERS = 2)"
     cache = {} if cache is None else cache
     t0 = time.perf_counter()
@@ -38,10 +40,9 @@ def run_round(prover, n_clients: int = 3, seed: int = 12345, weights=None, verif
     report = {"clients": n_clients, "verified": {"balance": 0, "training": 0, "secagg": 0}}
 
     def prove_phase(name, ins):
-        circ, zkey, vk = _setup(prover, name, cache)
+        circ, zkey, vk = _setup(prover, name, cache, setup_seed)
         t = time.perf_counter()
-        prover.calculate_witness(circ, ins)                                    # circom aborts on a failed ===
-        proofs, pubs = prover.full_prove(circ, zkey, ins)                      # r, s from the OS like snarkjs
+        proofs, pubs = prover.full_prove(circ, zkey, ins)                      # constraint check inside the pass; r, s from the OS like snarkjs
         timing[name + "_s"] = time.perf_counter() - t
         return vk, [formats.proof_bytes_to_json(p) for p in proofs], [formats.publics_bytes_to_json(q) for q in pubs]
 

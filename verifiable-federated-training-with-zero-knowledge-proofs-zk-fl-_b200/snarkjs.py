@@ -9,7 +9,9 @@ Node.js is not available on this image, hence the host side is Python (INTEGRATI
 Differences a caller can observe:
   * `<name>.wasm` holds our compiled witness program (magic `zkwp`), produced by `circom.compile`;
   * proving runs on the GPU (no CPU fallback); `fullProve` keeps the witness in HBM between the two steps;
-  * `zKey.newZKey` derives the key from a seed (the `.ptau` bytes + entropy) instead of a ceremony transcript;
+  * `zKey.newZKey` derives the key from OS randomness (mixed with the `.ptau` bytes and the caller's entropy) instead of a
+    ceremony transcript, and `zKey.contribute` re-randomises delta like snarkjs; a reproducible key needs an explicit
+    `deterministic_seed=` (tests only: whoever knows the seed can forge proofs);
   * batch variants (`fullProveBatch`) prove many clients of one circuit in lock-step.
 """
 from __future__ import annotations
@@ -23,12 +25,14 @@ from . import _lib, formats
 from .api import Circuit, Prover, Zkey
 from .circuits import CIRCUIT_NAMES, build_circuit
 
-_state = {"prover": None, "circuits": {}, "zkeys": {}}
+# "lib_path": None = the package's libzkfl.so.  Only the CPU test-suite sets it (to the host-emulation test double), in code;
+# no environment variable can redirect the library.
+_state = {"prover": None, "circuits": {}, "zkeys": {}, "lib_path": None}
 
 
 def _prover() -> Prover:
     if _state["prover"] is None:
-        _state["prover"] = Prover(int(os.environ.get("ZKFL_DEVICE", os.environ.get("LOCAL_RANK", "0"))))
+        _state["prover"] = Prover(int(os.environ.get("ZKFL_DEVICE", os.environ.get("LOCAL_RANK", "0"))), lib_path=_state["lib_path"])
     return _state["prover"]
 
 
@@ -119,18 +123,24 @@ class wtns:
 
 class zKey:
     @staticmethod
-    def newZKey(r1cs_path: str, ptau_path: str | None, zkey_out: str, entropy: str = "") -> None:
-        """`snarkjs groth16 setup r1cs ptau zkey` (tests/full_system_simulation.mjs:714-717)."""
-        seed = hashlib.sha256(b"zkfl-setup" + entropy.encode()).digest()
-        if ptau_path and os.path.exists(ptau_path):
-            seed = hashlib.sha256(seed + open(ptau_path, "rb").read()).digest()
+    def newZKey(r1cs_path: str, ptau_path: str | None, zkey_out: str, entropy: str = "", deterministic_seed: bytes | None = None) -> None:
+        """`snarkjs groth16 setup r1cs ptau zkey` (tests/full_system_simulation.mjs:714-717).  The toxic waste comes from the
+        OS CSPRNG (mixed with `entropy` and the ptau bytes) and is discarded; `deterministic_seed` (tests only) replaces it."""
+        if deterministic_seed is not None:
+            seed = hashlib.sha256(b"zkfl-setup-test" + deterministic_seed).digest()
+        else:
+            seed = hashlib.sha512(b"zkfl-setup" + os.urandom(64) + entropy.encode()).digest()
+            if ptau_path and os.path.exists(ptau_path):
+                seed = hashlib.sha512(seed + open(ptau_path, "rb").read()).digest()
         data = _prover().new_zkey(open(r1cs_path, "rb").read(), seed)
         open(zkey_out, "wb").write(data)
 
     @staticmethod
     def contribute(zkey_in: str, zkey_out: str, name: str = "", entropy: str = "") -> None:
-        """`snarkjs zkey contribute` (:726-731): our keys are final after newZKey; the contribution is a copy."""
-        open(zkey_out, "wb").write(open(zkey_in, "rb").read())
+        """`snarkjs zkey contribute <in> <out> --name= -e=` (:726-731): delta is re-randomised with a fresh secret (CSPRNG +
+        `entropy`), the C and H sections are rescaled, and a contribution record is appended (zkey_setup.contribute)."""
+        data = _prover().contribute_zkey(open(zkey_in, "rb").read(), name, entropy.encode())
+        open(zkey_out, "wb").write(data)
 
     @staticmethod
     def exportVerificationKey(zkey_path: str) -> dict:
@@ -149,9 +159,9 @@ class groth16:
         """Many client instances of one circuit in one GPU pass (independent proofs, shared bases)."""
         circ = _circuit(wasm)
         z, _ = _zkey(zkey)
-        p = _prover()
-        p.calculate_witness(circ, inputs)           # constraint check (circom aborts on a failed ===)
-        proofs, pubs = p.full_prove(circ, z, inputs, rs)
+        # one GPU pass: the constraint check (circom aborts on a failed ===) runs on the HBM-resident witness inside it and
+        # raises AssertFailed; a circuit loaded without its .r1cs cannot be checked and is refused, not silently proved
+        proofs, pubs = _prover().full_prove(circ, z, inputs, rs, check=True)
         return [_result(a, b) for a, b in zip(proofs, pubs)]
 
     @staticmethod
@@ -199,7 +209,7 @@ class groth16:
         """`snarkjs groth16 verify vkey public proof` (tests/full_system_simulation.mjs:865-868)."""
         if isinstance(vkey, str):
             vkey = json.load(open(vkey))
-        lib = _lib.load()
+        lib = _lib.load(_state["lib_path"])
         vk = formats.vkey_json_to_bytes(vkey)
         if len(publicSignals) != vk["n_public"]:
             return False

@@ -2,7 +2,10 @@
 (tests/full_system_simulation.mjs:714-731).
 
 No `.ptau` exists in the reference tree and none can be fetched, so the structured reference string
-is derived from explicit toxic waste (tau, alpha, beta, delta; gamma = 1 as in snarkjs).  The field
+is derived from explicit toxic waste (tau, alpha, beta, delta; gamma = 1 as in snarkjs).  SOUNDNESS: whoever knows
+the toxic waste can forge proofs, so outside tests the seed comes from the OS CSPRNG (`Prover.new_zkey(seed=None)`,
+`snarkjs.zKey.newZKey`) and is never stored; `contribute` re-randomises delta with fresh secret entropy the way
+`snarkjs zkey contribute` does, so the key stays sound as long as ONE contributor (or the initial setup) was honest.  The field
 arithmetic that builds the key scalars runs on the host (Python ints, one-off per circuit); every
 scalar multiplication k*G1 / k*G2 runs on the GPU (`zkfl_g1_mul_generator`).  Output: a `.zkey` with
 the exact snarkjs section layout, including the nPublic+1 extra A rows and the
@@ -11,6 +14,7 @@ odd-coset Lagrange H points the snarkjs prover expects.
 from __future__ import annotations
 
 import hashlib
+import os
 import struct
 
 from .formats import FQ, FR, read_container, write_container
@@ -160,4 +164,33 @@ def new_zkey(prover, r1cs, seed: bytes) -> bytes:
     # snarkjs writes A and B interleaved in constraint order; the prover does not depend on the order
     sections = [(1, struct.pack("<I", 1)), (2, hdr), (3, ic), (4, struct.pack("<I", n_coef) + coeffs),
                 (5, pa), (6, pb1), (7, pb2), (8, pc), (9, ph), (10, bytes(64) + struct.pack("<I", 0))]
+    return write_container(b"zkey", 1, sections)
+
+
+def contribute(prover, zkey: bytes, name: str = "", entropy: bytes = b"") -> bytes:
+    """`snarkjs zkey contribute <in> <out> --name= -e=` (tests/full_system_simulation.mjs:726-731): a fresh secret d
+    (OS CSPRNG mixed with the caller's entropy) rescales delta1, delta2 by d and the C and H sections by 1/d, so that nobody
+    who does not know d knows the new delta; a contribution record is appended to section 10 (deltaAfter, d*G1 data, a hash
+    chaining the previous transcript hash, the name).  The record has snarkjs's field layout but is NOT a verifiable ceremony
+    transcript (`zkey verify` needs the ptau the reference tree does not have); the scalar multiplications run on the GPU."""
+    s = read_container(zkey, b"zkey")
+    h = bytearray(s[2])
+    d = 0
+    while d < 2:
+        d = int.from_bytes(hashlib.sha512(os.urandom(64) + entropy + name.encode()).digest(), "little") % FR
+    dinv = pow(d, -1, FR)
+    o_d1, o_d2 = 84 + 64 + 64 + 128 + 128, 84 + 64 + 64 + 128 + 128 + 64
+    h[o_d1:o_d1 + 64] = prover.scale_points(bytes(h[o_d1:o_d1 + 64]), d, 1)
+    h[o_d2:o_d2 + 128] = prover.scale_points(bytes(h[o_d2:o_d2 + 128]), d, 2)
+    pc = prover.scale_points(s[8], dinv, 1) if len(s[8]) else b""
+    ph = prover.scale_points(s[9], dinv, 1)
+    prev = s.get(10, bytes(64) + struct.pack("<I", 0))
+    cs_hash, n_contrib = prev[:64], struct.unpack_from("<I", prev, 64)[0]
+    g1 = prover.g1_mul_generator([d])
+    transcript = hashlib.sha512(cs_hash + bytes(h[o_d1:o_d1 + 64]) + name.encode()).digest()
+    nm = name.encode()
+    params = bytes([1, len(nm)]) + nm if nm else b""        # snarkjs: type 1 = name
+    record = bytes(h[o_d1:o_d1 + 64]) + g1 + bytes(64) + bytes(128) + transcript + struct.pack("<I", len(params)) + params
+    sec10 = cs_hash + struct.pack("<I", n_contrib + 1) + prev[68:] + record
+    sections = [(sid, {2: bytes(h), 8: pc, 9: ph, 10: sec10}.get(sid, s[sid])) for sid in sorted(set(s) | {10})]
     return write_container(b"zkey", 1, sections)
