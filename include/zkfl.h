@@ -107,7 +107,10 @@ int zkfl_full_prove_fetch(zkfl_ctx* ctx, int B, uint8_t* proofs_out, uint32_t* f
  *      multi-scalar multiplications over ITS point range [part*m/nparts, (part+1)*m/nparts) and returns the partial
  *      sums; the ranks all-gather the partials (NCCL / gloo: 384 B per proof per rank) and any rank finishes with
  *      zkfl_groth16_finalize, which adds the partials (the group law is no NCCL reduction op) and applies the blinding.
- *      partials layout per call: [A(64) x B | B1 x B | C x B | H x B | B2(128) x B], affine canonical. --------------- */
+ *      partials layout per call: [A(64) x B | B1 x B | C x B | H x B | B2(128) x B], affine canonical.
+ *      wtns == NULL: the witness is the one the last witness calculation on this context left in HBM (zkfl_wtns_calculate_batch
+ *      with wtns_out == NULL keeps it there) -- nothing is uploaded.  partials_out / partials may be HOST or DEVICE buffers: with
+ *      device buffers the all-gather runs device-to-device (NCCL over NVLink) and nothing is staged through the host. */
 int zkfl_groth16_msm_partials(zkfl_ctx* ctx, const zkfl_zkey* z, const uint8_t* wtns, int B, uint32_t part, uint32_t nparts,
                               uint8_t* partials_out /* B x 384 */);
 int zkfl_groth16_finalize(zkfl_ctx* ctx, const zkfl_zkey* z, const uint8_t* partials /* nparts x B x 384 */, uint32_t nparts,
@@ -164,10 +167,29 @@ int zkfl_msm_run(zkfl_ctx* ctx, void* handle, const uint8_t* scalars /* host, or
 int zkfl_g1_mul_generator(zkfl_ctx* ctx, const uint8_t* scalars, size_t n, uint8_t* out /* n x 64 */);
 int zkfl_g2_mul_generator(zkfl_ctx* ctx, const uint8_t* scalars, size_t n, uint8_t* out /* n x 128 */);
 
+/* `snarkjs groth16 setup <r1cs> <ptau> <zkey>` (tests/full_system_simulation.mjs:714-717) on the GPU: Lagrange basis at tau, column
+ * sums of A / B / C, key scalars and all scalar multiplications run on the device; the result is the complete `.zkey` (snarkjs
+ * section layout).  The R1CS comes as coordinate lists per matrix k = 0 (A), 1 (B), 2 (C): rows[k][i], wires[k][i] and
+ * cidx[k][i] (index into coef_table: n_coef distinct coefficient values, 32 B canonical) for i < nnz[k].
+ * toxic = tau | alpha | beta | delta (4 x 32 B canonical, non-zero): WHOEVER KNOWS THEM CAN FORGE PROOFS -- callers draw them from a
+ * CSPRNG and forget them (zkfl_b200.zkey_setup), fixed values are for tests.  Call with zkey_out == NULL to learn *zkey_len. */
+int zkfl_groth16_setup(zkfl_ctx* ctx, uint32_t n_wires, uint32_t n_public, uint32_t n_constraints, const uint32_t* const rows[3],
+                       const uint32_t* const wires[3], const uint32_t* const cidx[3], const size_t nnz[3], const uint8_t* coef_table,
+                       uint32_t n_coef, const uint8_t toxic[128], uint8_t* zkey_out, size_t cap, size_t* zkey_len);
 /* `snarkjs zkey contribute <in> <out> --name= -e=` (tests/full_system_simulation.mjs:726-731) multiplies delta by a fresh
  * secret d and the C / H sections by 1/d: out[i] = scalar * pts[i], points affine Montgomery (zkey layout), scalar canonical */
 int zkfl_g1_scale_points(zkfl_ctx* ctx, const uint8_t* pts, size_t n, const uint8_t scalar[32], uint8_t* out /* n x 64 */);
 int zkfl_g2_scale_points(zkfl_ctx* ctx, const uint8_t* pts, size_t n, const uint8_t scalar[32], uint8_t* out /* n x 128 */);
+
+/* ---- Server.aggregateUpdates (tests/full_system_simulation.mjs:1137-1199) on the device: per model coordinate the field sum of
+ *      the accepted clients' masked updates (the pairwise masks cancel), the signed decode (sums above r/2 are negative integers,
+ *      converted like JavaScript's Number(BigInt)), the mean over the accepted clients and the SGD step
+ *      model_out[j] = model_in[j] - learning_rate * mean[j] (IEEE doubles, product and difference rounded separately as in JS).
+ *      masked: n_clients x dim x 32 B canonical (host or device); accept: n_clients bytes (NULL = all); no accepted client ->
+ *      ZKFL_ERR_ARG ("No verified updates to aggregate!": the reference returns null). ------------------------------------ */
+int zkfl_aggregate_updates(zkfl_ctx* ctx, const uint8_t* masked, const uint8_t* accept, uint32_t n_clients, uint32_t dim,
+                           double learning_rate, const double* model_in, uint8_t* agg_field_out /* dim x 32, may be NULL */,
+                           double* agg_mean_out /* dim */, double* model_out /* dim */, uint32_t* n_accepted /* may be NULL */);
 
 /* ---- measurement --------------------------------------------------------------------------- */
 /* number of CUDA kernels this library has launched in this process */

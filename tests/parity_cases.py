@@ -75,6 +75,23 @@ def case_g2_msm(P, n, seed=3):
     assert P.g2_msm(bases, sc) == ol.g2_msm(bases, sc)
 
 
+def case_msm_resident(P, n, group=1, seed=6):
+    """resident base set (zkfl_msm_bases_load: window-shifted table, one bucket set) against the oracle and the one-shot call"""
+    import ctypes
+    rnd = random.Random(seed)
+    ks = ol.fes([rnd.randrange(bn.R) for _ in range(n)])
+    bases = ol.g1_mul_gen(ks) if group == 1 else ol.g2_mul_gen(ks)
+    sc = ol.fes(edge_scalars(rnd, n))
+    h = P.msm_load_bases(bases, group)
+    out = ctypes.create_string_buffer(64 * group)
+    P.msm_run(h, sc, n, out)
+    ref = ol.g1_msm(bases, sc) if group == 1 else ol.g2_msm(bases, sc)
+    assert out.raw == ref
+    P.msm_run(h, sc[:32 * (n - 1)], n - 1, out)          # a prefix of the base set: falls back to the raw points
+    assert out.raw == (ol.g1_msm(bases[:64 * (n - 1)], sc[:32 * (n - 1)]) if group == 1 else ol.g2_msm(bases[:128 * (n - 1)], sc[:32 * (n - 1)]))
+    P.msm_free_bases(h)
+
+
 def case_linearity(P, n=64, seed=4):
     """size-independent property: MSM(a) + MSM(b) == MSM(a + b) (checked through the oracle's group law)."""
     rnd = random.Random(seed)

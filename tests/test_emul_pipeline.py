@@ -44,6 +44,12 @@ def test_tiny_circuit_witness_prove_verify(emul_prover):
     pc.case_prove(emul_prover, cc, pc.tiny_inputs(), [(11, 22), (33, 44), (0, 0)])
 
 
+def test_resident_msm_with_window_table(emul_prover):
+    pc.case_msm_resident(emul_prover, 1030, 1)
+    pc.case_msm_resident(emul_prover, 1024, 2)
+    pc.case_msm_resident(emul_prover, 40, 1)        # below the table threshold
+
+
 def test_batch_affine_accumulation(emul_prover, monkeypatch):
     """The batch-affine bucket accumulation (large-batch path) forced on small cases: degenerate buckets (doubling,
     P + (-P), infinity bases, runs cut by chunk borders) and a whole proof batch, bit-exact against the oracle."""
@@ -360,3 +366,57 @@ def test_proof_json_decoding_is_strict():
                 dict(pj, pi_b=pj["pi_b"][:2] + [["0", "1"]]), dict(pj, pi_c=pj["pi_c"][:2])):
         with pytest.raises((ValueError, IndexError)):
             formats.proof_json_to_bytes(bad)
+
+
+def _reference_aggregate(masked, accept, model, lr):
+    """restatement of Server.aggregateUpdates (tests/full_system_simulation.mjs:1137-1199) with JavaScript's semantics: BigInt sums
+    mod p, `> p / 2n` means negative, Number(BigInt) (round to nearest even), then IEEE-double mean and model update"""
+    import bn254_ref as bn
+    ids = [i for i, a in enumerate(accept) if a]
+    if not ids:
+        return None
+    dim = len(model)
+    agg = [sum(masked[i][j] for i in ids) % bn.R for j in range(dim)]
+    g = [float(a - bn.R) if a > bn.R // 2 else float(a) for a in agg]
+    g = [x / len(ids) for x in g]
+    return {"aggregated_field": agg, "aggregated_gradient": g, "new_model": [m - lr * x for m, x in zip(model, g)], "num_clients": len(ids)}
+
+
+def case_aggregate(P):
+    import random
+    import bn254_ref as bn
+    rnd = random.Random(3)
+    for n, dim in ((3, 4), (200, 4), (1023, 7)):
+        grads = [[rnd.randrange(-10 ** 6, 10 ** 6) for _ in range(dim)] for _ in range(n)]
+        masks = [[rnd.randrange(bn.R) for _ in range(dim)] for _ in range(n)]
+        masked = [[(grads[i][j] + masks[i][j] - masks[(i + 1) % n][j]) % bn.R for j in range(dim)] for i in range(n)]
+        model = [rnd.uniform(-1, 1) for _ in range(dim)]
+        got = P.aggregate_updates(masked, [True] * n, model, 0.01)
+        assert got == _reference_aggregate(masked, [True] * n, model, 0.01)
+        assert got["aggregated_gradient"] == [sum(g[j] for g in grads) / n for j in range(dim)]      # the masks cancel
+        accept = [rnd.random() < 0.7 for _ in range(n)]      # masks no longer cancel: 254-bit magnitudes through the double conversion
+        assert P.aggregate_updates(masked, accept, model, 0.01) == _reference_aggregate(masked, accept, model, 0.01)
+    assert P.aggregate_updates([[1, 2]], [False], [0.0, 0.0], 0.01) is None
+    with pytest.raises(_lib.ZkflError, match="not reduced"):
+        P.aggregate_updates([[bn.R, 0]], [True], [0.0, 0.0], 0.01)
+
+
+def test_masked_aggregation_and_model_update(emul_prover):
+    """SURVEY 8f item 4 / VERDICT r1 item 7: aggregateUpdates as device kernels against the restated JavaScript"""
+    case_aggregate(emul_prover)
+
+
+def test_gpu_commitment_inputs_equal_the_host_generators(emul_prover):
+    """clients whose commitments come from the batched commitment program (commitments.hydrate: trees, roots, derived key
+    material, masks) produce exactly the inputs of the per-client host generators, for all three circuits"""
+    from zkfl_b200 import commitments
+    ref = I.simulation_clients(6)
+    lcg = I.JsLcg(12345)
+    mine = [I.SimClient(i, lcg, hashed=False) for i in range(1, 7)]
+    commitments.hydrate(emul_prover, mine, [3, -2, 0, 7])
+    for a, b in zip(ref, mine):
+        assert a.balance_input() == b.balance_input()
+        assert a.training_input([3, -2, 0, 7]) == b.training_input([3, -2, 0, 7])
+        base = 3 * ((a.id - 1) // 3)
+        peers = [base + k for k in (1, 2, 3) if base + k != a.id]
+        assert a.secagg_input(peers) == b.secagg_input(peers)

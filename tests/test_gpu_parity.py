@@ -45,6 +45,28 @@ def test_g1_msm_2pow20_against_oracle(gpu_prover):
     assert gpu_prover.g1_msm(bases, sc) == ol.g1_msm(bases, sc)
 
 
+def test_resident_msm_with_window_table(gpu_prover):
+    """zkfl_msm_bases_load builds the window-shifted table (one bucket set per MSM): same result as the oracle, G1 and G2"""
+    for n in (1024, 5000, 1 << 16):
+        pc.case_msm_resident(gpu_prover, n, 1)
+    pc.case_msm_resident(gpu_prover, 3000, 2)
+    pc.case_msm_resident(gpu_prover, 100, 1)
+
+
+def test_g1_msm_2pow20_resident_table_against_oracle(gpu_prover):
+    """BASELINE.json's MSM size through the resident path the bench measures (table, c = 17, one set of 2^16 buckets)"""
+    import ctypes
+    n = 1 << 20
+    rnd = random.Random(21)
+    bases = gpu_prover.g1_mul_generator(b"".join(rnd.randrange(bn.R).to_bytes(32, "little") for _ in range(n)))
+    sc = b"".join(rnd.randrange(bn.R).to_bytes(32, "little") for _ in range(n))
+    h = gpu_prover.msm_load_bases(bases, 1)
+    out = ctypes.create_string_buffer(64)
+    gpu_prover.msm_run(h, sc, n, out)
+    gpu_prover.msm_free_bases(h)
+    assert out.raw == ol.g1_msm(bases, sc)
+
+
 def test_g2_msm(gpu_prover):
     for n in (1, 40, 4096):
         pc.case_g2_msm(gpu_prover, n)
@@ -269,6 +291,14 @@ def test_full_round_like_the_reference_simulation(gpu_prover):
     rep = simulation.run_round(gpu_prover, 24, cache=cache)
     assert rep["verified"] == {"balance": 24, "training": 24, "secagg": 24}
     assert rep["aggregated_gradient"] == rep["expected_gradient"]
+    host = simulation.run_round(gpu_prover, 24, cache=cache, gpu_inputs=False)      # per-client host Poseidon: same round
+    assert host["verified"] == rep["verified"] and host["aggregated_gradient"] == rep["aggregated_gradient"]
+    assert host["new_model"] == rep["new_model"]
+
+
+def test_masked_aggregation_and_model_update_on_gpu(gpu_prover):
+    from test_emul_pipeline import case_aggregate
+    case_aggregate(gpu_prover)
 
 
 def _host_ram_gb():

@@ -41,6 +41,16 @@ def _worker(rank, world, port, q):
             assert proofs is None
         split = sharding.prove_split(P, Z, ws[:2], rs[:2])
         assert split == [r[0] for r in ref[:2]], "split-MSM proof differs from the oracle"
+        # fullProve split: witness evaluated and kept resident on every rank, random blinding drawn on rank 0 and broadcast
+        full = sharding.full_prove_split(P, circ, Z, ins[:2], rs[:2])
+        assert full == split
+        rnd = sharding.full_prove_split(P, circ, Z, ins[:1], None)
+        import torch
+        t = torch.frombuffer(bytearray(rnd[0]), dtype=torch.uint8)
+        both = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(both, t)
+        assert all(bytes(x.numpy().tobytes()) == rnd[0] for x in both), "ranks returned different proofs"
+        assert rnd[0] != ref[0][0]
         q.put((rank, "ok"))
     except Exception as e:  # surface the failure in the parent
         import traceback

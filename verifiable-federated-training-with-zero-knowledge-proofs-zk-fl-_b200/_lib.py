@@ -21,7 +21,7 @@ SYMBOLS = [
     "zkfl_msm_bases_free", "zkfl_msm_run", "zkfl_g1_mul_generator", "zkfl_g2_mul_generator",
     "zkfl_launch_count", "zkfl_prof_enable", "zkfl_prof_read", "zkfl_bench_modmul", "zkfl_bench_imad", "zkfl_bench_widemac",
     "zkfl_timer_begin", "zkfl_timer_end", "zkfl_groth16_verify", "zkfl_groth16_verify_batch", "zkfl_debug_read", "zkfl_debug_pairing_selftest", "zkfl_wtns_calculate", "zkfl_groth16_prove", "zkfl_groth16_full_prove",
-    "zkfl_proof_to_json", "zkfl_public_to_json", "zkfl_g1_scale_points", "zkfl_g2_scale_points", "zkfl_groth16_msm_partials", "zkfl_groth16_finalize", "zkfl_ctx_wait_other",
+    "zkfl_proof_to_json", "zkfl_public_to_json", "zkfl_g1_scale_points", "zkfl_g2_scale_points", "zkfl_groth16_setup", "zkfl_aggregate_updates", "zkfl_groth16_msm_partials", "zkfl_groth16_finalize", "zkfl_ctx_wait_other",
 ]
 
 _libs = {}
@@ -88,6 +88,8 @@ def load(path: str | None = None):
         "zkfl_groth16_msm_partials": (i, [vp, vp, vp, i, ctypes.c_uint32, ctypes.c_uint32, vp]),
         "zkfl_groth16_finalize": (i, [vp, vp, vp, ctypes.c_uint32, vp, i, vp]),
         "zkfl_ctx_wait_other": (i, [vp, vp]),
+        "zkfl_aggregate_updates": (i, [vp, vp, vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_double, vp, vp, vp, vp, vp]),
+        "zkfl_groth16_setup": (i, [vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, vp, vp, vp, vp, vp, ctypes.c_uint32, vp, vp, sz, vp]),
         "zkfl_g1_scale_points": (i, [vp, vp, sz, vp, vp]), "zkfl_g2_scale_points": (i, [vp, vp, sz, vp, vp]),
         "zkfl_timer_begin": (i, [vp]), "zkfl_timer_end": (i, [vp, ctypes.POINTER(ctypes.c_float)]),
     }

@@ -218,16 +218,34 @@ class Prover:
         praw, qraw = proofs.raw, pubs.raw
         return ([praw[256 * b:256 * (b + 1)] for b in range(B)], [qraw[psz * b:psz * (b + 1)] for b in range(B)])
 
-    def msm_partials(self, zkey: Zkey, wtns, part: int, nparts: int) -> bytes:
-        """the five MSM sums over this rank's point range (B x 384 bytes), see zkfl_groth16_msm_partials"""
-        buf, B = self._wtns_buffer(zkey, wtns)
-        out = ctypes.create_string_buffer(384 * B)
-        self._check(self.lib.zkfl_groth16_msm_partials(self.ctx, zkey.handle, _lib.as_ptr(buf), B, part, nparts, out))
-        return out.raw
+    def msm_partials(self, zkey: Zkey, wtns, part: int, nparts: int, out=None, B: int | None = None):
+        """the five MSM sums over this rank's point range (B x 384 bytes), see zkfl_groth16_msm_partials.
+        wtns=None: the witness the last calculate_witness(..., keep_resident) left in HBM (pass B).  out: a torch uint8 tensor
+        (host or CUDA) that receives the partials in place -- with a CUDA tensor nothing touches the host; default: bytes."""
+        if wtns is None:
+            buf = None
+            assert B is not None
+        else:
+            buf, B = self._wtns_buffer(zkey, wtns)
+        dst = out if out is not None else ctypes.create_string_buffer(384 * B)
+        self._check(self.lib.zkfl_groth16_msm_partials(self.ctx, zkey.handle, _lib.as_ptr(buf), B, part, nparts,
+                                                      _lib.as_ptr(dst) if out is not None else dst))
+        return out if out is not None else dst.raw
 
-    def finalize(self, zkey: Zkey, partials: list[bytes], B: int, rs=None) -> list[bytes]:
+    def witness_resident(self, circuit: Circuit, inputs, check: bool = True) -> int:
+        """runs the witness program and LEAVES the witness in HBM (nothing is copied to the host); returns B"""
+        packed = inputs if isinstance(inputs, (bytes, bytearray)) else circuit.pack_inputs(inputs)
+        B = len(packed) // (32 * circuit.n_inputs)
+        r1 = circuit.r1cs_handle if (check and circuit.r1cs_handle) else None
+        self._check(self.lib.zkfl_wtns_calculate_batch(self.ctx, circuit.handle, r1, _lib.as_ptr(packed), B, None, None))
+        return B
+
+    def finalize(self, zkey: Zkey, partials, B: int, rs=None, nparts: int | None = None) -> list[bytes]:
+        """partials: list of per-rank byte strings, or ONE torch uint8 tensor (host or CUDA) holding nparts x B x 384 bytes"""
         proofs = ctypes.create_string_buffer(256 * B)
-        self._check(self.lib.zkfl_groth16_finalize(self.ctx, zkey.handle, _lib.as_ptr(b"".join(partials)), len(partials),
+        if isinstance(partials, (list, tuple)):
+            nparts, partials = len(partials), b"".join(partials)
+        self._check(self.lib.zkfl_groth16_finalize(self.ctx, zkey.handle, _lib.as_ptr(partials), nparts,
                                                   _lib.as_ptr(self._pack_rs(rs, B)), B, proofs))
         praw = proofs.raw
         return [praw[256 * b:256 * (b + 1)] for b in range(B)]
@@ -256,6 +274,26 @@ class Prover:
         out = ctypes.create_string_buffer(128 * n)
         self._check(self.lib.zkfl_g2_mul_generator(self.ctx, _lib.as_ptr(sc), n, out))
         return out.raw
+
+    # ---------------------------------------------------------------- masked aggregation + model update on the device
+    def aggregate_updates(self, masked_updates, accept, model, learning_rate: float) -> dict:
+        """Server.aggregateUpdates (tests/full_system_simulation.mjs:1137-1199): masked_updates[i] = the DIM field elements client i
+        published (ints), accept[i] = all of its proofs verified.  Field sum, signed decode, mean and the SGD step run on the GPU.
+        -> {"aggregated_field", "aggregated_gradient" (mean), "new_model", "num_clients"}; None when no client is accepted."""
+        n, dim = len(masked_updates), len(model)
+        if not any(accept):
+            return None
+        packed = b"".join(int(v).to_bytes(32, "little") for row in masked_updates for v in row)
+        acc = bytes(1 if a else 0 for a in accept)
+        model_in = (ctypes.c_double * dim)(*[float(x) for x in model])
+        mean, new_model = (ctypes.c_double * dim)(), (ctypes.c_double * dim)()
+        field = ctypes.create_string_buffer(32 * dim)
+        cnt = ctypes.c_uint32(0)
+        self._check(self.lib.zkfl_aggregate_updates(self.ctx, _lib.as_ptr(packed), _lib.as_ptr(acc), n, dim, float(learning_rate), model_in,
+                                                    field, mean, new_model, ctypes.byref(cnt)))
+        raw = field.raw
+        return {"aggregated_field": [int.from_bytes(raw[32 * j:32 * j + 32], "little") for j in range(dim)],
+                "aggregated_gradient": list(mean), "new_model": list(new_model), "num_clients": cnt.value}
 
     # ---------------------------------------------------------------- batch verification on the device
     def verify_batch(self, vk: dict, publics: list[bytes], proofs: list[bytes]) -> list[bool]:

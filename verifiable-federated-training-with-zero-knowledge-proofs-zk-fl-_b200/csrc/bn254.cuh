@@ -533,23 +533,6 @@ template <class F> ZK_HD void xyzz_add(Xyzz<F>& acc, const Xyzz<F>& q) {  // add
   acc.ZZ = acc.ZZ * q.ZZ * PP;
   acc.ZZZ = acc.ZZZ * q.ZZZ * PPP;
 }
-// the same addition with the hot-path products (inlined for Fq, one leaf call per Fq2 product): bucket reduction kernels
-template <class F> ZK_HD void xyzz_add_hot(Xyzz<F>& acc, const Xyzz<F>& q) {
-  if (q.is_inf()) return;
-  if (acc.is_inf()) { acc = q; return; }
-  const F U1 = F::mul_hot(acc.X, q.ZZ), U2 = F::mul_hot(q.X, acc.ZZ), S1 = F::mul_hot(acc.Y, q.ZZZ), S2 = F::mul_hot(q.Y, acc.ZZZ);
-  const F Pp = U2 - U1, Rr = S2 - S1;
-  if (Pp.is_zero()) {
-    if (Rr.is_zero()) acc = xyzz_dbl(acc); else acc = Xyzz<F>::infinity();
-    return;
-  }
-  const F PP = F::sqr_hot(Pp), PPP = F::mul_hot(Pp, PP), Qq = F::mul_hot(U1, PP);
-  const F X3 = F::sqr_hot(Rr) - PPP - Qq.dbl();
-  acc.Y = F::diff_of_products(Rr, Qq - X3, S1, PPP);
-  acc.X = X3;
-  acc.ZZ = F::mul_hot(F::mul_hot(acc.ZZ, q.ZZ), PP);
-  acc.ZZZ = F::mul_hot(F::mul_hot(acc.ZZZ, q.ZZZ), PPP);
-}
 template <class F> ZK_HD Xyzz<F> xyzz_neg(const Xyzz<F>& p) { Xyzz<F> r = p; r.Y = p.Y.neg(); return r; }
 
 // Montgomery-form affine; infinity -> (0,0)

@@ -4,7 +4,7 @@
 // kernel families in parallel (zkfl.cu: C ABI + artefact parsing + prove orchestration; witness.cu: witness / A.w,B.w /
 // H polynomial; msm_g1.cu, msm_g2.cu: the Pippenger pipeline per group; verify.cu: batch verifier).
 #pragma once
-#include "kernels.cuh"
+#include "types.cuh"
 
 #include <atomic>
 #include <cstdio>
@@ -65,7 +65,7 @@ struct zkfl_ctx {
   std::vector<std::string> order;
   // workspace (grow-only)
   DevBuf w, abc, hsc, stage_in, stage_rs, aos;
-  // counts / offsets of a bucket sort are read again by the fused level-1 reduction on a side stream while the main stream may
+  // counts / offsets of a bucket sort are still read by side-stream work (fix-up, reductions) while the main stream may
   // already run the NEXT sort: one set per sort of a proving pass (0: witness, 1: witness restricted to the B query, 2: H)
   DevBuf counts[3], offsets[3], cursors, chunk_sums, sorted, skey;
   DevBuf head[5], tail[5];   // chunk partials per MSM slot (read by that slot's reduction on its side stream)
@@ -85,6 +85,8 @@ struct zkfl_ctx {
   size_t chk_cap = 0;
   uint32_t chk_B = 0;        // instances covered by the pending constraint check (0: none pending)
   bool chk_wtns = false;     // a witness well-formedness check is pending
+  uint32_t w_wires = 0, w_B = 0;   // shape of the witness run_witness left in `w` (0: none)
+  bool sort_attr = false;    // k_msm_sort_cta has been granted its dynamic shared memory on this device
   DevBuf msm_sc, msm_out, mask_w, mask_wb, mask_h, part_out, part_in;
   cudaEvent_t t0 = nullptr, t1 = nullptr, ev_join = nullptr;
 };
@@ -155,6 +157,9 @@ struct zkfl_zkey {
 };
 struct MsmBases {
   zkfl_ctx* ctx; int group; size_t n; DevBuf pts;
+  // resident bases are constants of many MSMs: window-shifted table 2^(c*j) * P_i (index j*n + i) built once at load, so a
+  // run needs ONE bucket set and one reduction instead of one per window (c_tab = 0: no table, per-window sets)
+  DevBuf table; uint32_t c_tab = 0;
 };
 
 static inline uint32_t env_u32(const char* name, uint32_t dflt) {
@@ -195,3 +200,20 @@ int run_h_poly(zkfl_ctx* c, const zkfl_zkey* z, uint32_t B);   // witness in c->
 
 // ---- field helpers (zkfl.cu)
 bool fr_bytes_lt_mod(const uint8_t* p);
+Fr fr_root_of_unity(int power);      // ffjavascript's 2^power-th root of unity (w[28] = 5^((r-1)/2^28), w[k] = w[k+1]^2), Montgomery
+
+// the BN254 generators (1, 2) of G1 and the standard G2 generator, Montgomery affine
+static inline G1Affine g1_generator() {
+  G1Affine g; g.x = Fq::zero(); g.x.v[0] = 1; g.x = g.x.to_mont(); g.y = Fq::zero(); g.y.v[0] = 2; g.y = g.y.to_mont();
+  return g;
+}
+static inline G2Affine g2_generator() {
+  static const uint32_t W[4][8] = {{0xd992f6edu, 0x46debd5cu, 0xf75edaddu, 0x674322d4u, 0x5e5c4479u, 0x426a0066u, 0x121f1e76u, 0x1800deefu},
+                                   {0xaef312c2u, 0x97e485b7u, 0x35a9e712u, 0xf1aa4933u, 0x31fb5d25u, 0x7260bfb7u, 0x920d483au, 0x198e9393u},
+                                   {0x66fa7daau, 0x4ce6cc01u, 0x0c43d37bu, 0xe3d1e769u, 0x8dcb408fu, 0x4aab7180u, 0xdb8c6debu, 0x12c85ea5u},
+                                   {0xd122975bu, 0x55acdadcu, 0x70b38ef3u, 0xbc4b3133u, 0x690c3395u, 0xec9e99adu, 0x585ff075u, 0x090689d0u}};
+  Fq v[4];
+  for (int k = 0; k < 4; k++) { for (int i = 0; i < 8; i++) v[k].v[i] = W[k][i]; v[k] = v[k].to_mont(); }
+  G2Affine g; g.x.a = v[0]; g.x.b = v[1]; g.y.a = v[2]; g.y.b = v[3];
+  return g;
+}

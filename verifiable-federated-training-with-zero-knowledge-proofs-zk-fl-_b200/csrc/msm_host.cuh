@@ -1,12 +1,12 @@
 // Host side of the Pippenger pipeline, templated over the coordinate field; msm_g1.cu / msm_g2.cu instantiate it.
 #pragma once
 #include "host.h"
+#include "k_msm.cuh"
 
 static inline uint32_t affine_slots() { uint32_t K = env_u32("ZKFL_MSM_AFFINE_K", 64); return K < 1 ? 1 : (K > 4096 ? 4096 : K); }   // chunks per thread
 
-// bucket accumulation of one MSM (slot = which of the five buffer sets), on the main stream; uses the lists left by msm_sort(gen).
-// The fix-up of buckets cut by chunk borders is fused into level 1 of the batch reduction; only the paths that read completed
-// bucket arrays (latency variant of the reduction, batch-affine accumulation) still run k_msm_fixup.
+// bucket accumulation of one MSM (slot = which of the five buffer sets) and the fix-up of the buckets cut by chunk borders, on the
+// main stream; uses the lists left by msm_sort(gen).
 template <class F>
 int msm_accumulate(zkfl_ctx* c, const Affine<F>* bases, const MsmShape& s, int slot, const char* tag, int gen) {
   size_t rows = (size_t)s.B * s.R;
@@ -33,7 +33,7 @@ int msm_accumulate(zkfl_ctx* c, const Affine<F>* bases, const MsmShape& s, int s
     ZK_LAUNCH(k_msm_accumulate_chunks<F>, rows * cpr, 128, c->stream, bases, c->sorted.as<uint32_t>(), c->skey.as<uint16_t>(),
               offsets, counts, s, S, cpr, c->buckets[slot].as<Xyzz<F>>(), head, tail);
   }
-  if (reduce_deep(s)) {
+  {
     Stage st(c, "msm_fixup");
     ZK_LAUNCH(k_msm_fixup<F>, rows * s.nb, 128, c->stream, offsets, counts, s, S, cpr, (const Xyzz<F>*)head, (const Xyzz<F>*)tail,
               c->buckets[slot].as<Xyzz<F>>());
@@ -72,12 +72,9 @@ int msm_reduce(zkfl_ctx* c, const MsmShape& s, int slot, Xyzz<F>* out, cudaStrea
     CU(cudaGetLastError());
     return 0;
   }
-  const uint32_t S = s.lsS ? (1u << s.lsS) : accumulate_chunk(), cpr = (s.cap + S - 1) / S;
-  ZK_LAUNCH(k_reduce_level1_fused<F>, rows * p.N1, 128, stream, (const Xyzz<F>*)c->buckets[slot].as<Xyzz<F>>(),
-            (const Xyzz<F>*)c->head[slot].as<Xyzz<F>>(), (const Xyzz<F>*)c->tail[slot].as<Xyzz<F>>(), c->offsets[gen].as<uint32_t>(),
-            c->counts[gen].as<uint32_t>(), rows, s.nb, p.L1, S, cpr, R1, T1);
-  ZK_LAUNCH(k_reduce_level<F>, rows * p.N2, 128, stream, (const Xyzz<F>*)R1, rows, p.N1, p.L2, R2, T2);
-  ZK_LAUNCH(k_reduce_level<F>, rows * p.N2, 128, stream, (const Xyzz<F>*)T1, rows, p.N1, p.L2, RT, (Xyzz<F>*)nullptr);
+  ZK_LAUNCH(k_reduce_level<F>, rows * p.N1, 64, stream, (const Xyzz<F>*)c->buckets[slot].as<Xyzz<F>>(), rows, s.nb, p.L1, R1, T1);
+  ZK_LAUNCH(k_reduce_level<F>, rows * p.N2, 64, stream, (const Xyzz<F>*)R1, rows, p.N1, p.L2, R2, T2);
+  ZK_LAUNCH(k_reduce_level<F>, rows * p.N2, 64, stream, (const Xyzz<F>*)T1, rows, p.N1, p.L2, RT, (Xyzz<F>*)nullptr);
   ZK_LAUNCH(k_reduce_final<F>, rows, 32, stream, (const Xyzz<F>*)R2, (const Xyzz<F>*)T2, (const Xyzz<F>*)RT, rows, p.N2, p.L1, p.L2,
             c->win[slot].as<Xyzz<F>>());
   ZK_LAUNCH(k_msm_combine<F>, s.B, 32, stream, c->win[slot].as<Xyzz<F>>(), s, out);

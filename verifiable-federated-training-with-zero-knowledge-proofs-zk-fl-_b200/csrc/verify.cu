@@ -1,6 +1,6 @@
 // libzkfl.so: Groth16 verification -- single proof on the host, batches on the GPU (same pairing code, pairing.cuh).
-#define ZK_K_VERIFY
 #include "host.h"
+#include "k_verify.cuh"
 #include "verify_host.h"
 
 extern "C" {

@@ -1,6 +1,6 @@
 // libzkfl.so: batched witness evaluation (W1), constraint check, sparse A.w / B.w (K1) and the H polynomial (K2-K5).
-#define ZK_K_WITNESS
 #include "host.h"
+#include "k_witness.cuh"
 
 int zk_aos_to_soa(zkfl_ctx* c, const Fr* src, Fr* dst, uint32_t n_elem, uint32_t B, uint32_t dst_elem_off) {
   ZK_LAUNCH(k_aos_to_soa, (size_t)n_elem * B, 256, c->stream, src, dst, n_elem, B, dst_elem_off);
@@ -40,6 +40,7 @@ int run_witness(zkfl_ctx* c, const zkfl_circuit* circ, const uint8_t* inputs_hos
     ZK_LAUNCH(k_witness_level, (size_t)(hi - lo) * B, 64, c->stream, circ->dev, c->w.as<Fr>(), B, lo, hi);
   }
   CU(cudaGetLastError());
+  c->w_wires = circ->n_wires; c->w_B = B;
   return 0;
 }
 
@@ -149,5 +150,47 @@ int run_h_poly(zkfl_ctx* c, const zkfl_zkey* z, uint32_t B) {
     ZK_LAUNCH(k_join_abc, (size_t)n * B, 256, c->stream, abc, c->hsc.as<Fr>(), n, B);
   }
   CU(cudaGetLastError());
+  return 0;
+}
+
+// ---- masked aggregation + model update on the device
+extern "C" int zkfl_aggregate_updates(zkfl_ctx* c, const uint8_t* masked, const uint8_t* accept, uint32_t n_clients, uint32_t dim,
+                                      double learning_rate, const double* model_in, uint8_t* agg_field_out, double* agg_mean_out,
+                                      double* model_out, uint32_t* n_accepted) {
+  if (!c || !masked || !model_in || !agg_mean_out || !model_out || n_clients == 0 || dim == 0) return fail(ZKFL_ERR_ARG, "bad argument");
+  uint32_t count = 0;
+  for (uint32_t i = 0; i < n_clients; i++) count += (!accept || accept[i]) ? 1u : 0u;
+  if (n_accepted) *n_accepted = count;
+  if (count == 0) return fail(ZKFL_ERR_ARG, "No verified updates to aggregate!");     // the reference returns null here
+  CU(cudaSetDevice(c->device));
+  const uint32_t n_chunks = (n_clients + ZK_AGG_CHUNK - 1) / ZK_AGG_CHUNK;
+  DevBuf dMasked, dAccept, dPartial, dOut, dFlag;
+  const size_t mbytes = (size_t)n_clients * dim * sizeof(Fr);
+  TRY(dMasked.reserve(mbytes)); TRY(dPartial.reserve((size_t)dim * n_chunks * sizeof(Fr)));
+  TRY(dOut.reserve((size_t)dim * (sizeof(Fr) + 3 * sizeof(double)))); TRY(dFlag.reserve(4));
+  CU(cudaMemcpyAsync(dMasked.p, masked, mbytes, cudaMemcpyDefault, c->stream));          // host or device buffer
+  const uint8_t* acc_dev = nullptr;
+  if (accept) { TRY(dAccept.reserve(n_clients)); CU(cudaMemcpyAsync(dAccept.p, accept, n_clients, cudaMemcpyHostToDevice, c->stream)); acc_dev = dAccept.as<uint8_t>(); }
+  CU(cudaMemsetAsync(dFlag.p, 0, 4, c->stream));
+  Fr* agg = dOut.as<Fr>();
+  double* d_model_in = (double*)(agg + dim);
+  double* d_mean = d_model_in + dim;
+  double* d_model_out = d_mean + dim;
+  CU(cudaMemcpyAsync(d_model_in, model_in, dim * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  {
+    Stage st(c, "aggregate");
+    ZK_LAUNCH(k_agg_partial, (size_t)dim * n_chunks, 64, c->stream, dMasked.as<Fr>(), acc_dev, n_clients, dim, n_chunks, dPartial.as<Fr>(),
+              dFlag.as<uint32_t>());
+    ZK_LAUNCH(k_agg_final, dim, 32, c->stream, (const Fr*)dPartial.as<Fr>(), n_chunks, dim, count, learning_rate, (const double*)d_model_in, agg,
+              d_mean, d_model_out);
+    CU(cudaGetLastError());
+  }
+  uint32_t flag = 0;
+  CU(cudaMemcpyAsync(&flag, dFlag.p, 4, cudaMemcpyDeviceToHost, c->stream));
+  if (agg_field_out) CU(cudaMemcpyAsync(agg_field_out, agg, dim * sizeof(Fr), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(agg_mean_out, d_mean, dim * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(model_out, d_model_out, dim * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  if (flag) return fail(ZKFL_ERR_ARG, "masked update not reduced mod r");
   return 0;
 }

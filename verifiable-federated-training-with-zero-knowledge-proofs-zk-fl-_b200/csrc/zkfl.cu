@@ -1,9 +1,9 @@
 // libzkfl.so host side: artefact parsing (.zkey / .r1cs / .zkwp), HBM residency, orchestration of the proving
 // pipeline on one CUDA stream per context (side streams for the bucket reductions), and the C ABI declared in
 // include/zkfl.h.  Kernel families live in witness.cu, msm_g1.cu, msm_g2.cu, verify.cu (see host.h).
-#define ZK_K_FIN
-#define ZK_K_BENCH
 #include "host.h"
+#include "k_fin.cuh"
+#include "k_bench.cuh"
 
 #ifdef ZKFL_EMUL
 thread_local zk_emul_idx zk_emul_cur;
@@ -44,7 +44,7 @@ static Fr fr_pow(Fr base, const uint32_t* e, int nwords) {
   for (int i = nwords * 32 - 1; i >= 0; i--) { r = r.sqr(); if ((e[i >> 5] >> (i & 31)) & 1) r = r * base; }
   return r;
 }
-static Fr fr_root_of_unity(int power) {  // ffjavascript: nqr = 5, w[28] = 5^((r-1)/2^28), w[k] = w[k+1]^2
+Fr fr_root_of_unity(int power) {  // ffjavascript: nqr = 5, w[28] = 5^((r-1)/2^28), w[k] = w[k+1]^2
   uint32_t e[8];
   for (int i = 0; i < 8; i++) e[i] = FrP::mod(i);
   e[0] -= 1;
@@ -574,6 +574,7 @@ int zkfl_r1cs_check_batch(zkfl_ctx* c, const zkfl_r1cs* r, const uint8_t* wtns, 
   TRY(c->aos.reserve(cnt * sizeof(Fr))); TRY(c->w.reserve(cnt * sizeof(Fr)));
   CU(cudaMemcpyAsync(c->aos.p, wtns, cnt * sizeof(Fr), cudaMemcpyDefault, c->stream));   // pageable, pinned or device memory
   TRY(zk_aos_to_soa(c, c->aos.as<Fr>(), c->w.as<Fr>(), r->n_wires, (uint32_t)B, 0u));
+  c->w_wires = r->n_wires; c->w_B = (uint32_t)B;
   return check_r1cs_device(c, r, (uint32_t)B, first_bad);
 }
 
@@ -589,6 +590,7 @@ int zkfl_groth16_prove_batch(zkfl_ctx* c, const zkfl_zkey* z, const uint8_t* wtn
     TRY(c->aos.reserve(cnt * sizeof(Fr))); TRY(c->w.reserve(cnt * sizeof(Fr)));
     CU(cudaMemcpyAsync(c->aos.p, wtns, cnt * sizeof(Fr), cudaMemcpyDefault, c->stream));   // pageable, pinned or device memory
     TRY(zk_aos_to_soa(c, c->aos.as<Fr>(), c->w.as<Fr>(), z->n_vars, (uint32_t)B, 0u));
+    c->w_wires = z->n_vars; c->w_B = (uint32_t)B;
     TRY(check_wtns_launch(c, z->n_vars, (uint32_t)B));   // snarkjs reads the .wtns through its field class: reduced values, w[0] = 1
   }
   TRY(prove_from_device_witness(c, z, c->stage_rs.as<Fr>(), (uint32_t)B));
@@ -657,20 +659,26 @@ int zkfl_full_prove_fetch(zkfl_ctx* c, int B, uint8_t* proofs_out, uint32_t* fir
 // ---- single large proof split over several GPUs: per-rank MSM partials, then gather + add + blind
 int zkfl_groth16_msm_partials(zkfl_ctx* c, const zkfl_zkey* z, const uint8_t* wtns, int B, uint32_t part, uint32_t nparts,
                               uint8_t* partials_out) {
-  if (!c || !z || !wtns || !partials_out || B <= 0 || nparts == 0 || part >= nparts) return fail(ZKFL_ERR_ARG, "bad argument");
+  if (!c || !z || !partials_out || B <= 0 || nparts == 0 || part >= nparts) return fail(ZKFL_ERR_ARG, "bad argument");
   CU(cudaSetDevice(c->device));
   size_t cnt = (size_t)z->n_vars * B;
-  TRY(c->aos.reserve(cnt * sizeof(Fr))); TRY(c->w.reserve(cnt * sizeof(Fr)));
-  CU(cudaMemcpyAsync(c->aos.p, wtns, cnt * sizeof(Fr), cudaMemcpyDefault, c->stream));   // pageable, pinned or device memory
-  TRY(zk_aos_to_soa(c, c->aos.as<Fr>(), c->w.as<Fr>(), z->n_vars, (uint32_t)B, 0u));
-  TRY(check_wtns_launch(c, z->n_vars, (uint32_t)B));
+  if (wtns) {
+    TRY(c->aos.reserve(cnt * sizeof(Fr))); TRY(c->w.reserve(cnt * sizeof(Fr)));
+    CU(cudaMemcpyAsync(c->aos.p, wtns, cnt * sizeof(Fr), cudaMemcpyDefault, c->stream));   // pageable, pinned or device memory
+    TRY(zk_aos_to_soa(c, c->aos.as<Fr>(), c->w.as<Fr>(), z->n_vars, (uint32_t)B, 0u));
+    c->w_wires = z->n_vars; c->w_B = (uint32_t)B;
+    TRY(check_wtns_launch(c, z->n_vars, (uint32_t)B));
+  } else if (c->w.cap < cnt * sizeof(Fr) || c->w_wires != z->n_vars || c->w_B != (uint32_t)B) {
+    // wtns == NULL: the witness the last witness calculation of this context left in HBM (no upload, no host copy)
+    return fail(ZKFL_ERR_ARG, "no resident witness of this shape: run zkfl_wtns_calculate_batch on this context first");
+  }
   TRY(prove_from_device_witness(c, z, nullptr, (uint32_t)B, part, nparts, false));
   // layout per proof b: A | B1 | C | H (64 B each, affine canonical) | B2 (128 B)  -> stored as [5 blocks][B]
   TRY(c->part_out.reserve((size_t)B * 384));
   uint8_t* o = c->part_out.as<uint8_t>();
   TRY(msm_to_affine_canonical<Fq>(c, c->res_g1.as<G1Xyzz>(), (size_t)4 * B, (G1Affine*)o));
   TRY(msm_to_affine_canonical<Fq2>(c, c->res_g2.as<G2Xyzz>(), (size_t)B, (G2Affine*)(o + (size_t)B * 256)));
-  CU(cudaMemcpyAsync(partials_out, o, (size_t)B * 384, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(partials_out, o, (size_t)B * 384, cudaMemcpyDefault, c->stream));   // host or device buffer (NCCL exchanges device memory)
   CU(cudaStreamSynchronize(c->stream));
   return checks_result(c, nullptr);
 }
@@ -683,7 +691,7 @@ int zkfl_groth16_finalize(zkfl_ctx* c, const zkfl_zkey* z, const uint8_t* partia
   TRY(c->part_in.reserve(per * nparts));
   TRY(c->res_g1.reserve(4 * (size_t)B * sizeof(G1Xyzz)));
   TRY(c->res_g2.reserve((size_t)B * sizeof(G2Xyzz)));
-  CU(cudaMemcpyAsync(c->part_in.p, partials, per * nparts, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(c->part_in.p, partials, per * nparts, cudaMemcpyDefault, c->stream));   // host or device buffer
   const uint8_t* in = c->part_in.as<uint8_t>();
   TRY(msm_sum_partials<Fq>(c, (const G1Affine*)in, nparts, per / sizeof(G1Affine), (size_t)4 * B, c->res_g1.as<G1Xyzz>()));
   TRY(msm_sum_partials<Fq2>(c, (const G2Affine*)(in + (size_t)B * 256), nparts, per / sizeof(G2Affine), (size_t)B, c->res_g2.as<G2Xyzz>()));
@@ -694,13 +702,31 @@ int zkfl_groth16_finalize(zkfl_ctx* c, const zkfl_zkey* z, const uint8_t* partia
 }
 
 // ---- standalone MSM
-int zkfl_msm_bases_load(zkfl_ctx* c, const uint8_t* bases, size_t n, int group, void** handle) {
+static int msm_bases_upload(zkfl_ctx* c, const uint8_t* bases, size_t n, int group, void** handle) {
   if (!c || !bases || !handle || (group != 1 && group != 2) || n == 0 || n > 0x7FFFFFFFu) return fail(ZKFL_ERR_ARG, "bad argument");
   CU(cudaSetDevice(c->device));
   std::unique_ptr<MsmBases> b(new MsmBases());
   b->ctx = c; b->group = group; b->n = n;
   TRY(upload(c, b->pts, bases, n * (group == 1 ? 64 : 128)));
   *handle = b.release();
+  return 0;
+}
+// the window-shifted table of a resident base set (zkfl_msm_bases_load builds it; the one-shot calls do not)
+static int msm_bases_build_table(zkfl_ctx* c, MsmBases* b) {
+  const uint32_t cw = msm_shape((uint32_t)b->n, 1, true, env_u32("ZKFL_MSM_C_TABLE", 0)).c, W = 254 / cw + 1;
+  TRY(b->table.reserve((size_t)W * b->n * (b->group == 1 ? 64 : 128)));
+  if (b->group == 1) TRY(msm_precompute_windows<Fq>(c, b->pts.as<G1Affine>(), (uint32_t)b->n, cw, W, b->table.as<G1Affine>()));
+  else TRY(msm_precompute_windows<Fq2>(c, b->pts.as<G2Affine>(), (uint32_t)b->n, cw, W, b->table.as<G2Affine>()));
+  CU(cudaStreamSynchronize(c->stream));
+  b->c_tab = cw;
+  return 0;
+}
+int zkfl_msm_bases_load(zkfl_ctx* c, const uint8_t* bases, size_t n, int group, void** handle) {
+  TRY(msm_bases_upload(c, bases, n, group, handle));
+  if (n >= 1024 && env_u32("ZKFL_MSM_TABLE", 1)) {
+    int rc = msm_bases_build_table(c, (MsmBases*)*handle);
+    if (rc) { zkfl_msm_bases_free(*handle); *handle = nullptr; return rc; }
+  }
   return 0;
 }
 void zkfl_msm_bases_free(void* h) { if (h) { MsmBases* b = (MsmBases*)h; cudaSetDevice(b->ctx->device); delete b; } }
@@ -710,15 +736,16 @@ int zkfl_msm_run(zkfl_ctx* c, void* handle, const uint8_t* scalars, size_t n, ui
   CU(cudaSetDevice(c->device));
   TRY(c->msm_sc.reserve(n * sizeof(Fr)));
   if (scalars) CU(cudaMemcpyAsync(c->msm_sc.p, scalars, n * sizeof(Fr), cudaMemcpyHostToDevice, c->stream));
-  MsmShape s = msm_shape((uint32_t)n, 1, false);
+  const bool tab = b->c_tab && n == b->n;      // the table is indexed j * n + i: whole base set only
+  MsmShape s = tab ? msm_shape((uint32_t)n, 1, true, b->c_tab) : msm_shape((uint32_t)n, 1, false);
   { Stage st(c, "msm_sort"); TRY(msm_sort(c, c->msm_sc.as<Fr>(), nullptr, s)); }
   TRY(c->msm_out.reserve(sizeof(G2Xyzz) + sizeof(G2Affine)));
   uint8_t* o = c->msm_out.as<uint8_t>();
   if (b->group == 1) {
-    TRY(msm_run<Fq>(c, b->pts.as<G1Affine>(), s, (G1Xyzz*)o, "msm_acc_g1", "msm_reduce_g1"));
+    TRY(msm_run<Fq>(c, tab ? b->table.as<G1Affine>() : b->pts.as<G1Affine>(), s, (G1Xyzz*)o, "msm_acc_g1", "msm_reduce_g1"));
     TRY(msm_to_affine_canonical<Fq>(c, (const G1Xyzz*)o, (size_t)1, (G1Affine*)(o + sizeof(G2Xyzz))));
   } else {
-    TRY(msm_run<Fq2>(c, b->pts.as<G2Affine>(), s, (G2Xyzz*)o, "msm_acc_g2", "msm_reduce_g2"));
+    TRY(msm_run<Fq2>(c, tab ? b->table.as<G2Affine>() : b->pts.as<G2Affine>(), s, (G2Xyzz*)o, "msm_acc_g2", "msm_reduce_g2"));
     TRY(msm_to_affine_canonical<Fq2>(c, (const G2Xyzz*)o, (size_t)1, (G2Affine*)(o + sizeof(G2Xyzz))));
   }
   if (out) {
@@ -730,7 +757,7 @@ int zkfl_msm_run(zkfl_ctx* c, void* handle, const uint8_t* scalars, size_t n, ui
 static int msm_oneshot(zkfl_ctx* c, const uint8_t* bases, const uint8_t* scalars, size_t n, int group, uint8_t* out) {
   if (!scalars || !out) return fail(ZKFL_ERR_ARG, "bad argument");
   void* h = nullptr;
-  TRY(zkfl_msm_bases_load(c, bases, n, group, &h));
+  TRY(msm_bases_upload(c, bases, n, group, &h));     // one MSM over these bases: no table (it would cost more than it saves)
   int rc = zkfl_msm_run(c, h, scalars, n, out);
   zkfl_msm_bases_free(h);
   return rc;
@@ -740,21 +767,9 @@ int zkfl_g2_msm(zkfl_ctx* c, const uint8_t* bases, const uint8_t* scalars, size_
 
 // ---- setup support
 }  // extern "C"
-static Fq fq_small(uint32_t v) { Fq r = Fq::zero(); r.v[0] = v; return r.to_mont(); }
-static Fq fq_words(const uint32_t (&w)[8]) { Fq r; for (int i = 0; i < 8; i++) r.v[i] = w[i]; return r.to_mont(); }
 extern "C" {
-int zkfl_g1_mul_generator(zkfl_ctx* c, const uint8_t* scalars, size_t n, uint8_t* out) {
-  G1Affine g; g.x = fq_small(1); g.y = fq_small(2);
-  return msm_gen_mul<Fq>(c, g, scalars, n, out);
-}
-int zkfl_g2_mul_generator(zkfl_ctx* c, const uint8_t* scalars, size_t n, uint8_t* out) {
-  static const uint32_t X0[8] = {0xd992f6edu, 0x46debd5cu, 0xf75edaddu, 0x674322d4u, 0x5e5c4479u, 0x426a0066u, 0x121f1e76u, 0x1800deefu};
-  static const uint32_t X1[8] = {0xaef312c2u, 0x97e485b7u, 0x35a9e712u, 0xf1aa4933u, 0x31fb5d25u, 0x7260bfb7u, 0x920d483au, 0x198e9393u};
-  static const uint32_t Y0[8] = {0x66fa7daau, 0x4ce6cc01u, 0x0c43d37bu, 0xe3d1e769u, 0x8dcb408fu, 0x4aab7180u, 0xdb8c6debu, 0x12c85ea5u};
-  static const uint32_t Y1[8] = {0xd122975bu, 0x55acdadcu, 0x70b38ef3u, 0xbc4b3133u, 0x690c3395u, 0xec9e99adu, 0x585ff075u, 0x090689d0u};
-  G2Affine g; g.x.a = fq_words(X0); g.x.b = fq_words(X1); g.y.a = fq_words(Y0); g.y.b = fq_words(Y1);
-  return msm_gen_mul<Fq2>(c, g, scalars, n, out);
-}
+int zkfl_g1_mul_generator(zkfl_ctx* c, const uint8_t* scalars, size_t n, uint8_t* out) { return msm_gen_mul<Fq>(c, g1_generator(), scalars, n, out); }
+int zkfl_g2_mul_generator(zkfl_ctx* c, const uint8_t* scalars, size_t n, uint8_t* out) { return msm_gen_mul<Fq2>(c, g2_generator(), scalars, n, out); }
 
 // `zkey contribute`: every point of a section times one scalar
 int zkfl_g1_scale_points(zkfl_ctx* c, const uint8_t* pts, size_t n, const uint8_t scalar[32], uint8_t* out) { return msm_point_scale<Fq>(c, pts, scalar, n, out); }

@@ -87,8 +87,14 @@ class SimClient:
     """One client of full_system_simulation.mjs (N=8, MODEL_DIM=4, DEPTH=3, tau^2=1e8, round 1)."""
     N, DIM, DEPTH, TAU2, PRECISION, ROUND = 8, 4, 3, 100000000, 1000, 1
 
-    def __init__(self, client_id: int, lcg: JsLcg, n: int | None = None, dim: int | None = None, depth: int | None = None):
+    KEY_SEED = 12345     # masterKey = Poseidon(id, 12345), K_ij = Poseidon(min, max, 12345) (:1321-1336)
+
+    def __init__(self, client_id: int, lcg: JsLcg, n: int | None = None, dim: int | None = None, depth: int | None = None,
+                 hashed: bool = True):
+        """hashed=False defers every Poseidon evaluation: the commitments then come from the GPU pipeline
+        (commitments.hydrate fills tree / roots / keys / masks for all clients of a round in one batched pass)."""
         self.id = client_id
+        self.pre = None      # commitments computed elsewhere: {"root_W", "root_G", "master", "keys", "root_K", "masks"}
         if n is not None:          # scaled configurations (BASELINE configs[4]); defaults are the reference's (8, 4, 3)
             self.N, self.DIM, self.DEPTH = n, dim, depth
         self.features, self.labels = [], []
@@ -97,10 +103,20 @@ class SimClient:
             self.labels.append((i + client_id) % 2)
         self.c1 = sum(self.labels)
         self.c0 = self.N - self.c1
-        leaves = [vector_hash(f + [l]) for f, l in zip(self.features, self.labels)]  # :315-320
-        self.tree = build_merkle_tree(leaves, self.DEPTH)
+        if hashed:
+            leaves = [vector_hash(f + [l]) for f, l in zip(self.features, self.labels)]  # :315-320
+            self.attach_tree(build_merkle_tree(leaves, self.DEPTH))
+
+    def attach_tree(self, tree):
+        self.tree = tree
         self.root_d = self.tree[-1][0]
         self.proofs = [merkle_proof(self.tree, i, self.DEPTH) for i in range(self.N)]
+
+    def prepare_gradient(self, weights):
+        """the clear gradient of this round (needed BEFORE the commitments can be computed anywhere)"""
+        self.weights = list(weights)
+        self.gradient, self._summed, self._rem = verified_gradient(self.features, self.labels, self.weights, self.PRECISION)
+        return self.gradient
 
     def balance_input(self) -> dict:                                      # :355-365
         return {"client_id": _s(self.id), "root": _s(self.root_d), "N_public": _s(self.N), "c0": _s(self.c0),
@@ -110,12 +126,14 @@ class SimClient:
                 "pathIndices": [[_s(x) for x in p[1]] for p in self.proofs]}
 
     def training_input(self, weights) -> dict:                            # :401-474
-        self.weights = list(weights)
-        grad, summed, rem = verified_gradient(self.features, self.labels, self.weights, self.PRECISION)
-        self.gradient = grad
+        grad = self.prepare_gradient(weights)
+        summed, rem = self._summed, self._rem
         assert sum(g * g for g in grad) <= self.TAU2
-        self.root_w = vector_hash(self.weights)
-        self.root_g = gradient_commitment(grad, self.id, self.ROUND)
+        if self.pre is not None:
+            self.root_w, self.root_g = self.pre["root_W"], self.pre["root_G"]
+        else:
+            self.root_w = vector_hash(self.weights)
+            self.root_g = gradient_commitment(grad, self.id, self.ROUND)
         return {"client_id": _s(self.id), "round": _s(self.ROUND), "root_D": _s(self.root_d), "root_G": _s(self.root_g),
                 "root_W": _s(self.root_w), "tauSquared": _s(self.TAU2), "weights": [_s(w) for w in self.weights],
                 "expectedSummedGrad": [_s(x) for x in summed], "remainder": [_s(x) for x in rem],
@@ -125,15 +143,18 @@ class SimClient:
                 "pathIndices": [[_s(x) for x in p[1]] for p in self.proofs]}
 
     def secagg_input(self, peer_ids) -> dict:                             # :558-637, keys :1321-1336
-        master = poseidon_hash([self.id, 12345])
-        keys = [poseidon_hash([min(self.id, j), max(self.id, j), 12345]) for j in peer_ids]
-        root_k = poseidon_hash([master] + keys)
+        if self.pre is not None:
+            master, keys, root_k, masks = self.pre["master"], self.pre["keys"], self.pre["root_K"], self.pre["masks"]
+        else:
+            master = poseidon_hash([self.id, self.KEY_SEED])
+            keys = [poseidon_hash([min(self.id, j), max(self.id, j), self.KEY_SEED]) for j in peer_ids]
+            root_k = poseidon_hash([master] + keys)
+            masks = [[poseidon_hash([key, self.ROUND, min(self.id, j), max(self.id, j), k]) for k in range(self.DIM)]
+                     for j, key in zip(peer_ids, keys)]
         masked = [g % FR for g in self.gradient]
-        for j, key in zip(peer_ids, keys):
-            lo, hi = min(self.id, j), max(self.id, j)
+        for j, row in zip(peer_ids, masks):
             for k in range(self.DIM):
-                mask = poseidon_hash([key, self.ROUND, lo, hi, k])
-                masked[k] = (masked[k] + mask) % FR if self.id < j else (masked[k] - mask) % FR
+                masked[k] = (masked[k] + row[k]) % FR if self.id < j else (masked[k] - row[k]) % FR
         self.masked_update = masked
         return {"client_id": _s(self.id), "round": _s(self.ROUND), "root_D": _s(self.root_d), "root_G": _s(self.root_g),
                 "root_W": _s(self.root_w), "root_K": _s(root_k), "tauSquared": _s(self.TAU2),

@@ -83,12 +83,26 @@ def prove_split(prover, zkey, wtns: list[bytes], rs: list | None):
     (rs=None: rank 0 draws r, s and broadcasts them)."""
     world, rank = dist.get_world_size(), dist.get_rank()
     B = len(wtns) if isinstance(wtns, (list, tuple)) else (wtns.numel() * wtns.element_size() if hasattr(wtns, "data_ptr") else len(wtns)) // (32 * zkey.n_vars)
-    if hasattr(wtns, "is_cuda") and wtns.is_cuda:
-        torch.cuda.current_stream(wtns.device).synchronize()   # the library copies on its own stream: the producer must be done
     rs = _shared_rs(rs, B)
-    part = prover.msm_partials(zkey, wtns, rank, world)
-    mine = torch.frombuffer(bytearray(part), dtype=torch.uint8).to(_device())
-    allp = [torch.zeros_like(mine) for _ in range(world)]
-    dist.all_gather(allp, mine)            # the one exchange step: 384 B per proof per rank
-    partials = [bytes(t.cpu().numpy().tobytes()) for t in allp]
-    return prover.finalize(zkey, partials, B, rs)
+    return _exchange_and_finalize(prover, zkey, wtns, B, rs)
+
+
+def _exchange_and_finalize(prover, zkey, wtns, B: int, rs):
+    """partials straight into a device tensor, all-gather device-to-device (NCCL over NVLink; gloo on host memory in the CPU
+    tests), finalize from the gathered device tensor: no host staging on the data path."""
+    world, rank = dist.get_world_size(), dist.get_rank()
+    mine = torch.empty(384 * B, dtype=torch.uint8, device=_device())
+    prover.msm_partials(zkey, wtns, rank, world, out=mine, B=B)      # returns after the library's stream is done
+    allp = torch.empty(world * 384 * B, dtype=torch.uint8, device=_device())
+    dist.all_gather_into_tensor(allp, mine)                          # the one exchange step: 384 B per proof per rank
+    if allp.is_cuda:
+        torch.cuda.current_stream().synchronize()                    # the library reads `allp` on its own stream
+    return prover.finalize(zkey, allp, B, rs, nparts=world)
+
+
+def full_prove_split(prover, circuit, zkey, inputs, rs: list | None, check: bool = True):
+    """`fullProve` of one (or a few) large proofs over all ranks: every rank evaluates the witness on its GPU and keeps it in HBM
+    (no witness ever crosses PCIe), proves its point range, then the exchange above.  Every rank returns the same proofs."""
+    B = prover.witness_resident(circuit, inputs, check)
+    rs = _shared_rs(rs, B)
+    return _exchange_and_finalize(prover, zkey, None, B, rs)

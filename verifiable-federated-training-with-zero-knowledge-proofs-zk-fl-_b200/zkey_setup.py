@@ -115,56 +115,42 @@ class _Terms:
 
 
 def new_zkey(prover, r1cs, seed: bytes) -> bytes:
-    """prover: zkfl_b200.api.Prover (its GPU does the scalar multiplications). r1cs: `.r1cs` bytes or a CompiledCircuit."""
+    """`groth16 setup` on the GPU (zkfl_groth16_setup, csrc/setup.cu): Lagrange basis, column sums, key scalars and every scalar
+    multiplication run on the device and the library writes the `.zkey`.  The host only flattens the three matrices into
+    coordinate arrays with a table of the distinct coefficients.  r1cs: `.r1cs` bytes or a CompiledCircuit.
+    `seed` determines the toxic waste: pass OS randomness (Prover.new_zkey(seed=None) does) unless a test needs a fixed key."""
+    import ctypes
+    from array import array
+    from . import _lib
     r = _Terms(r1cs)
-    r_info = {"n_wires": r.n_wires, "n_public": r.n_public, "n_constraints": r.n_constraints}
-    m, l, nc = r_info["n_wires"], r_info["n_public"], r_info["n_constraints"]
-    tau, alpha, beta, delta = toxic_from_seed(seed)
-    lg = max((nc + l).bit_length(), 1)  # smallest 2^lg >= nc + l + 1
-    n = 1 << lg
-    L = lagrange_at(tau, lg)
-    At, Bt, Ct = [0] * m, [0] * m, [0] * m
-    for row, wire, k in r["A"]:
-        At[wire] = (At[wire] + k * L[row]) % FR
-    for row, wire, k in r["B"]:
-        Bt[wire] = (Bt[wire] + k * L[row]) % FR
-    for row, wire, k in r["C"]:
-        Ct[wire] = (Ct[wire] + k * L[row]) % FR
-    for s in range(l + 1):
-        At[s] = (At[s] + L[nc + s]) % FR
-    dinv = pow(delta, -1, FR)
-    comb = [(beta * a + alpha * b + c) % FR for a, b, c in zip(At, Bt, Ct)]
-    L2 = lagrange_at(tau, lg + 1)
-    h_sc = [L2[2 * i + 1] * dinv % FR for i in range(n)]
-    g1_scalars = ([alpha, beta, delta] + comb[:l + 1] + At + Bt + [c * dinv % FR for c in comb[l + 1:]] + h_sc)
-    g1 = prover.g1_mul_generator(g1_scalars)
-    g2 = prover.g2_mul_generator([beta, 1, delta] + Bt)
-    pos = 0
+    table, index = [], {}
+    arrs = []
+    for key in "ABC":
+        rows, wires, coefs = r._m[key]
+        idx = []
+        for cval in coefs:
+            k = index.get(cval)
+            if k is None:
+                k = index[cval] = len(table)
+                table.append(cval)
+            idx.append(k)
+        arrs.append((array("I", rows), array("I", wires), array("I", idx)))
+    coef_bytes = b"".join((int(v) % FR).to_bytes(32, "little") for v in table) or bytes(32)
+    toxic = b"".join(int(v).to_bytes(32, "little") for v in toxic_from_seed(seed))
+    vp = ctypes.c_void_p
 
-    def take(cnt):
-        nonlocal pos
-        out = g1[64 * pos:64 * (pos + cnt)]
-        pos += cnt
-        return out
-
-    alpha1, beta1, delta1 = take(1), take(1), take(1)
-    ic, pa, pb1, pc, ph = take(l + 1), take(m), take(m), take(m - l - 1), take(n)
-    beta2, gamma2, delta2, pb2 = g2[:128], g2[128:256], g2[256:384], g2[384:]
-    hdr = (struct.pack("<I", 32) + FQ.to_bytes(32, "little") + struct.pack("<I", 32) + FR.to_bytes(32, "little")
-           + struct.pack("<III", m, l, n) + alpha1 + beta1 + beta2 + gamma2 + delta1 + delta2)
-    parts = []
-    n_coef = 0
-    pack = struct.Struct("<III").pack
-    for mtx, key in ((0, "A"), (1, "B")):
-        parts.append(b"".join(pack(mtx, row, wire) + (k * _R2 % FR).to_bytes(32, "little") for row, wire, k in r[key]))
-        n_coef += r.count(key)
-    parts.append(b"".join(pack(0, nc + s, s) + (_R2 % FR).to_bytes(32, "little") for s in range(l + 1)))
-    n_coef += l + 1
-    coeffs = b"".join(parts)
-    # snarkjs writes A and B interleaved in constraint order; the prover does not depend on the order
-    sections = [(1, struct.pack("<I", 1)), (2, hdr), (3, ic), (4, struct.pack("<I", n_coef) + coeffs),
-                (5, pa), (6, pb1), (7, pb2), (8, pc), (9, ph), (10, bytes(64) + struct.pack("<I", 0))]
-    return write_container(b"zkey", 1, sections)
+    def ptrs(k):
+        return (vp * 3)(*[a[k].buffer_info()[0] if len(a[k]) else None for a in arrs])
+    rows_p, wires_p, cidx_p = ptrs(0), ptrs(1), ptrs(2)
+    nnz = (ctypes.c_size_t * 3)(*[len(a[0]) for a in arrs])
+    need = ctypes.c_size_t(0)
+    lib = prover.lib
+    args = (prover.ctx, r.n_wires, r.n_public, r.n_constraints, rows_p, wires_p, cidx_p, nnz, _lib.as_ptr(coef_bytes), max(len(table), 1),
+            _lib.as_ptr(toxic))
+    prover._check(lib.zkfl_groth16_setup(*args, None, 0, ctypes.byref(need)))
+    out = bytearray(need.value)
+    prover._check(lib.zkfl_groth16_setup(*args, _lib.as_ptr(out), len(out), ctypes.byref(need)))
+    return bytes(out)
 
 
 def contribute(prover, zkey: bytes, name: str = "", entropy: bytes = b"") -> bytes:
