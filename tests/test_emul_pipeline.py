@@ -291,6 +291,15 @@ def test_c_abi_argument_and_format_errors(emul_prover):
     assert rc == -5 and bad_first[0] == 0xFFFFFFFF and bad_first[1] != 0xFFFFFFFF and out_p.raw == bytes(512)
     with pytest.raises(_lib.ZkflError, match="not reduced"):
         emul_prover.full_prove(circ, Z, b"\xff" * (32 * circ.n_inputs), [(1, 2)])
+    # an asynchronous run whose verdicts nobody fetched must not leak into the next, smaller call (it once overflowed first_bad)
+    three = circ.pack_inputs(pc.tiny_inputs())
+    emul_prover.stage(circ, Z, three, emul_prover._pack_rs([(1, 2), (3, 4), (5, 6)], 3), 3)
+    emul_prover.run_staged(circ, Z, 3, check=True)
+    guard = (ctypes.c_uint32 * 4)(7, 7, 7, 7)
+    one = circ.pack_inputs(pc.tiny_inputs()[:1])
+    p1 = ctypes.create_string_buffer(256)
+    assert lib.zkfl_groth16_full_prove_batch(ctx, circ.handle, Z.handle, circ.r1cs_handle, _lib.as_ptr(one), None, 1, p1, None, guard) == 0
+    assert list(guard) == [0xFFFFFFFF, 7, 7, 7]
     h = ctypes.c_void_p()
     assert lib.zkfl_zkey_load(ctx, None, 0, ctypes.byref(h)) != 0 and lib.zkfl_last_error()
     assert lib.zkfl_groth16_prove_batch(ctx, Z.handle, None, None, 1, None, None) != 0

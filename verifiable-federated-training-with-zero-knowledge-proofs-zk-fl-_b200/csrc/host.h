@@ -69,6 +69,7 @@ struct zkfl_ctx {
   // already run the NEXT sort: one set per sort of a proving pass (0: witness, 1: witness restricted to the B query, 2: H)
   DevBuf counts[3], offsets[3], cursors, chunk_sums, sorted, skey;
   DevBuf head[5], tail[5];   // chunk partials per MSM slot (read by that slot's reduction on its side stream)
+  DevBuf heavy;              // queue of heavy buckets of the current fix-up (count, then bucket ids)
   DevBuf v_ic, v_pub, v_proofs, v_t, v_g1, v_g2, v_flags, v_f, v_halves, v_ok;   // batch verifier
   DevBuf aff_acc, aff_pre;   // batch-affine accumulation: running affine sums and prefix products, [slot group][lane]
   // five MSMs per proof batch (A, C, B1, H on G1; B2 on G2): own bucket / reduction buffers each, so the
@@ -170,7 +171,7 @@ static inline uint32_t env_u32(const char* name, uint32_t dflt) {
 // ---- msm_g1.cu (group-independent parts) and msm_g1.cu / msm_g2.cu (explicit instantiations for Fq / Fq2)
 struct ReducePlan { uint32_t L1, L2, N1, N2; };
 uint32_t accumulate_chunk();
-MsmShape msm_shape(uint32_t m, uint32_t B, bool shared, uint32_t force_c = 0);
+MsmShape msm_shape(uint32_t m, uint32_t B, bool shared, uint32_t force_c = 0, uint32_t c_cap = 0);
 ReducePlan reduce_plan(const MsmShape& s);
 int msm_sort(zkfl_ctx* c, const Fr* scalars, const uint8_t* skip, const MsmShape& s, int gen = 0);   // gen: which counts/offsets set
 int msm_range_mask(zkfl_ctx* c, const uint8_t* base_skip, uint32_t m, uint32_t lo, uint32_t hi, uint8_t* out);
@@ -195,8 +196,12 @@ int check_r1cs_device(zkfl_ctx* c, const zkfl_r1cs* r, uint32_t B, uint32_t* fir
 // deferred form: launch now (stream-ordered), judge after the caller's cudaStreamSynchronize
 int check_r1cs_launch(zkfl_ctx* c, const zkfl_r1cs* r, uint32_t B);
 int check_wtns_launch(zkfl_ctx* c, uint32_t n_wires, uint32_t B);   // every element < r and wire 0 == 1, on the [n_wires][B] witness in c->w
-int checks_result(zkfl_ctx* c, uint32_t* first_bad);                // ZKFL_ERR_ASSERT / ZKFL_ERR_ARG when a pending check failed
-int run_h_poly(zkfl_ctx* c, const zkfl_zkey* z, uint32_t B);   // witness in c->w -> H-MSM scalars in c->hsc
+// ZKFL_ERR_ASSERT / ZKFL_ERR_ARG when a pending check failed; first_bad (may be NULL) has room for B entries
+int checks_result(zkfl_ctx* c, uint32_t* first_bad, uint32_t B);
+// a new pass starts: verdicts of an earlier asynchronous pass that nobody collected are dropped
+static inline void checks_reset(zkfl_ctx* c) { c->chk_B = 0; c->chk_wtns = false; }
+// witness in c->w -> H-MSM scalars in c->hsc; check != NULL: the constraint check is folded into the A.w / B.w pass (deferred verdict)
+int run_h_poly(zkfl_ctx* c, const zkfl_zkey* z, uint32_t B, const zkfl_r1cs* check = nullptr);
 
 // ---- field helpers (zkfl.cu)
 bool fr_bytes_lt_mod(const uint8_t* p);

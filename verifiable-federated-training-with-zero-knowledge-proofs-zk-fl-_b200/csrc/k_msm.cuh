@@ -85,7 +85,7 @@ ZK_GLOBAL void k_msm_scan_write(const uint32_t* __restrict__ counts, const uint3
 // pass 3: scatter point references into bucket order. sorted: [B*W][cap], entry = point | sign << 31;
 // skey: the bucket index of every entry (lets pass 4 walk the list in fixed-size chunks)
 ZK_GLOBAL void k_msm_scatter(const Fr* __restrict__ scalars, const uint8_t* __restrict__ skip, MsmShape s,
-                             uint32_t* __restrict__ cursors, uint32_t* __restrict__ sorted, uint16_t* __restrict__ skey) {
+                             uint32_t* __restrict__ cursors, uint32_t* __restrict__ sorted, zk_key_t* __restrict__ skey) {
   size_t tid = ZK_TID;
   if (tid >= (size_t)s.m * s.B) return;
   uint32_t b = (uint32_t)(tid / s.m), i = (uint32_t)(tid % s.m);   // proof-major, see k_msm_count
@@ -102,7 +102,7 @@ ZK_GLOBAL void k_msm_scatter(const Fr* __restrict__ scalars, const uint8_t* __re
     uint32_t ref = s.R == 1 ? j * s.m + i : i;
     const size_t at = (size_t)row * s.cap + msm_list_index(s, pos);
     sorted[at] = ref | (d < 0 ? 0x80000000u : 0u);
-    skey[at] = (uint16_t)(mag - 1);
+    skey[at] = (zk_key_t)(mag - 1);
   }
 }
 #ifndef ZKFL_EMUL
@@ -114,7 +114,7 @@ ZK_GLOBAL void k_msm_scatter(const Fr* __restrict__ scalars, const uint8_t* __re
 // grid = rows (R == 1: row = proof), block = 1024 threads, dynamic shared memory = (nb + 32) * 4 bytes.
 static __global__ void __launch_bounds__(1024) k_msm_sort_cta(const Fr* __restrict__ scalars, const uint8_t* __restrict__ skip, MsmShape s,
                                                               uint32_t* __restrict__ offsets, uint32_t* __restrict__ counts,
-                                                              uint32_t* __restrict__ sorted, uint16_t* __restrict__ skey) {
+                                                              uint32_t* __restrict__ sorted, zk_key_t* __restrict__ skey) {
   extern __shared__ uint32_t zk_sort_sm[];
   uint32_t* cnt = zk_sort_sm;            // nb counters, later the scatter cursors
   uint32_t* wsum = zk_sort_sm + s.nb;    // 32 warp totals of the scan
@@ -158,7 +158,7 @@ static __global__ void __launch_bounds__(1024) k_msm_sort_cta(const Fr* __restri
   }
   __syncthreads();
   uint32_t* list = sorted + (size_t)b * s.cap;
-  uint16_t* keys = skey + (size_t)b * s.cap;
+  zk_key_t* keys = skey + (size_t)b * s.cap;
   for (uint32_t i = tid; i < s.m; i += nt) {
     if (skip && skip[i]) continue;
     const Fr k = scalars[(size_t)i * s.B + b];
@@ -170,7 +170,7 @@ static __global__ void __launch_bounds__(1024) k_msm_sort_cta(const Fr* __restri
       const uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
       const uint32_t at = msm_list_index(s, atomicAdd(cnt + (mag - 1), 1u));
       list[at] = (j * s.m + i) | (d < 0 ? 0x80000000u : 0u);
-      keys[at] = (uint16_t)(mag - 1);
+      keys[at] = (zk_key_t)(mag - 1);
     }
   }
 }
@@ -183,7 +183,7 @@ static __global__ void __launch_bounds__(1024) k_msm_sort_cta(const Fr* __restri
 // (head = run containing the chunk's first entry, tail = run containing its last entry) for pass 4b.
 template <class F>
 ZK_GLOBAL ZK_ACC_BOUNDS(F) void k_msm_accumulate_chunks(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ sorted,
-                                       const uint16_t* __restrict__ skey, const uint32_t* __restrict__ offsets,
+                                       const zk_key_t* __restrict__ skey, const uint32_t* __restrict__ offsets,
                                        const uint32_t* __restrict__ counts, MsmShape s, uint32_t S, uint32_t chunks_per_row,
                                        Xyzz<F>* __restrict__ buckets, Xyzz<F>* __restrict__ head, Xyzz<F>* __restrict__ tail) {
   size_t tid = ZK_TID;
@@ -197,7 +197,7 @@ ZK_GLOBAL ZK_ACC_BOUNDS(F) void k_msm_accumulate_chunks(const Affine<F>* __restr
   if (pos0 >= total) return;
   uint32_t pos1 = pos0 + S < total ? pos0 + S : total;
   const uint32_t* list = sorted + row * s.cap;
-  const uint16_t* keys = skey + row * s.cap;
+  const zk_key_t* keys = skey + row * s.cap;
   uint32_t cur = keys[msm_list_index(s, pos0)];
   bool first = true;
   Xyzz<F> acc = Xyzz<F>::infinity();
@@ -276,7 +276,7 @@ template <class F> ZK_D Xyzz<F> aff_to_xyzz(const Affine<F>& a) { return Xyzz<F>
 
 template <class F>
 ZK_GLOBAL void k_msm_accumulate_affine(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ sorted,
-                                       const uint16_t* __restrict__ skey, const uint32_t* __restrict__ offsets,
+                                       const zk_key_t* __restrict__ skey, const uint32_t* __restrict__ offsets,
                                        const uint32_t* __restrict__ counts, MsmShape s, uint32_t K, uint32_t n_rows,
                                        Affine<F>* __restrict__ acc, F* __restrict__ pre, Xyzz<F>* __restrict__ buckets,
                                        Xyzz<F>* __restrict__ head, Xyzz<F>* __restrict__ tail) {
@@ -298,7 +298,7 @@ ZK_GLOBAL void k_msm_accumulate_affine(const Affine<F>* __restrict__ bases, cons
     return g <= grp0 ? 0u : (g - grp0 < K ? g - grp0 : K);
   };
   const uint32_t* row_list = sorted + (size_t)row * s.cap;
-  const uint16_t* row_keys = skey + (size_t)row * s.cap;
+  const zk_key_t* row_keys = skey + (size_t)row * s.cap;
   const size_t slot0 = ((size_t)row * cpr32 + grp0) * 32 + lane;
   F inv = F::one();
   ZK_NOUNROLL for (uint32_t r = 0; r < S; r++) {
@@ -400,10 +400,14 @@ ZK_GLOBAL void k_msm_accumulate_affine(const Affine<F>* __restrict__ bases, cons
 
 // pass 4b: one thread per (row, bucket): empty buckets become infinity, buckets spread over several chunks are
 // summed from the partials those chunks left.
-template <class F>
-ZK_GLOBAL void k_msm_fixup(const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ counts, MsmShape s, uint32_t S,
+// BOUND = 1: registers capped for one more CTA per SM (G1: 136 -> 128 registers, 4 CTAs; G2: 252 -> 168, 3 CTAs)
+template <class F, int BOUND>
+// HEAVY buckets (a run crossing more than heavy_span chunks: the bits and small values of a large witness put 10^5 entries into
+// one bucket) are not summed by their one thread -- thousands of dependent additions, 8.6 ms of a 28 ms proof at 2^20 constraints --
+// but queued (heavy[0] = count, heavy[1 + i] = bucket id) for k_msm_fixup_heavy, one warp per bucket.  heavy == NULL: no queue.
+ZK_GLOBAL ZK_FIX_BOUNDS(F, BOUND) void k_msm_fixup(const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ counts, MsmShape s, uint32_t S,
                            uint32_t chunks_per_row, const Xyzz<F>* __restrict__ head, const Xyzz<F>* __restrict__ tail,
-                           Xyzz<F>* __restrict__ buckets) {
+                           Xyzz<F>* __restrict__ buckets, uint32_t heavy_span, uint32_t heavy_cap, uint32_t* __restrict__ heavy) {
   size_t tid = ZK_TID;
   if (tid >= (size_t)s.B * s.R * s.nb) return;
   size_t row = tid / s.nb;
@@ -411,12 +415,45 @@ ZK_GLOBAL void k_msm_fixup(const uint32_t* __restrict__ offsets, const uint32_t*
   if (cnt == 0) { buckets[tid] = Xyzz<F>::infinity(); return; }
   uint32_t c0 = st / S, c1 = (st + cnt - 1) / S;
   if (c0 == c1) return;  // written whole by its chunk
+  if (heavy && c1 - c0 > heavy_span) {
+    const uint32_t slot = ZK_ATOMIC_ADD(heavy, 1u);
+    if (slot < heavy_cap) { heavy[1 + slot] = (uint32_t)tid; return; }     // queue full: fall through and sum it here
+  }
   const Xyzz<F>* h = head + row * chunks_per_row;
   const Xyzz<F>* t = tail + row * chunks_per_row;
   Xyzz<F> acc = (st > c0 * S) ? t[c0] : h[c0];
   for (uint32_t ch = c0 + 1; ch <= c1; ch++) xyzz_add(acc, h[ch]);
   buckets[tid] = acc;
 }
+#ifndef ZKFL_EMUL
+// one WARP per queued heavy bucket: lane l sums the partials of chunks c0 + l, c0 + l + 32, ...; the 32 lane sums meet in a
+// shuffle tree (all lanes run the same additions, lane 0's result is the bucket)
+template <class F>
+static __global__ void k_msm_fixup_heavy(const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ counts, MsmShape s, uint32_t S,
+                                         uint32_t chunks_per_row, const Xyzz<F>* __restrict__ head, const Xyzz<F>* __restrict__ tail,
+                                         Xyzz<F>* __restrict__ buckets, uint32_t heavy_cap, const uint32_t* __restrict__ heavy) {
+  const uint32_t warp = (uint32_t)(ZK_TID >> 5), lane = threadIdx.x & 31u;
+  const uint32_t n_heavy = heavy[0] < heavy_cap ? heavy[0] : heavy_cap;
+  if (warp >= n_heavy) return;
+  const uint32_t id = heavy[1 + warp];
+  const size_t row = id / s.nb;
+  const uint32_t st = offsets[id], cnt = counts[id], c0 = st / S, c1 = (st + cnt - 1) / S;
+  const Xyzz<F>* h = head + row * chunks_per_row;
+  const Xyzz<F>* t = tail + row * chunks_per_row;
+  Xyzz<F> acc = Xyzz<F>::infinity();
+  for (uint32_t ch = c0 + lane; ch <= c1; ch += 32) {
+    const Xyzz<F>* p = (ch == c0 && st > c0 * S) ? t + c0 : h + ch;
+    xyzz_add(acc, *p);
+  }
+  ZK_NOUNROLL for (uint32_t off = 16; off >= 1; off >>= 1) {
+    Xyzz<F> o;
+    o.X = warp_shfl<ZK_SHFL_DOWN>(acc.X, off); o.Y = warp_shfl<ZK_SHFL_DOWN>(acc.Y, off);
+    o.ZZ = warp_shfl<ZK_SHFL_DOWN>(acc.ZZ, off); o.ZZZ = warp_shfl<ZK_SHFL_DOWN>(acc.ZZZ, off);
+    xyzz_add(acc, o);
+  }
+  if (lane == 0) buckets[id] = acc;
+}
+#endif
 // pass 5: bucket reduction S = sum_k (k+1) * X[k] over the nb buckets of a row, as a three-level tree so that the
 // serial depth is ~ 2*L1 + 2*L2 + 5*N2 additions instead of 2*sqrt(nb) + 3*sqrt(nb).
 // Level kernel: chunk t of L consecutive elements -> R_t = sum X, T_t = sum j * X[t*L + j] (zero-based local weights).
@@ -428,8 +465,8 @@ ZK_GLOBAL void k_msm_fixup(const uint32_t* __restrict__ offsets, const uint32_t*
 // addition against 0.75 ns for this call-based form: all variants sit at ~30 % of the multiplier rate because a thread is one long
 // chain of dependent additions at 2 warps per scheduler; concentrating the fix-up work in this low-occupancy kernel only made it
 // worse than leaving it in the massively parallel k_msm_fixup.  What would pay is fewer additions, not a different packaging.
-template <class F>
-ZK_GLOBAL void k_reduce_level(const Xyzz<F>* __restrict__ in, size_t rows, uint32_t N, uint32_t L, Xyzz<F>* __restrict__ R,
+template <class F, int BOUND>
+ZK_GLOBAL ZK_LVL_BOUNDS(F, BOUND) void k_reduce_level(const Xyzz<F>* __restrict__ in, size_t rows, uint32_t N, uint32_t L, Xyzz<F>* __restrict__ R,
                                    Xyzz<F>* __restrict__ T) {
   size_t tid = ZK_TID;
   uint32_t nchunk = N / L;

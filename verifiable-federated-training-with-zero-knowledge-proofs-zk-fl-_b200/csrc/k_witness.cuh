@@ -192,6 +192,21 @@ ZK_GLOBAL void k_build_abc(CsrDev A, CsrDev Bm, const Fr* __restrict__ w, Fr* __
   abc[(size_t)n * B + tid] = bv;
   abc[2 * (size_t)n * B + tid] = a * bv;
 }
+// K1 with the constraint check folded in (full-prove path): rows below n_rows are the circuit's constraints (the zkey's A / B
+// coefficient rows ARE the R1CS rows there; rows above only bind the public inputs), so A.w and B.w are computed once and only
+// C.w is extra work.  first_bad as in k_r1cs_check.
+ZK_GLOBAL void k_build_abc_check(CsrDev A, CsrDev Bm, CsrDev C, const Fr* __restrict__ w, Fr* __restrict__ abc, uint32_t n, uint32_t B,
+                                 uint32_t n_rows, uint32_t* __restrict__ first_bad) {
+  size_t tid = ZK_TID;
+  if (tid >= (size_t)n * B) return;
+  uint32_t row = (uint32_t)(tid / B), b = (uint32_t)(tid % B);
+  Fr a = csr_row(A, row, w, B, b), bv = csr_row(Bm, row, w, B, b);
+  const Fr ab = a * bv;
+  abc[tid] = a;
+  abc[(size_t)n * B + tid] = bv;
+  abc[2 * (size_t)n * B + tid] = ab;
+  if (row < n_rows && !(ab == csr_row(C, row, w, B, b))) ZK_ATOMIC_MIN(first_bad + b, row);
+}
 // constraint check (what a failing `===` is for circom): first violated row per client, or 0xFFFFFFFF
 ZK_GLOBAL void k_r1cs_check(CsrDev A, CsrDev Bm, CsrDev C, const Fr* __restrict__ w, uint32_t n_rows, uint32_t B,
                             uint32_t* __restrict__ first_bad) {

@@ -5,9 +5,11 @@
 
 uint32_t accumulate_chunk() { uint32_t S = env_u32("ZKFL_MSM_CHUNK", 32); return S < 4 ? 4 : S; }
 // shared = all windows of a proof accumulate into ONE bucket set (bases table precomputed with the window shifts)
-MsmShape msm_shape(uint32_t m, uint32_t B, bool shared, uint32_t force_c) {
+MsmShape msm_shape(uint32_t m, uint32_t B, bool shared, uint32_t force_c, uint32_t c_cap) {
   uint32_t best_c = 4; double best = 1e300;
-  const uint32_t c_max = shared ? 17 : 16;   // bucket keys are 16-bit: 2^(c-1) buckets <= 65536; per-window sets stop at 16
+  // one shared bucket set: up to 17 bits for proving keys (a split proof reduces the whole set on every rank, so it must stay small);
+  // the standalone MSM over a resident table passes c_cap = 20 (2^19 buckets); per-window sets stop at 16
+  const uint32_t c_max = c_cap ? c_cap : (shared ? 17 : 16);
   for (uint32_t c = 4; c <= c_max; c++) {
     double W = 254 / c + 1, nb = (double)(1u << (c - 1));
     double cost = shared ? W * (double)m + 2.6 * nb : W * ((double)m + 2.6 * nb);
@@ -52,7 +54,7 @@ int msm_sort(zkfl_ctx* c, const Fr* scalars, const uint8_t* skip, const MsmShape
   TRY(c->cursors.reserve(rows * s.nb * 4));
   TRY(c->chunk_sums.reserve(rows * nchunk * 4));
   TRY(c->sorted.reserve(rows * s.cap * 4));
-  TRY(c->skey.reserve(rows * s.cap * 2));
+  TRY(c->skey.reserve(rows * s.cap * sizeof(zk_key_t)));
 #ifndef ZKFL_EMUL
   // OPT-IN (ZKFL_MSM_SORT_CTA=1): one CTA per proof with the histogram in shared memory.  Measured on B200 at 1024 proofs: 8.6 ms per
   // sort against ~7 ms for the global-atomics passes below -- ~300 proofs are in flight at once, their 1.2 MB list regions no longer fit
@@ -62,7 +64,7 @@ int msm_sort(zkfl_ctx* c, const Fr* scalars, const uint8_t* skip, const MsmShape
     const size_t smem = ((size_t)s.nb + 32) * 4;
     if (!c->sort_attr) { CU(cudaFuncSetAttribute(k_msm_sort_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (32768 + 32) * 4)); c->sort_attr = true; }
     k_msm_sort_cta<<<(unsigned)rows, 1024, smem, c->stream>>>(scalars, skip, s, c->offsets[gen].as<uint32_t>(), c->counts[gen].as<uint32_t>(),
-                                                             c->sorted.as<uint32_t>(), c->skey.as<uint16_t>());
+                                                             c->sorted.as<uint32_t>(), c->skey.as<zk_key_t>());
     zkrt::note_launch("k_msm_sort_cta");
     if (zkrt::debug_sync()) zkrt::debug_check("k_msm_sort_cta", c->stream);
     CU(cudaGetLastError());
@@ -75,7 +77,7 @@ int msm_sort(zkfl_ctx* c, const Fr* scalars, const uint8_t* skip, const MsmShape
   ZK_LAUNCH(k_msm_scan_write, rows * nchunk, 128, c->stream, c->counts[gen].as<uint32_t>(), c->chunk_sums.as<uint32_t>(), s,
             c->offsets[gen].as<uint32_t>(), c->cursors.as<uint32_t>());
   ZK_LAUNCH(k_msm_scatter, (size_t)s.m * s.B, 256, c->stream, scalars, skip, s, c->cursors.as<uint32_t>(), c->sorted.as<uint32_t>(),
-            c->skey.as<uint16_t>());
+            c->skey.as<zk_key_t>());
   CU(cudaGetLastError());
   return 0;
 }

@@ -26,17 +26,38 @@ int msm_accumulate(zkfl_ctx* c, const Affine<F>* bases, const MsmShape& s, int s
     TRY(c->aff_pre.reserve(n_groups * 32 * sizeof(F)));
     Stage st(c, tag);
     ZK_LAUNCH(k_msm_accumulate_affine<F>, n_groups / K * 32, 128, c->stream, bases, c->sorted.as<uint32_t>(),
-              c->skey.as<uint16_t>(), offsets, counts, s, K, (uint32_t)rows,
+              c->skey.as<zk_key_t>(), offsets, counts, s, K, (uint32_t)rows,
               c->aff_acc.as<Affine<F>>(), c->aff_pre.as<F>(), c->buckets[slot].as<Xyzz<F>>(), head, tail);
   } else {
     Stage st(c, tag);
-    ZK_LAUNCH(k_msm_accumulate_chunks<F>, rows * cpr, 128, c->stream, bases, c->sorted.as<uint32_t>(), c->skey.as<uint16_t>(),
+    ZK_LAUNCH(k_msm_accumulate_chunks<F>, rows * cpr, 128, c->stream, bases, c->sorted.as<uint32_t>(), c->skey.as<zk_key_t>(),
               offsets, counts, s, S, cpr, c->buckets[slot].as<Xyzz<F>>(), head, tail);
   }
   {
     Stage st(c, "msm_fixup");
-    ZK_LAUNCH(k_msm_fixup<F>, rows * s.nb, 128, c->stream, offsets, counts, s, S, cpr, (const Xyzz<F>*)head, (const Xyzz<F>*)tail,
-              c->buckets[slot].as<Xyzz<F>>());
+    // heavy buckets (runs over more than 64 chunks) go to one warp each; the queue lives in the context (count + 4096 ids)
+    const uint32_t heavy_span = 64, heavy_cap = 4096;
+    uint32_t* heavy = nullptr;
+#ifndef ZKFL_EMUL
+    if (env_u32("ZKFL_FIXUP_HEAVY", 1) && rows <= 64 && rows * s.nb < 0xFFFFFFFFull) {   // few rows: single proofs, split proofs
+      TRY(c->heavy.reserve((heavy_cap + 1) * 4));
+      heavy = c->heavy.as<uint32_t>();
+      CU(cudaMemsetAsync(heavy, 0, 4, c->stream));
+    }
+#endif
+    if (env_u32("ZKFL_FIXUP_BOUND", 1))
+      ZK_LAUNCH((k_msm_fixup<F, 1>), rows * s.nb, 128, c->stream, offsets, counts, s, S, cpr, (const Xyzz<F>*)head, (const Xyzz<F>*)tail,
+                c->buckets[slot].as<Xyzz<F>>(), heavy_span, heavy_cap, heavy);
+    else
+      ZK_LAUNCH((k_msm_fixup<F, 0>), rows * s.nb, 128, c->stream, offsets, counts, s, S, cpr, (const Xyzz<F>*)head, (const Xyzz<F>*)tail,
+                c->buckets[slot].as<Xyzz<F>>(), heavy_span, heavy_cap, heavy);
+#ifndef ZKFL_EMUL
+    // the heavy count is only known on the device: a fixed grid of warps (idle ones exit at once) keeps the stream free of host round
+    // trips; large batches never queue (their rows are small circuits) and skip the launch
+    if (heavy)
+      ZK_LAUNCH(k_msm_fixup_heavy<F>, (size_t)heavy_cap * 32, 128, c->stream, offsets, counts, s, S, cpr, (const Xyzz<F>*)head, (const Xyzz<F>*)tail,
+                c->buckets[slot].as<Xyzz<F>>(), heavy_cap, (const uint32_t*)heavy);
+#endif
   }
   CU(cudaGetLastError());
   return 0;
@@ -72,9 +93,15 @@ int msm_reduce(zkfl_ctx* c, const MsmShape& s, int slot, Xyzz<F>* out, cudaStrea
     CU(cudaGetLastError());
     return 0;
   }
-  ZK_LAUNCH(k_reduce_level<F>, rows * p.N1, 64, stream, (const Xyzz<F>*)c->buckets[slot].as<Xyzz<F>>(), rows, s.nb, p.L1, R1, T1);
-  ZK_LAUNCH(k_reduce_level<F>, rows * p.N2, 64, stream, (const Xyzz<F>*)R1, rows, p.N1, p.L2, R2, T2);
-  ZK_LAUNCH(k_reduce_level<F>, rows * p.N2, 64, stream, (const Xyzz<F>*)T1, rows, p.N1, p.L2, RT, (Xyzz<F>*)nullptr);
+  if (env_u32("ZKFL_REDUCE_BOUND", 1)) {
+    ZK_LAUNCH((k_reduce_level<F, 1>), rows * p.N1, 64, stream, (const Xyzz<F>*)c->buckets[slot].as<Xyzz<F>>(), rows, s.nb, p.L1, R1, T1);
+    ZK_LAUNCH((k_reduce_level<F, 1>), rows * p.N2, 64, stream, (const Xyzz<F>*)R1, rows, p.N1, p.L2, R2, T2);
+    ZK_LAUNCH((k_reduce_level<F, 1>), rows * p.N2, 64, stream, (const Xyzz<F>*)T1, rows, p.N1, p.L2, RT, (Xyzz<F>*)nullptr);
+  } else {
+    ZK_LAUNCH((k_reduce_level<F, 0>), rows * p.N1, 64, stream, (const Xyzz<F>*)c->buckets[slot].as<Xyzz<F>>(), rows, s.nb, p.L1, R1, T1);
+    ZK_LAUNCH((k_reduce_level<F, 0>), rows * p.N2, 64, stream, (const Xyzz<F>*)R1, rows, p.N1, p.L2, R2, T2);
+    ZK_LAUNCH((k_reduce_level<F, 0>), rows * p.N2, 64, stream, (const Xyzz<F>*)T1, rows, p.N1, p.L2, RT, (Xyzz<F>*)nullptr);
+  }
   ZK_LAUNCH(k_reduce_final<F>, rows, 32, stream, (const Xyzz<F>*)R2, (const Xyzz<F>*)T2, (const Xyzz<F>*)RT, rows, p.N2, p.L1, p.L2,
             c->win[slot].as<Xyzz<F>>());
   ZK_LAUNCH(k_msm_combine<F>, s.B, 32, stream, c->win[slot].as<Xyzz<F>>(), s, out);

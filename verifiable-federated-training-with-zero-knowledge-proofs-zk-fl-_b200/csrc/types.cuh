@@ -29,8 +29,12 @@ static inline void zk_atomic_min_u32(uint32_t* p, uint32_t v) {
 #endif
 #if defined(__CUDACC__) && !defined(ZKFL_EMUL)
 #define ZK_ACC_BOUNDS(F) __launch_bounds__(128, sizeof(F) > 32 ? ZKFL_G2_MIN_CTAS : 4)
+#define ZK_FIX_BOUNDS(F, BOUND) __launch_bounds__(128, (BOUND) ? (sizeof(F) > 32 ? 3 : 4) : 1)
+#define ZK_LVL_BOUNDS(F, BOUND) __launch_bounds__(64, (BOUND) ? (sizeof(F) > 32 ? 6 : 8) : 1)
 #else
 #define ZK_ACC_BOUNDS(F)
+#define ZK_FIX_BOUNDS(F, BOUND)
+#define ZK_LVL_BOUNDS(F, BOUND)
 #endif
 
 struct PoseidonDev {
@@ -59,6 +63,8 @@ struct VkDev {
   G1Affine alpha1, beta1, delta1;
   G2Affine beta2, delta2;
 };
+typedef uint32_t zk_key_t;   // bucket index of a sorted entry (32 bits: the standalone MSM over resident bases uses up to 2^19 buckets)
+
 // Batched over B proofs that share the bases. Signed c-bit digits: W = 254/c + 1 windows,
 // nb = 2^(c-1) buckets per bucket set, row = b*R + (R == 1 ? 0 : j) identifies one bucket set.
 struct MsmShape {

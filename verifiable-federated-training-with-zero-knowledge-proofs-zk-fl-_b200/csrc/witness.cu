@@ -70,20 +70,28 @@ static int chk_reserve(zkfl_ctx* c, uint32_t B) {
   c->chk_host[0] = 0;
   return 0;
 }
-int check_r1cs_launch(zkfl_ctx* c, const zkfl_r1cs* r, uint32_t B) {
-  Stage st(c, "r1cs_check");
+// reserve + reset the per-instance verdicts (before the checking kernel), then queue their copy to pinned memory (after it)
+static int check_prepare(zkfl_ctx* c, uint32_t B) {
   const bool keep_flags = c->chk_wtns;
   const uint32_t flags = keep_flags ? c->chk_host[0] : 0;
   TRY(chk_reserve(c, B));
   if (keep_flags) c->chk_host[0] = flags;
   TRY(c->bad.reserve(((size_t)B + 1) * 4));
   CU(cudaMemsetAsync(c->bad.as<uint32_t>() + 1, 0xFF, (size_t)B * 4, c->stream));
-  ZK_LAUNCH(k_r1cs_check, (size_t)r->n_constraints * B, 128, c->stream, r->A.dev(), r->B.dev(), r->C.dev(), c->w.as<Fr>(),
-            r->n_constraints, B, c->bad.as<uint32_t>() + 1);
+  return 0;
+}
+static int check_collect(zkfl_ctx* c, uint32_t B) {
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(c->chk_host + 1, c->bad.as<uint32_t>() + 1, (size_t)B * 4, cudaMemcpyDeviceToHost, c->stream));
   c->chk_B = B;
   return 0;
+}
+int check_r1cs_launch(zkfl_ctx* c, const zkfl_r1cs* r, uint32_t B) {
+  Stage st(c, "r1cs_check");
+  TRY(check_prepare(c, B));
+  ZK_LAUNCH(k_r1cs_check, (size_t)r->n_constraints * B, 128, c->stream, r->A.dev(), r->B.dev(), r->C.dev(), c->w.as<Fr>(),
+            r->n_constraints, B, c->bad.as<uint32_t>() + 1);
+  return check_collect(c, B);
 }
 int check_wtns_launch(zkfl_ctx* c, uint32_t n_wires, uint32_t B) {
   TRY(chk_reserve(c, c->chk_B > B ? c->chk_B : B));
@@ -96,7 +104,7 @@ int check_wtns_launch(zkfl_ctx* c, uint32_t n_wires, uint32_t B) {
   return 0;
 }
 // call after the stream has been synchronised
-int checks_result(zkfl_ctx* c, uint32_t* first_bad) {
+int checks_result(zkfl_ctx* c, uint32_t* first_bad, uint32_t cap) {
   int rc = 0;
   if (c->chk_wtns) {
     c->chk_wtns = false;
@@ -108,7 +116,7 @@ int checks_result(zkfl_ctx* c, uint32_t* first_bad) {
     const uint32_t B = c->chk_B;
     c->chk_B = 0;
     uint32_t bad = 0;
-    for (uint32_t b = 0; b < B; b++) { if (first_bad) first_bad[b] = c->chk_host[1 + b]; if (c->chk_host[1 + b] != 0xFFFFFFFFu) bad++; }
+    for (uint32_t b = 0; b < B; b++) { if (first_bad && b < cap) first_bad[b] = c->chk_host[1 + b]; if (c->chk_host[1 + b] != 0xFFFFFFFFu) bad++; }
     if (bad && !rc) rc = fail(ZKFL_ERR_ASSERT, "Assert Failed: " + std::to_string(bad) + " of " + std::to_string(B) + " witnesses violate a constraint");
   }
   return rc;
@@ -116,13 +124,20 @@ int checks_result(zkfl_ctx* c, uint32_t* first_bad) {
 
 // A.w, B.w, C = A o B over the constraint domain, then 3 iNTT -> odd-coset shift -> 3 NTT -> A*B - C (snarkjs: buildABC1,
 // ifft x3, batchApplyKey, fft x3, joinABC); the witness is in c->w, the H-MSM scalars (canonical) land in c->hsc
-int run_h_poly(zkfl_ctx* c, const zkfl_zkey* z, uint32_t B) {
+int run_h_poly(zkfl_ctx* c, const zkfl_zkey* z, uint32_t B, const zkfl_r1cs* check) {
   const uint32_t n = z->domain;
   Fr* w = c->w.as<Fr>();
   TRY(c->abc.reserve(3 * (size_t)n * B * sizeof(Fr)));
   TRY(c->hsc.reserve((size_t)n * B * sizeof(Fr)));
   Fr* abc = c->abc.as<Fr>();
-  {
+  if (check) {       // full-prove: the constraint check rides on the A.w / B.w products (deferred verdict, see checks_result)
+    if (check->n_wires != z->n_vars || check->n_constraints > n) return fail(ZKFL_ERR_ARG, "r1cs does not match the proving key");
+    Stage st(c, "build_abc");
+    TRY(check_prepare(c, B));
+    ZK_LAUNCH(k_build_abc_check, (size_t)n * B, 128, c->stream, z->A.dev(), z->B.dev(), check->C.dev(), w, abc, n, B, check->n_constraints,
+              c->bad.as<uint32_t>() + 1);
+    TRY(check_collect(c, B));
+  } else {
     Stage st(c, "build_abc");
     ZK_LAUNCH(k_build_abc, (size_t)n * B, 128, c->stream, z->A.dev(), z->B.dev(), w, abc, n, B);
   }

@@ -91,10 +91,10 @@ static int finalize_from_sums(zkfl_ctx* c, const zkfl_zkey* z, const Fr* rs_dev,
 // part / nparts: this context handles the point range [part*m/nparts, (part+1)*m/nparts) of every MSM (nparts == 1: all).
 // finalize == false stops after the five MSM sums (res_g1 / res_g2).
 static int prove_from_device_witness(zkfl_ctx* c, const zkfl_zkey* z, const Fr* rs_dev, uint32_t B, uint32_t part = 0,
-                                     uint32_t nparts = 1, bool finalize = true) {
+                                     uint32_t nparts = 1, bool finalize = true, const zkfl_r1cs* check = nullptr) {
   const uint32_t n = z->domain, m = z->n_vars;
   Fr* w = c->w.as<Fr>();
-  TRY(run_h_poly(c, z, B));
+  TRY(run_h_poly(c, z, B, check));
   TRY(c->res_g1.reserve(4 * (size_t)B * sizeof(G1Xyzz)));
   TRY(c->res_g2.reserve((size_t)B * sizeof(G2Xyzz)));
   G1Xyzz* r1 = c->res_g1.as<G1Xyzz>();
@@ -539,6 +539,7 @@ int zkfl_wtns_calculate_batch(zkfl_ctx* c, const zkfl_circuit* k, const zkfl_r1c
   for (size_t i = 0; i < (size_t)B * k->n_inputs; i++)
     if (!fr_bytes_lt_mod(inputs + 32 * i)) return fail(ZKFL_ERR_ARG, "input not reduced mod r");
   CU(cudaSetDevice(c->device));
+  checks_reset(c);
   TRY(run_witness(c, k, inputs, (uint32_t)B));
   if (wtns_out) {
     TRY(c->aos.reserve((size_t)k->n_wires * B * sizeof(Fr)));
@@ -558,6 +559,7 @@ int zkfl_wtns_eval_wires(zkfl_ctx* c, const zkfl_circuit* k, const uint8_t* inpu
   for (size_t i = 0; i < (size_t)B * k->n_inputs; i++)
     if (!fr_bytes_lt_mod(inputs + 32 * i)) return fail(ZKFL_ERR_ARG, "input not reduced mod r");
   CU(cudaSetDevice(c->device));
+  checks_reset(c);
   TRY(run_witness(c, k, inputs, (uint32_t)B));
   TRY(c->bad.reserve((size_t)n_sel * 4));
   TRY(c->aos.reserve((size_t)n_sel * B * sizeof(Fr)));
@@ -570,6 +572,7 @@ int zkfl_wtns_eval_wires(zkfl_ctx* c, const zkfl_circuit* k, const uint8_t* inpu
 int zkfl_r1cs_check_batch(zkfl_ctx* c, const zkfl_r1cs* r, const uint8_t* wtns, int B, uint32_t* first_bad) {
   if (!c || !r || !wtns || B <= 0) return fail(ZKFL_ERR_ARG, "bad argument");
   CU(cudaSetDevice(c->device));
+  checks_reset(c);
   size_t cnt = (size_t)r->n_wires * B;
   TRY(c->aos.reserve(cnt * sizeof(Fr))); TRY(c->w.reserve(cnt * sizeof(Fr)));
   CU(cudaMemcpyAsync(c->aos.p, wtns, cnt * sizeof(Fr), cudaMemcpyDefault, c->stream));   // pageable, pinned or device memory
@@ -583,6 +586,7 @@ int zkfl_groth16_prove_batch(zkfl_ctx* c, const zkfl_zkey* z, const uint8_t* wtn
                              uint8_t* proofs_out, uint8_t* publics_out) {
   if (!c || !z || !wtns || !proofs_out || B <= 0) return fail(ZKFL_ERR_ARG, "bad argument");
   CU(cudaSetDevice(c->device));
+  checks_reset(c);
   size_t cnt = (size_t)z->n_vars * B;
   TRY(stage_rs(c, rs, B));
   {
@@ -597,7 +601,7 @@ int zkfl_groth16_prove_batch(zkfl_ctx* c, const zkfl_zkey* z, const uint8_t* wtn
   CU(cudaMemcpyAsync(proofs_out, c->proofs.p, (size_t)B * 256, cudaMemcpyDeviceToHost, c->stream));
   TRY(fetch_publics(c, z->n_public, (uint32_t)B, publics_out));
   CU(cudaStreamSynchronize(c->stream));
-  return checks_result(c, nullptr);
+  return checks_result(c, nullptr, 0);
 }
 static int validate_inputs(const uint8_t* inputs, size_t count) {
   for (size_t i = 0; i < count; i++)
@@ -615,14 +619,14 @@ int zkfl_groth16_full_prove_batch(zkfl_ctx* c, const zkfl_circuit* k, const zkfl
   if (r && r->n_wires != k->n_wires) return fail(ZKFL_ERR_ARG, "r1cs does not match circuit");
   TRY(validate_inputs(inputs, (size_t)B * k->n_inputs));
   CU(cudaSetDevice(c->device));
+  checks_reset(c);
   TRY(stage_rs(c, rs, B));
   TRY(run_witness(c, k, inputs, (uint32_t)B));
-  if (r) TRY(check_r1cs_launch(c, r, (uint32_t)B));
-  TRY(prove_from_device_witness(c, z, c->stage_rs.as<Fr>(), (uint32_t)B));
+  TRY(prove_from_device_witness(c, z, c->stage_rs.as<Fr>(), (uint32_t)B, 0, 1, true, r));
   CU(cudaMemcpyAsync(proofs_out, c->proofs.p, (size_t)B * 256, cudaMemcpyDeviceToHost, c->stream));
   TRY(fetch_publics(c, z->n_public, (uint32_t)B, publics_out));
   CU(cudaStreamSynchronize(c->stream));
-  int rc = checks_result(c, first_bad);
+  int rc = checks_result(c, first_bad, (uint32_t)B);
   if (rc) memset(proofs_out, 0, (size_t)B * 256);
   return rc;
 }
@@ -641,9 +645,9 @@ int zkfl_full_prove_run(zkfl_ctx* c, const zkfl_circuit* k, const zkfl_zkey* z, 
   if (!c || !k || !z || B <= 0) return fail(ZKFL_ERR_ARG, "bad argument");
   if (r && r->n_wires != k->n_wires) return fail(ZKFL_ERR_ARG, "r1cs does not match circuit");
   CU(cudaSetDevice(c->device));
+  checks_reset(c);
   TRY(run_witness(c, k, nullptr, (uint32_t)B));
-  if (r) TRY(check_r1cs_launch(c, r, (uint32_t)B));
-  TRY(prove_from_device_witness(c, z, c->stage_rs.as<Fr>(), (uint32_t)B));
+  TRY(prove_from_device_witness(c, z, c->stage_rs.as<Fr>(), (uint32_t)B, 0, 1, true, r));
   return 0;  // asynchronous: the caller brackets with its own events / zkfl_full_prove_fetch (which reports the check)
 }
 int zkfl_full_prove_fetch(zkfl_ctx* c, int B, uint8_t* proofs_out, uint32_t* first_bad) {
@@ -651,7 +655,7 @@ int zkfl_full_prove_fetch(zkfl_ctx* c, int B, uint8_t* proofs_out, uint32_t* fir
   CU(cudaSetDevice(c->device));
   if (proofs_out) CU(cudaMemcpyAsync(proofs_out, c->proofs.p, (size_t)B * 256, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
-  int rc = checks_result(c, first_bad);
+  int rc = checks_result(c, first_bad, (uint32_t)B);
   if (rc && proofs_out) memset(proofs_out, 0, (size_t)B * 256);
   return rc;
 }
@@ -661,6 +665,7 @@ int zkfl_groth16_msm_partials(zkfl_ctx* c, const zkfl_zkey* z, const uint8_t* wt
                               uint8_t* partials_out) {
   if (!c || !z || !partials_out || B <= 0 || nparts == 0 || part >= nparts) return fail(ZKFL_ERR_ARG, "bad argument");
   CU(cudaSetDevice(c->device));
+  checks_reset(c);
   size_t cnt = (size_t)z->n_vars * B;
   if (wtns) {
     TRY(c->aos.reserve(cnt * sizeof(Fr))); TRY(c->w.reserve(cnt * sizeof(Fr)));
@@ -680,7 +685,7 @@ int zkfl_groth16_msm_partials(zkfl_ctx* c, const zkfl_zkey* z, const uint8_t* wt
   TRY(msm_to_affine_canonical<Fq2>(c, c->res_g2.as<G2Xyzz>(), (size_t)B, (G2Affine*)(o + (size_t)B * 256)));
   CU(cudaMemcpyAsync(partials_out, o, (size_t)B * 384, cudaMemcpyDefault, c->stream));   // host or device buffer (NCCL exchanges device memory)
   CU(cudaStreamSynchronize(c->stream));
-  return checks_result(c, nullptr);
+  return checks_result(c, nullptr, 0);
 }
 int zkfl_groth16_finalize(zkfl_ctx* c, const zkfl_zkey* z, const uint8_t* partials, uint32_t nparts, const uint8_t* rs, int B,
                           uint8_t* proofs_out) {
@@ -713,7 +718,7 @@ static int msm_bases_upload(zkfl_ctx* c, const uint8_t* bases, size_t n, int gro
 }
 // the window-shifted table of a resident base set (zkfl_msm_bases_load builds it; the one-shot calls do not)
 static int msm_bases_build_table(zkfl_ctx* c, MsmBases* b) {
-  const uint32_t cw = msm_shape((uint32_t)b->n, 1, true, env_u32("ZKFL_MSM_C_TABLE", 0)).c, W = 254 / cw + 1;
+  const uint32_t cw = msm_shape((uint32_t)b->n, 1, true, env_u32("ZKFL_MSM_C_TABLE", 0), 20).c, W = 254 / cw + 1;
   TRY(b->table.reserve((size_t)W * b->n * (b->group == 1 ? 64 : 128)));
   if (b->group == 1) TRY(msm_precompute_windows<Fq>(c, b->pts.as<G1Affine>(), (uint32_t)b->n, cw, W, b->table.as<G1Affine>()));
   else TRY(msm_precompute_windows<Fq2>(c, b->pts.as<G2Affine>(), (uint32_t)b->n, cw, W, b->table.as<G2Affine>()));
@@ -737,7 +742,7 @@ int zkfl_msm_run(zkfl_ctx* c, void* handle, const uint8_t* scalars, size_t n, ui
   TRY(c->msm_sc.reserve(n * sizeof(Fr)));
   if (scalars) CU(cudaMemcpyAsync(c->msm_sc.p, scalars, n * sizeof(Fr), cudaMemcpyHostToDevice, c->stream));
   const bool tab = b->c_tab && n == b->n;      // the table is indexed j * n + i: whole base set only
-  MsmShape s = tab ? msm_shape((uint32_t)n, 1, true, b->c_tab) : msm_shape((uint32_t)n, 1, false);
+  MsmShape s = tab ? msm_shape((uint32_t)n, 1, true, b->c_tab, 20) : msm_shape((uint32_t)n, 1, false);
   { Stage st(c, "msm_sort"); TRY(msm_sort(c, c->msm_sc.as<Fr>(), nullptr, s)); }
   TRY(c->msm_out.reserve(sizeof(G2Xyzz) + sizeof(G2Affine)));
   uint8_t* o = c->msm_out.as<uint8_t>();
