@@ -556,8 +556,11 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clk,
             "roofline": mac_roofline("k_msm_accumulate_chunks<Fq> (4 launches per step: A, C, B1, H)", g1_pts * MAC_PER_G1_POINT, acc_ms, peaks, {
-                "traffic": traffic.get("g1_accumulate_dram_bytes_per_launch"), "traffic_source": traffic.get("source"),
-                "algorithmic_bytes_per_launch": traffic.get("g1_accumulate_algorithmic_bytes_per_launch"),
+                # per launch, like `achieved`: one A-query launch covers the B / lanes proofs of one context
+                "traffic": (traffic["g1_accumulate_dram_bytes_per_proof"] * (B // lanes)) if traffic else None,
+                "traffic_source": traffic.get("source"),
+                "algorithmic_bytes_per_launch": (traffic["g1_accumulate_algorithmic_bytes_per_proof"] * (B // lanes)) if traffic else None,
+                "proofs_per_launch": B // lanes,
                 "share_of_step": acc_ms / prof_step_ms, "share_of_main_stream": acc_ms / main_stream,
                 "peak_imad32_gops": peaks["imad32_per_s"] / 1e9, "modmul_per_s": peaks["modmul_per_s"],
                 "note": "MAC = 32x32->64 multiply-accumulate; algorithmic MAC = G1 points x 16 windows x 1360 (SURVEY 8d normalisation); "
