@@ -257,7 +257,7 @@ def bench_split(prover, torch, dist, rank, world, barrier, reps: int = 5, with_c
     zk = prover.new_zkey(cc, b"zkfl-bench-split")         # fixed seed: every rank derives the same (benchmark-only) key
     t_setup = time.perf_counter() - t0
     t0 = time.perf_counter()
-    Z = prover.load_zkey(zk)
+    Z = prover.load_zkey(zk, nparts=world)                 # window tables sized for a rank's share of the points
     circ = prover.load_circuit(cc, check_constraints=False)
     t_load = time.perf_counter() - t0
     packed = circ.pack_inputs([inp])

@@ -56,6 +56,10 @@ int zkfl_circuit_info(const zkfl_circuit* c, uint32_t info[4]);
 /* replaces snarkjs reading `<name>_final.zkey` in `groth16 prove` (tests/full_system_simulation.mjs:773-775);
  * parses the snarkjs layout and uploads coefficients and bases once */
 int zkfl_zkey_load(zkfl_ctx* ctx, const uint8_t* zkey, size_t len, zkfl_zkey** out);
+/* the same key for ONE proof split over nparts GPUs (zkfl_groth16_msm_partials, BASELINE.json configs[4]; the reference has no
+ * multi-GPU form: this is the north-star's "single large proofs split ... across GPUs"): window tables sized for a rank's share
+ * of the points, so that the per-rank bucket reduction shrinks with the number of ranks.  Proof bytes do not depend on it. */
+int zkfl_zkey_load_split(zkfl_ctx* ctx, const uint8_t* zkey, size_t len, uint32_t nparts, zkfl_zkey** out);
 void zkfl_zkey_free(zkfl_zkey* z);
 /* info[0..2] = n_vars, n_public, domain_size */
 int zkfl_zkey_info(const zkfl_zkey* z, uint32_t info[3]);

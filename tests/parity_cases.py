@@ -137,6 +137,41 @@ def case_prove(P, cc, ins, rs, seed=b"zkfl-test", python_verify=1):
     return zk, proofs, pubs
 
 
+def _twist_point_off_subgroup() -> bytes:
+    """128 bytes (x.c0, x.c1, y.c0, y.c1 little-endian): a point of the twist y^2 = x^3 + 3/(9+u) that is not in the order-r
+    subgroup (the cofactor is ~2^254, so the first point found on the curve is outside it; checked)."""
+    q = bn.Q
+
+    def fq2_pow(a, e):
+        r = bn.Fq2(1, 0)
+        while e:
+            if e & 1:
+                r = r * a
+            a = a * a
+            e >>= 1
+        return r
+
+    x0 = 1
+    while True:
+        x = bn.Fq2(x0, 1)
+        a = x * x * x + bn.B2
+        a1 = fq2_pow(a, (q - 3) // 4)                 # square root in Fq2 for q = 3 mod 4 (Adj, Rodriguez-Henriquez, alg. 9)
+        alpha = a1 * a1 * a
+        if not (fq2_pow(alpha, q) * alpha == bn.Fq2(q - 1, 0)):
+            xr = a1 * a
+            y = bn.Fq2(0, 1) * xr if alpha == bn.Fq2(q - 1, 0) else fq2_pow(alpha + bn.Fq2(1, 0), (q - 1) // 2) * xr
+            assert y * y == a
+            pt, acc, k = (x, y), None, bn.R
+            while k:                                 # r * P without reducing the scalar
+                if k & 1:
+                    acc = bn.ec_add(acc, pt)
+                pt = bn.ec_double(pt)
+                k >>= 1
+            assert acc is not None
+            return b"".join(v.to_bytes(32, "little") for v in (x.a, x.b, y.a, y.b))
+        x0 += 1
+
+
 def case_verify_batch(P, zk: bytes, proofs, pubs):
     """GPU (or emulated) batch verifier against the oracle's pairing check and the single-proof host verifier: the valid
     proofs, and a set of tampered / malformed ones."""
@@ -171,6 +206,40 @@ def case_verify_batch(P, zk: bytes, proofs, pubs):
         assert sj.groth16.verify(vkj, sig, pj) == got[k], k
     for k in (1, len(bad)):     # pure-Python pairing: slow, two items
         assert g16.verify(vko, ol.ints(mixed_pubs[k]), g16.proof_from_bytes(mixed_proofs[k])) == got[k]
+    # ---- the combined (random-linear-combination) check: settles a batch of valid proofs in one final exponentiation ...
+    import os
+    rlc_on = all(os.environ.get(k, d) == d for k, d in (("ZKFL_VERIFY_FLAT", "0"), ("ZKFL_VERIFY_COOP", "1"), ("ZKFL_VERIFY_RLC", "1")))
+
+    def settled_by_rlc(expect=True):
+        import ctypes
+        v = ctypes.c_int32(-1)
+        P._check(P.lib.zkfl_debug_read(P.ctx, b"v_last_rlc", ctypes.byref(v), 4))
+        return (v.value == 1) == expect if rlc_on else True          # the cross-check forms never use the combined check
+    assert settled_by_rlc(False)                                           # the mixed batch above fell back to per-proof verdicts
+    rep = 2 if n >= 2 else 4
+    assert P.verify_batch(vk, list(pubs) * rep, list(proofs) * rep) == [True] * (n * rep)
+    assert n * rep < 4 or settled_by_rlc()
+    # ... malformed items (A = infinity, coordinate >= q) stay out of the sums and come back False without spoiling the batch
+    mal = [bad[3], bad[5]]
+    got = P.verify_batch(vk, [b[0] for b in mal] + list(pubs) * rep, [b[1] for b in mal] + list(proofs) * rep)
+    assert got == [False, False] + [True] * (n * rep) and settled_by_rlc()
+    # ... a B on the twist but OUTSIDE the order-r subgroup makes the weighted sum meaningless: the subgroup test sends the batch
+    # to the per-proof form, whose verdict is the single-proof verifier's
+    off = _twist_point_off_subgroup()
+    odd = proofs[0][:64] + off + proofs[0][192:]
+    got = P.verify_batch(vk, [pubs[0]] + list(pubs) * rep, [odd] + list(proofs) * rep)
+    assert settled_by_rlc(False)
+    assert got == [sj.groth16.verify(vkj, formats.publics_bytes_to_json(pubs[0]), formats.proof_bytes_to_json(odd))] + [True] * (n * rep)
+    # ... and the thread-per-proof kernels (ZKFL_VERIFY_COOP=0) give the same verdicts as the lane-cooperative ones
+    prev = os.environ.get("ZKFL_VERIFY_COOP")
+    os.environ["ZKFL_VERIFY_COOP"] = "0"
+    try:
+        assert P.verify_batch(vk, mixed_pubs, mixed_proofs) == [False] * len(bad) + [True] * n
+    finally:
+        if prev is None:
+            del os.environ["ZKFL_VERIFY_COOP"]
+        else:
+            os.environ["ZKFL_VERIFY_COOP"] = prev
     # snarkjs-shaped entry point, including items it cannot even encode
     items = [(formats.publics_bytes_to_json(q), formats.proof_bytes_to_json(p)) for p, q in zip(proofs, pubs)]
     items.append((items[0][0][:-1], items[0][1]))                                             # one signal missing

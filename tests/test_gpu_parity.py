@@ -248,6 +248,10 @@ def test_split_msm_partials_single_gpu(gpu_prover):
         got = gpu_prover.finalize(Z, parts, 2, rs)
         assert got == [ol.groth16_prove(zk, w, *r)[0] for w, r in zip(ws, rs)], nparts
     Z.close()
+    Z = gpu_prover.load_zkey(zk, nparts=8)        # zkfl_zkey_load_split: smaller windows, same proof bytes
+    parts = [gpu_prover.msm_partials(Z, ws, r, 8) for r in range(8)]
+    assert gpu_prover.finalize(Z, parts, 2, rs) == got
+    Z.close()
     circ.close()
 
 
@@ -342,6 +346,12 @@ def test_scaled_training_circuit_2pow20_single_proof_and_split(gpu_prover):
     assert proofs[0] == ref_p and pubs[0] == ref_pub
     parts = [gpu_prover.msm_partials(Z, ws, r, 8) for r in range(8)]
     assert gpu_prover.finalize(Z, parts, 1, [(3, 4)]) == [ref_p]
+    Z.close()
+    Z = gpu_prover.load_zkey(zk, nparts=8)        # the key as the 8 ranks load it (zkfl_zkey_load_split)
+    t = time.time()
+    parts = [gpu_prover.msm_partials(Z, ws, r, 8) for r in range(8)]
+    assert gpu_prover.finalize(Z, parts, 1, [(3, 4)]) == [ref_p]
+    print(f"8 emulated ranks with the split key: {time.time() - t:.3f} s")
     sig = formats.publics_bytes_to_json(pubs[0])
     assert sj.groth16.verify(formats.export_verification_key(zk), sig, formats.proof_bytes_to_json(proofs[0]))
     Z.close()

@@ -28,7 +28,7 @@ def _worker(rank, world, port, q):
         cc = pc.tiny_circuit()
         circ = P.load_circuit(cc)
         zk = open(os.path.join(ROOT, "tests", "golden", "tiny.zkey"), "rb").read()
-        Z = P.load_zkey(zk)
+        Z = P.load_zkey(zk, nparts=world)      # zkfl_zkey_load_split: window tables sized for a rank's share
         ins = pc.tiny_inputs()
         rs = [(11, 22), (33, 44), (55, 66)]
         assert sharding.shard_indices(5, rank, world) == ([0, 2, 4] if rank == 0 else [1, 3])

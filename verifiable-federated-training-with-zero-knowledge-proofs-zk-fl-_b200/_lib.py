@@ -14,7 +14,7 @@ DEFAULT_PATH = os.path.join(_HERE, "libzkfl.so")
 
 SYMBOLS = [
     "zkfl_last_error", "zkfl_version", "zkfl_ctx_create", "zkfl_ctx_free", "zkfl_circuit_load",
-    "zkfl_circuit_free", "zkfl_circuit_info", "zkfl_zkey_load", "zkfl_zkey_free", "zkfl_zkey_info",
+    "zkfl_circuit_free", "zkfl_circuit_info", "zkfl_zkey_load", "zkfl_zkey_load_split", "zkfl_zkey_free", "zkfl_zkey_info",
     "zkfl_r1cs_load", "zkfl_r1cs_free", "zkfl_wtns_calculate_batch", "zkfl_r1cs_check_batch", "zkfl_wtns_eval_wires",
     "zkfl_groth16_prove_batch", "zkfl_groth16_full_prove_batch", "zkfl_full_prove_stage",
     "zkfl_full_prove_run", "zkfl_full_prove_fetch", "zkfl_g1_msm", "zkfl_g2_msm", "zkfl_msm_bases_load",
@@ -57,7 +57,7 @@ def load(path: str | None = None):
         "zkfl_ctx_create": (i, [i, pp]), "zkfl_ctx_free": (None, [vp]),
         "zkfl_circuit_load": (i, [vp, vp, sz, pp]), "zkfl_circuit_free": (None, [vp]),
         "zkfl_circuit_info": (i, [vp, u32p]),
-        "zkfl_zkey_load": (i, [vp, vp, sz, pp]), "zkfl_zkey_free": (None, [vp]), "zkfl_zkey_info": (i, [vp, u32p]),
+        "zkfl_zkey_load": (i, [vp, vp, sz, pp]), "zkfl_zkey_load_split": (i, [vp, vp, sz, ctypes.c_uint32, pp]), "zkfl_zkey_free": (None, [vp]), "zkfl_zkey_info": (i, [vp, u32p]),
         "zkfl_r1cs_load": (i, [vp, vp, sz, pp]), "zkfl_r1cs_free": (None, [vp]),
         "zkfl_wtns_calculate_batch": (i, [vp, vp, vp, vp, i, vp, vp]),
         "zkfl_r1cs_check_batch": (i, [vp, vp, vp, i, vp]),

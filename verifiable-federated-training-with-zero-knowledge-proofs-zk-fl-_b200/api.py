@@ -77,10 +77,14 @@ class Circuit:
 
 
 class Zkey:
-    def __init__(self, prover: "Prover", data: bytes):
+    def __init__(self, prover: "Prover", data: bytes, nparts: int = 1):
+        """nparts > 1: key for one proof split over that many GPUs (window tables sized for a rank's share of the points)"""
         self.prover = prover
         self.handle = ctypes.c_void_p()
-        prover._check(prover.lib.zkfl_zkey_load(prover.ctx, _lib.as_ptr(data), len(data), ctypes.byref(self.handle)))
+        if nparts > 1:
+            prover._check(prover.lib.zkfl_zkey_load_split(prover.ctx, _lib.as_ptr(data), len(data), nparts, ctypes.byref(self.handle)))
+        else:
+            prover._check(prover.lib.zkfl_zkey_load(prover.ctx, _lib.as_ptr(data), len(data), ctypes.byref(self.handle)))
         info = (ctypes.c_uint32 * 3)()
         prover._check(prover.lib.zkfl_zkey_info(self.handle, info))
         self.n_vars, self.n_public, self.domain = info[0], info[1], info[2]
@@ -116,8 +120,8 @@ class Prover:
         r1cs = open(r1cs_path, "rb").read() if r1cs_path and os.path.exists(r1cs_path) else None
         return Circuit(self, zkwp, r1cs)
 
-    def load_zkey(self, data: bytes) -> Zkey:
-        return Zkey(self, data)
+    def load_zkey(self, data: bytes, nparts: int = 1) -> Zkey:
+        return Zkey(self, data, nparts)
 
     def new_zkey(self, r1cs, seed: bytes | None = None) -> bytes:
         """r1cs: `.r1cs` bytes or a CompiledCircuit.  seed=None (the default, what every non-test caller should use): the toxic

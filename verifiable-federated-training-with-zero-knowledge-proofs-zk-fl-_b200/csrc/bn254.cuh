@@ -411,11 +411,24 @@ struct alignas(16) Fq2 {
   friend ZK_HD Fq2 operator-(const Fq2& x, const Fq2& y) { Fq2 r; r.a = x.a - y.a; r.b = x.b - y.b; return r; }
   ZK_HD Fq2 neg() const { Fq2 r; r.a = a.neg(); r.b = b.neg(); return r; }
   ZK_HD Fq2 dbl() const { Fq2 r; r.a = a.dbl(); r.b = b.dbl(); return r; }
+  // ZKFL_FQ2_OPS_AS_ONE_CALL (set by verify.cu): the generic product / square are the one-call forms below, whose three (two)
+  // inlined Fq products interleave -- the verifier's kernels are serial chains on nearly idle SMs, where three back-to-back
+  // Fq calls cost three full product latencies (~1 500 cycles each)
   friend ZK_HD Fq2 operator*(const Fq2& x, const Fq2& y) {
+#if defined(ZKFL_FQ2_OPS_AS_ONE_CALL) && defined(__CUDA_ARCH__)   // device code of that unit only
+    return mul_call2(x, y);
+#else
     Fq aa = x.a * y.a, bb = x.b * y.b, s = (x.a + x.b) * (y.a + y.b);
     Fq2 r; r.a = aa - bb; r.b = s - aa - bb; return r;
+#endif
   }
-  ZK_HD Fq2 sqr() const { Fq t = a * b; Fq2 r; r.a = (a + b) * (a - b); r.b = t.dbl(); return r; }
+  ZK_HD Fq2 sqr() const {
+#if defined(ZKFL_FQ2_OPS_AS_ONE_CALL) && defined(__CUDA_ARCH__)   // device code of that unit only
+    return sqr_call2(*this);
+#else
+    Fq t = a * b; Fq2 r; r.a = (a + b) * (a - b); r.b = t.dbl(); return r;
+#endif
+  }
   static ZK_HD Fq2 sqr_hot(const Fq2& x) {   // (a + b)(a - b) + 2ab u: two products instead of three
 #if !defined(ZKFL_FQ2_PER_FQ_CALLS) && !defined(ZKFL_LAZY_REDUCTION)
     if (true) return sqr_call2(x);

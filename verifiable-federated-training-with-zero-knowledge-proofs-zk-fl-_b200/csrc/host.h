@@ -71,6 +71,7 @@ struct zkfl_ctx {
   DevBuf head[5], tail[5];   // chunk partials per MSM slot (read by that slot's reduction on its side stream)
   DevBuf heavy;              // queue of heavy buckets of the current fix-up (count, then bucket ids)
   DevBuf v_ic, v_pub, v_proofs, v_t, v_g1, v_g2, v_flags, v_f, v_halves, v_ok;   // batch verifier
+  DevBuf v_lines, v_rho, v_cps, v_sum[2], v_s, v_spart, v_tmul, v_sub, v_tree[2], v_misc;   // lane-cooperative / batched (RLC) verifier
   DevBuf aff_acc, aff_pre;   // batch-affine accumulation: running affine sums and prefix products, [slot group][lane]
   // five MSMs per proof batch (A, C, B1, H on G1; B2 on G2): own bucket / reduction buffers each, so the
   // latency-bound bucket reduction of one MSM runs on `side` while the next MSM accumulates on `stream`
@@ -87,6 +88,13 @@ struct zkfl_ctx {
   uint32_t chk_B = 0;        // instances covered by the pending constraint check (0: none pending)
   bool chk_wtns = false;     // a witness well-formedness check is pending
   uint32_t w_wires = 0, w_B = 0;   // shape of the witness run_witness left in `w` (0: none)
+  // per-key precomputations of the batch verifier, kept for the last four verification keys seen (a round alternates between
+  // the three circuits' keys): byte-window tables of IC_0..IC_l and alpha (fixed-base scalar multiplications in 32 mixed
+  // additions) and the Miller line tables of gamma, delta, beta
+  struct VkCacheEntry { std::vector<uint8_t> key; DevBuf tabs, lines; uint64_t stamp = 0; };
+  VkCacheEntry vk_cache[4];
+  uint64_t vk_stamp = 0;
+  int v_last_rlc = 0;        // 1 when the last zkfl_groth16_verify_batch was settled by the combined (random-linear-combination) check
   bool sort_attr = false;    // k_msm_sort_cta has been granted its dynamic shared memory on this device
   DevBuf msm_sc, msm_out, mask_w, mask_wb, mask_h, part_out, part_in;
   cudaEvent_t t0 = nullptr, t1 = nullptr, ev_join = nullptr;

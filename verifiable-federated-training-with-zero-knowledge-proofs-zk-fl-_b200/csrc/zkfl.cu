@@ -424,8 +424,10 @@ int zkfl_r1cs_load(zkfl_ctx* c, const uint8_t* d, size_t len, zkfl_r1cs** out) {
 void zkfl_r1cs_free(zkfl_r1cs* r) { if (r) { cudaSetDevice(r->ctx->device); delete r; } }
 
 // ---- zkey
-int zkfl_zkey_load(zkfl_ctx* c, const uint8_t* d, size_t len, zkfl_zkey** out) {
-  if (!c || !out) return fail(ZKFL_ERR_ARG, "bad argument");
+// nparts > 1: the key will prove ONE proof split over nparts GPUs (zkfl_groth16_msm_partials): every rank accumulates 1 / nparts
+// of the points but reduces a whole bucket set, so the window tables are sized for the rank's share (fewer, smaller bucket sets)
+static int zkey_load_impl(zkfl_ctx* c, const uint8_t* d, size_t len, uint32_t nparts, zkfl_zkey** out) {
+  if (!c || !out || nparts == 0) return fail(ZKFL_ERR_ARG, "bad argument");
   std::map<uint32_t, Sec> S;
   TRY(parse_sections(d, len, "zkey", S));
   for (uint32_t id : {1u, 2u, 4u, 5u, 6u, 7u, 8u, 9u}) if (!S.count(id)) return fail(ZKFL_ERR_FORMAT, "zkey: missing section");
@@ -472,8 +474,8 @@ int zkfl_zkey_load(zkfl_ctx* c, const uint8_t* d, size_t len, zkfl_zkey** out) {
   coo_to_csr(n, rows[1], wires[1], coefs[1], hB);
   TRY(upload_csr(c, hA, z->A)); TRY(upload_csr(c, hB, z->B));
   // bases -> window-shifted tables 2^(c*j) * P_i (built on the device once per key)
-  z->c_w = msm_shape(m, 1, true, env_u32("ZKFL_MSM_C_W", 0)).c;   // tuning knobs; 0 = cost model
-  z->c_h = msm_shape(n, 1, true, env_u32("ZKFL_MSM_C_H", 0)).c;
+  z->c_w = msm_shape(m / nparts + 1, 1, true, env_u32("ZKFL_MSM_C_W", 0)).c;   // tuning knobs; 0 = cost model
+  z->c_h = msm_shape(n / nparts + 1, 1, true, env_u32("ZKFL_MSM_C_H", 0)).c;
   auto build_table = [&](const uint8_t* pts, size_t bytes, uint32_t cnt, uint32_t cw, bool g2, DevBuf& out) -> int {
     DevBuf raw;
     TRY(upload(c, raw, pts, bytes));
@@ -524,6 +526,8 @@ int zkfl_zkey_load(zkfl_ctx* c, const uint8_t* d, size_t len, zkfl_zkey** out) {
   *out = z.release();
   return 0;
 }
+int zkfl_zkey_load(zkfl_ctx* c, const uint8_t* d, size_t len, zkfl_zkey** out) { return zkey_load_impl(c, d, len, 1, out); }
+int zkfl_zkey_load_split(zkfl_ctx* c, const uint8_t* d, size_t len, uint32_t nparts, zkfl_zkey** out) { return zkey_load_impl(c, d, len, nparts, out); }
 void zkfl_zkey_free(zkfl_zkey* z) { if (z) { cudaSetDevice(z->ctx->device); delete z; } }
 int zkfl_zkey_info(const zkfl_zkey* z, uint32_t info[3]) {
   if (!z || !info) return fail(ZKFL_ERR_ARG, "bad argument");
@@ -718,7 +722,11 @@ static int msm_bases_upload(zkfl_ctx* c, const uint8_t* bases, size_t n, int gro
 }
 // the window-shifted table of a resident base set (zkfl_msm_bases_load builds it; the one-shot calls do not)
 static int msm_bases_build_table(zkfl_ctx* c, MsmBases* b) {
-  const uint32_t cw = msm_shape((uint32_t)b->n, 1, true, env_u32("ZKFL_MSM_C_TABLE", 0), 20).c, W = 254 / cw + 1;
+  // window bits of the table: measured on B200 at 2^20 points (tests/dev/msm_c_sweep.py): c = 16 / 17 / 19 / 20 -> 4.11 / 3.88 / 4.36 /
+  // 4.11 ms -- beyond 17 bits the single-row sort and the 3 additions per bucket of the latency reduction cost more than the saved
+  // windows, so the cost model is capped at 17; ZKFL_MSM_C_TABLE forces any width up to 20
+  const uint32_t c_forced = env_u32("ZKFL_MSM_C_TABLE", 0);
+  const uint32_t cw = msm_shape((uint32_t)b->n, 1, true, c_forced, c_forced ? 20 : 17).c, W = 254 / cw + 1;
   TRY(b->table.reserve((size_t)W * b->n * (b->group == 1 ? 64 : 128)));
   if (b->group == 1) TRY(msm_precompute_windows<Fq>(c, b->pts.as<G1Affine>(), (uint32_t)b->n, cw, W, b->table.as<G1Affine>()));
   else TRY(msm_precompute_windows<Fq2>(c, b->pts.as<G2Affine>(), (uint32_t)b->n, cw, W, b->table.as<G2Affine>()));
