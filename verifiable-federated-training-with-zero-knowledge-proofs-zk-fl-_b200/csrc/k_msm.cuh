@@ -83,7 +83,8 @@ ZK_GLOBAL void k_msm_scan_write(const uint32_t* __restrict__ counts, const uint3
   }
 }
 // pass 3: scatter point references into bucket order. sorted: [B*W][cap], entry = point | sign << 31;
-// skey: the bucket index of every entry (lets pass 4 walk the list in fixed-size chunks)
+// skey (may be NULL): the bucket index of every entry -- only the batch-affine accumulation reads it; the chunk kernel finds its
+// runs from the offsets, which saves the second scattered store per entry (measured: the stores, not the atomics, bound this pass)
 ZK_GLOBAL void k_msm_scatter(const Fr* __restrict__ scalars, const uint8_t* __restrict__ skip, MsmShape s,
                              uint32_t* __restrict__ cursors, uint32_t* __restrict__ sorted, zk_key_t* __restrict__ skey) {
   size_t tid = ZK_TID;
@@ -102,7 +103,7 @@ ZK_GLOBAL void k_msm_scatter(const Fr* __restrict__ scalars, const uint8_t* __re
     uint32_t ref = s.R == 1 ? j * s.m + i : i;
     const size_t at = (size_t)row * s.cap + msm_list_index(s, pos);
     sorted[at] = ref | (d < 0 ? 0x80000000u : 0u);
-    skey[at] = (zk_key_t)(mag - 1);
+    if (skey) skey[at] = (zk_key_t)(mag - 1);
   }
 }
 #ifndef ZKFL_EMUL
@@ -170,7 +171,7 @@ static __global__ void __launch_bounds__(1024) k_msm_sort_cta(const Fr* __restri
       const uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
       const uint32_t at = msm_list_index(s, atomicAdd(cnt + (mag - 1), 1u));
       list[at] = (j * s.m + i) | (d < 0 ? 0x80000000u : 0u);
-      keys[at] = (zk_key_t)(mag - 1);
+      if (skey) keys[at] = (zk_key_t)(mag - 1);
     }
   }
 }
@@ -197,32 +198,35 @@ ZK_GLOBAL ZK_ACC_BOUNDS(F) void k_msm_accumulate_chunks(const Affine<F>* __restr
   if (pos0 >= total) return;
   uint32_t pos1 = pos0 + S < total ? pos0 + S : total;
   const uint32_t* list = sorted + row * s.cap;
-  const zk_key_t* keys = skey + row * s.cap;
-  uint32_t cur = keys[msm_list_index(s, pos0)];
+  // the run containing pos0: the last bucket whose offset is <= pos0 (offsets are exclusive prefix sums, so among buckets sharing
+  // an offset the last one is the non-empty one); binary search over the row's nb offsets
+  uint32_t lo = 0, hi = s.nb;                       // invariant: off[lo] <= pos0, (hi == nb or off[hi] > pos0)
+  while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (off[mid] <= pos0) lo = mid; else hi = mid; }
+  uint32_t cur = lo, run_end = off[cur] + cnt[cur];
   bool first = true;
   Xyzz<F> acc = Xyzz<F>::infinity();
-  // one entry of lookahead: the next key / list word are loaded, and the next base prefetched, while this entry's mixed add runs
-  uint32_t k_next = cur, e_next = list[msm_list_index(s, pos0)], e_next2 = 0;
+  // one entry of lookahead: the next list word is loaded, and the next base prefetched, while this entry's mixed add runs
+  uint32_t e_next = list[msm_list_index(s, pos0)], e_next2 = 0;
   if (pos0 + 1 < pos1) e_next2 = list[msm_list_index(s, pos0 + 1)];
   for (uint32_t pos = pos0; pos < pos1; pos++) {
-    const uint32_t k = k_next, e = e_next;
+    const uint32_t e = e_next;
     e_next = e_next2;
     if (pos + 1 < pos1) {
       ZK_PREFETCH(bases + (e_next & 0x7FFFFFFFu));
-      k_next = keys[msm_list_index(s, pos + 1)];
       if (pos + 2 < pos1) e_next2 = list[msm_list_index(s, pos + 2)];
     }
-    if (k != cur) {
+    if (pos == run_end) {
       // the run of bucket `cur` ends inside this chunk; it is whole unless it began in an earlier chunk
       if (first && off[cur] < pos0) head[tid] = acc; else buckets[row * s.nb + cur] = acc;
       acc = Xyzz<F>::infinity();
-      cur = k;
+      do { cur++; } while (cnt[cur] == 0);           // pos < total: a later non-empty bucket exists
+      run_end = off[cur] + cnt[cur];
       first = false;
     }
     xyzz_madd(acc, bases[e & 0x7FFFFFFFu], (e >> 31) != 0);
   }
   bool starts_here = !(first && off[cur] < pos0);
-  bool ends_here = off[cur] + cnt[cur] <= pos1;
+  bool ends_here = run_end <= pos1;
   if (starts_here && ends_here) buckets[row * s.nb + cur] = acc;
   else if (first) head[tid] = acc;   // run covers the chunk's first entry (possibly the whole chunk)
   else tail[tid] = acc;              // run started here and continues in the next chunk
@@ -401,10 +405,14 @@ ZK_GLOBAL void k_msm_accumulate_affine(const Affine<F>* __restrict__ bases, cons
 // pass 4b: one thread per (row, bucket): empty buckets become infinity, buckets spread over several chunks are
 // summed from the partials those chunks left.
 // BOUND = 1: registers capped for one more CTA per SM (G1: 136 -> 128 registers, 4 CTAs; G2: 252 -> 168, 3 CTAs)
+// HEAVY buckets (a run crossing more than heavy_span chunks: the bits and small values of a large witness put 10^5 entries -- more
+// than 10^4 chunks -- into the bucket of digit 1) are not summed by their one thread, thousands of dependent additions (8.6 ms of a
+// 28 ms proof at 2^20 constraints), but cut into SEGMENTS of ZK_HEAVY_SEG chunks and queued: heavy[0] = slots used, then per slot
+// four words (bucket id, segment, segments of the bucket, first slot of the bucket).  k_msm_fixup_heavy sums one segment per warp
+// (phase 0) and then the segment sums of one bucket per warp (phase 1): ~2 * (8 + 5) dependent additions whatever the bucket size.
+// heavy == NULL: no queue.  A bucket that does not fit the queue is summed here after all.
+#define ZK_HEAVY_SEG 256u
 template <class F, int BOUND>
-// HEAVY buckets (a run crossing more than heavy_span chunks: the bits and small values of a large witness put 10^5 entries into
-// one bucket) are not summed by their one thread -- thousands of dependent additions, 8.6 ms of a 28 ms proof at 2^20 constraints --
-// but queued (heavy[0] = count, heavy[1 + i] = bucket id) for k_msm_fixup_heavy, one warp per bucket.  heavy == NULL: no queue.
 ZK_GLOBAL ZK_FIX_BOUNDS(F, BOUND) void k_msm_fixup(const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ counts, MsmShape s, uint32_t S,
                            uint32_t chunks_per_row, const Xyzz<F>* __restrict__ head, const Xyzz<F>* __restrict__ tail,
                            Xyzz<F>* __restrict__ buckets, uint32_t heavy_span, uint32_t heavy_cap, uint32_t* __restrict__ heavy) {
@@ -416,8 +424,16 @@ ZK_GLOBAL ZK_FIX_BOUNDS(F, BOUND) void k_msm_fixup(const uint32_t* __restrict__ 
   uint32_t c0 = st / S, c1 = (st + cnt - 1) / S;
   if (c0 == c1) return;  // written whole by its chunk
   if (heavy && c1 - c0 > heavy_span) {
-    const uint32_t slot = ZK_ATOMIC_ADD(heavy, 1u);
-    if (slot < heavy_cap) { heavy[1 + slot] = (uint32_t)tid; return; }     // queue full: fall through and sum it here
+    const uint32_t nseg = (c1 - c0 + ZK_HEAVY_SEG) / ZK_HEAVY_SEG;          // ceil((c1 - c0 + 1) / SEG)
+    const uint32_t slot0 = ZK_ATOMIC_ADD(heavy, nseg);
+    if (slot0 + nseg <= heavy_cap) {
+      for (uint32_t g = 0; g < nseg; g++) {
+        uint32_t* q = heavy + 4 + 4 * (size_t)(slot0 + g);
+        q[0] = (uint32_t)tid; q[1] = g; q[2] = nseg; q[3] = slot0;
+      }
+      return;
+    }
+    // queue full (the count stays above heavy_cap, which k_msm_fixup_heavy clamps): fall through and sum it here
   }
   const Xyzz<F>* h = head + row * chunks_per_row;
   const Xyzz<F>* t = tail + row * chunks_per_row;
@@ -426,24 +442,35 @@ ZK_GLOBAL ZK_FIX_BOUNDS(F, BOUND) void k_msm_fixup(const uint32_t* __restrict__ 
   buckets[tid] = acc;
 }
 #ifndef ZKFL_EMUL
-// one WARP per queued heavy bucket: lane l sums the partials of chunks c0 + l, c0 + l + 32, ...; the 32 lane sums meet in a
-// shuffle tree (all lanes run the same additions, lane 0's result is the bucket)
+// one WARP per queue slot.  phase 0: lane l sums the partials of the slot's segment, chunks c0 + seg * SEG + l, + 32, ...; the 32 lane
+// sums meet in a shuffle tree (all lanes run the same additions, lane 0 holds the result) -> hsum[slot].  phase 1 (slots with
+// segment 0 only): the same over the bucket's segment sums -> buckets[id].
 template <class F>
 static __global__ void k_msm_fixup_heavy(const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ counts, MsmShape s, uint32_t S,
                                          uint32_t chunks_per_row, const Xyzz<F>* __restrict__ head, const Xyzz<F>* __restrict__ tail,
-                                         Xyzz<F>* __restrict__ buckets, uint32_t heavy_cap, const uint32_t* __restrict__ heavy) {
+                                         Xyzz<F>* __restrict__ buckets, uint32_t heavy_cap, const uint32_t* __restrict__ heavy,
+                                         Xyzz<F>* __restrict__ hsum, int phase) {
   const uint32_t warp = (uint32_t)(ZK_TID >> 5), lane = threadIdx.x & 31u;
-  const uint32_t n_heavy = heavy[0] < heavy_cap ? heavy[0] : heavy_cap;
-  if (warp >= n_heavy) return;
-  const uint32_t id = heavy[1 + warp];
-  const size_t row = id / s.nb;
-  const uint32_t st = offsets[id], cnt = counts[id], c0 = st / S, c1 = (st + cnt - 1) / S;
-  const Xyzz<F>* h = head + row * chunks_per_row;
-  const Xyzz<F>* t = tail + row * chunks_per_row;
+  // slots are handed out in whole buckets: the last bucket that asked may not have fitted; every slot below its slot0 is valid.
+  // A slot is valid iff its record says so: records are written only by buckets that fitted, stale ones are cleared by the host memset.
+  if (warp >= heavy_cap) return;
+  const uint32_t* q = heavy + 4 + 4 * (size_t)warp;
+  const uint32_t id = q[0], seg = q[1], nseg = q[2], slot0 = q[3];
+  if (nseg == 0) return;                                    // unused slot
+  if (phase == 1 && seg != 0) return;
   Xyzz<F> acc = Xyzz<F>::infinity();
-  for (uint32_t ch = c0 + lane; ch <= c1; ch += 32) {
-    const Xyzz<F>* p = (ch == c0 && st > c0 * S) ? t + c0 : h + ch;
-    xyzz_add(acc, *p);
+  if (phase == 0) {
+    const size_t row = id / s.nb;
+    const uint32_t st = offsets[id], cnt = counts[id], c0 = st / S, c1 = (st + cnt - 1) / S;
+    const Xyzz<F>* h = head + row * chunks_per_row;
+    const Xyzz<F>* t = tail + row * chunks_per_row;
+    const uint32_t lo = c0 + seg * ZK_HEAVY_SEG, hi = lo + ZK_HEAVY_SEG - 1 < c1 ? lo + ZK_HEAVY_SEG - 1 : c1;
+    for (uint32_t ch = lo + lane; ch <= hi; ch += 32) {
+      const Xyzz<F>* p = (ch == c0 && st > c0 * S) ? t + c0 : h + ch;
+      xyzz_add(acc, *p);
+    }
+  } else {
+    for (uint32_t g = lane; g < nseg; g += 32) xyzz_add(acc, hsum[slot0 + g]);
   }
   ZK_NOUNROLL for (uint32_t off = 16; off >= 1; off >>= 1) {
     Xyzz<F> o;
@@ -451,7 +478,7 @@ static __global__ void k_msm_fixup_heavy(const uint32_t* __restrict__ offsets, c
     o.ZZ = warp_shfl<ZK_SHFL_DOWN>(acc.ZZ, off); o.ZZZ = warp_shfl<ZK_SHFL_DOWN>(acc.ZZZ, off);
     xyzz_add(acc, o);
   }
-  if (lane == 0) buckets[id] = acc;
+  if (lane == 0) { if (phase == 0) hsum[warp] = acc; else buckets[id] = acc; }
 }
 #endif
 // pass 5: bucket reduction S = sum_k (k+1) * X[k] over the nb buckets of a row, as a three-level tree so that the

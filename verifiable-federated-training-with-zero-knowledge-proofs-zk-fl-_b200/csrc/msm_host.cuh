@@ -30,19 +30,25 @@ int msm_accumulate(zkfl_ctx* c, const Affine<F>* bases, const MsmShape& s, int s
               c->aff_acc.as<Affine<F>>(), c->aff_pre.as<F>(), c->buckets[slot].as<Xyzz<F>>(), head, tail);
   } else {
     Stage st(c, tag);
-    ZK_LAUNCH(k_msm_accumulate_chunks<F>, rows * cpr, 128, c->stream, bases, c->sorted.as<uint32_t>(), c->skey.as<zk_key_t>(),
+    ZK_LAUNCH(k_msm_accumulate_chunks<F>, rows * cpr, 128, c->stream, bases, c->sorted.as<uint32_t>(), (const zk_key_t*)nullptr,
               offsets, counts, s, S, cpr, c->buckets[slot].as<Xyzz<F>>(), head, tail);
   }
   {
     Stage st(c, "msm_fixup");
-    // heavy buckets (runs over more than 64 chunks) go to one warp each; the queue lives in the context (count + 4096 ids)
-    const uint32_t heavy_span = 64, heavy_cap = 4096;
+    // heavy buckets (runs over more than 16 chunks) go to warps, one per segment of 256 chunks; the queue lives in the context:
+    // [slots used | heavy_cap records of four words], then heavy_cap segment sums.  Measured on B200 (2^20-domain proof / 2^20-point
+    // MSM): span 16, segments of 256 -> fix-up 2.9 / 0.19 ms; span 4, segments of 64 (every bucket of such a proof spans ~7 chunks
+    // and goes to a warp, whose five-round shuffle tree runs 32 lanes for ~8 partials) -> 8.6 / 2.0 ms.
+    const uint32_t heavy_span = 16, heavy_cap = 16384;
     uint32_t* heavy = nullptr;
+    Xyzz<F>* hsum = nullptr;
 #ifndef ZKFL_EMUL
     if (env_u32("ZKFL_FIXUP_HEAVY", 1) && rows <= 64 && rows * s.nb < 0xFFFFFFFFull) {   // few rows: single proofs, split proofs
-      TRY(c->heavy.reserve((heavy_cap + 1) * 4));
+      const size_t qbytes = ((size_t)heavy_cap + 1) * 16;
+      TRY(c->heavy.reserve(qbytes + (size_t)heavy_cap * sizeof(Xyzz<Fq2>)));
       heavy = c->heavy.as<uint32_t>();
-      CU(cudaMemsetAsync(heavy, 0, 4, c->stream));
+      hsum = (Xyzz<F>*)((uint8_t*)c->heavy.p + qbytes);
+      CU(cudaMemsetAsync(heavy, 0, qbytes, c->stream));
     }
 #endif
     if (env_u32("ZKFL_FIXUP_BOUND", 1))
@@ -52,11 +58,14 @@ int msm_accumulate(zkfl_ctx* c, const Affine<F>* bases, const MsmShape& s, int s
       ZK_LAUNCH((k_msm_fixup<F, 0>), rows * s.nb, 128, c->stream, offsets, counts, s, S, cpr, (const Xyzz<F>*)head, (const Xyzz<F>*)tail,
                 c->buckets[slot].as<Xyzz<F>>(), heavy_span, heavy_cap, heavy);
 #ifndef ZKFL_EMUL
-    // the heavy count is only known on the device: a fixed grid of warps (idle ones exit at once) keeps the stream free of host round
-    // trips; large batches never queue (their rows are small circuits) and skip the launch
-    if (heavy)
+    // the number of queued segments is only known on the device: a fixed grid of warps (unused slots exit at once) keeps the stream
+    // free of host round trips; large batches never queue (their rows are small circuits) and skip the launches
+    if (heavy) {
       ZK_LAUNCH(k_msm_fixup_heavy<F>, (size_t)heavy_cap * 32, 128, c->stream, offsets, counts, s, S, cpr, (const Xyzz<F>*)head, (const Xyzz<F>*)tail,
-                c->buckets[slot].as<Xyzz<F>>(), heavy_cap, (const uint32_t*)heavy);
+                c->buckets[slot].as<Xyzz<F>>(), heavy_cap, (const uint32_t*)heavy, hsum, 0);
+      ZK_LAUNCH(k_msm_fixup_heavy<F>, (size_t)heavy_cap * 32, 128, c->stream, offsets, counts, s, S, cpr, (const Xyzz<F>*)head, (const Xyzz<F>*)tail,
+                c->buckets[slot].as<Xyzz<F>>(), heavy_cap, (const uint32_t*)heavy, hsum, 1);
+    }
 #endif
   }
   CU(cudaGetLastError());
