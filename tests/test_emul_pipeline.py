@@ -50,6 +50,20 @@ def test_resident_msm_with_window_table(emul_prover):
     pc.case_msm_resident(emul_prover, 40, 1)        # below the table threshold
 
 
+def test_queued_fixup_of_large_batches(emul_prover, monkeypatch):
+    """The fix-up of large batches (cut buckets queued by cut count, summed by k_msm_fixup_apply) forced on small cases with short
+    chunks, so that buckets are whole, cut once and cut several times: MSMs with degenerate buckets and a proof batch, bit-exact."""
+    monkeypatch.setenv("ZKFL_FIXUP_QUEUE_MIN_ROWS", "1")
+    for chunk in ("4", "7", "64"):
+        monkeypatch.setenv("ZKFL_MSM_CHUNK", chunk)
+        pc.case_g1_msm_degenerate(emul_prover)
+        for n in (1, 33, 300):
+            pc.case_g1_msm(emul_prover, n)
+        pc.case_g2_msm(emul_prover, 40)
+        cc = pc.tiny_circuit()
+        pc.case_prove(emul_prover, cc, pc.tiny_inputs(), [(11, 22), (33, 44), (0, 0)])
+
+
 def test_batch_affine_accumulation(emul_prover, monkeypatch):
     """The batch-affine bucket accumulation (large-batch path) forced on small cases: degenerate buckets (doubling,
     P + (-P), infinity bases, runs cut by chunk borders) and a whole proof batch, bit-exact against the oracle."""

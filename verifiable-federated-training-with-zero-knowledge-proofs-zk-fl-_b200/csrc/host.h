@@ -69,6 +69,7 @@ struct zkfl_ctx {
   // already run the NEXT sort: one set per sort of a proving pass (0: witness, 1: witness restricted to the B query, 2: H)
   DevBuf counts[3], offsets[3], cursors, chunk_sums, sorted, skey;
   DevBuf head[5], tail[5];   // chunk partials per MSM slot (read by that slot's reduction on its side stream)
+  DevBuf fixq;               // large batches: ids of the buckets cut once / more than once (k_msm_fixup -> k_msm_fixup_apply)
   DevBuf heavy;              // heavy buckets of the current fix-up: [slots used | records (bucket, segment, segments, first slot)] + segment sums
   DevBuf v_ic, v_pub, v_proofs, v_t, v_g1, v_g2, v_flags, v_f, v_halves, v_ok;   // batch verifier
   DevBuf v_lines, v_rho, v_cps, v_sum[2], v_s, v_spart, v_tmul, v_sub, v_tree[2], v_misc;   // lane-cooperative / batched (RLC) verifier

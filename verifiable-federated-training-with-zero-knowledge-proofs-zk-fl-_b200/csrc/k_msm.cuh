@@ -412,11 +412,44 @@ ZK_GLOBAL void k_msm_accumulate_affine(const Affine<F>* __restrict__ bases, cons
 // (phase 0) and then the segment sums of one bucket per warp (phase 1): ~2 * (8 + 5) dependent additions whatever the bucket size.
 // heavy == NULL: no queue.  A bucket that does not fit the queue is summed here after all.
 #define ZK_HEAVY_SEG 256u
+// fq != NULL (large batches): the cut buckets are only SORTED OUT here -- ids of buckets cut once go to queue 0, of buckets cut more
+// often to queue 1 (fq = [n0, n1, -, - | queue 0: q_cap ids | queue 1: q_cap ids]) -- and k_msm_fixup_apply sums them, one thread per
+// queued id: every lane of a warp then has an addition to make, and the same number of them.  One thread per bucket summing in
+// place ran with 16 of 32 lanes active (ncu, profiles/r02_ncu_full_fixup_reduce_b1024.csv): most buckets are whole or cut once,
+// a few twice, and the warp waits for those.
+#ifndef ZKFL_EMUL
+__device__ __forceinline__ void zk_warp_push(uint32_t* counter, uint32_t* queue, bool pred, uint32_t value) {
+  const unsigned m = __ballot_sync(0xffffffffu, pred);       // every lane of the warp arrives here (no early exits before)
+  if (!m) return;
+  const unsigned lane = threadIdx.x & 31u;
+  const int leader = __ffs(m) - 1;
+  uint32_t base = 0;
+  if ((int)lane == leader) base = atomicAdd(counter, (uint32_t)__popc(m));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  if (pred) queue[base + __popc(m & ((1u << lane) - 1u))] = value;
+}
+#else
+static inline void zk_warp_push(uint32_t* counter, uint32_t* queue, bool pred, uint32_t value) {
+  if (pred) queue[ZK_ATOMIC_ADD(counter, 1u)] = value;
+}
+#endif
 template <class F, int BOUND>
 ZK_GLOBAL ZK_FIX_BOUNDS(F, BOUND) void k_msm_fixup(const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ counts, MsmShape s, uint32_t S,
                            uint32_t chunks_per_row, const Xyzz<F>* __restrict__ head, const Xyzz<F>* __restrict__ tail,
-                           Xyzz<F>* __restrict__ buckets, uint32_t heavy_span, uint32_t heavy_cap, uint32_t* __restrict__ heavy) {
+                           Xyzz<F>* __restrict__ buckets, uint32_t heavy_span, uint32_t heavy_cap, uint32_t* __restrict__ heavy,
+                           uint32_t* __restrict__ fq, uint32_t q_cap) {
   size_t tid = ZK_TID;
+  if (fq) {
+    uint32_t cuts = 0;
+    if (tid < (size_t)s.B * s.R * s.nb) {
+      const uint32_t st = offsets[tid], cnt = counts[tid];
+      if (cnt == 0) buckets[tid] = Xyzz<F>::infinity();
+      else cuts = (st + cnt - 1) / S - st / S;
+    }
+    zk_warp_push(fq, fq + 4, cuts == 1, (uint32_t)tid);
+    zk_warp_push(fq + 1, fq + 4 + q_cap, cuts > 1, (uint32_t)tid);
+    return;
+  }
   if (tid >= (size_t)s.B * s.R * s.nb) return;
   size_t row = tid / s.nb;
   uint32_t st = offsets[tid], cnt = counts[tid];
@@ -440,6 +473,22 @@ ZK_GLOBAL ZK_FIX_BOUNDS(F, BOUND) void k_msm_fixup(const uint32_t* __restrict__ 
   Xyzz<F> acc = (st > c0 * S) ? t[c0] : h[c0];
   for (uint32_t ch = c0 + 1; ch <= c1; ch++) xyzz_add(acc, h[ch]);
   buckets[tid] = acc;
+}
+// thread i of queue `which`: the bucket's partial sums, tail (or head) of its first chunk plus the heads of the following ones
+template <class F, int BOUND>
+ZK_GLOBAL ZK_FIX_BOUNDS(F, BOUND) void k_msm_fixup_apply(const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ counts, MsmShape s,
+                           uint32_t S, uint32_t chunks_per_row, const Xyzz<F>* __restrict__ head, const Xyzz<F>* __restrict__ tail,
+                           Xyzz<F>* __restrict__ buckets, const uint32_t* __restrict__ fq, uint32_t q_cap, uint32_t which) {
+  const size_t i = ZK_TID;
+  if (i >= fq[which]) return;
+  const uint32_t id = fq[4 + (size_t)which * q_cap + i];
+  const size_t row = id / s.nb;
+  const uint32_t st = offsets[id], cnt = counts[id], c0 = st / S, c1 = (st + cnt - 1) / S;
+  const Xyzz<F>* h = head + row * chunks_per_row;
+  const Xyzz<F>* t = tail + row * chunks_per_row;
+  Xyzz<F> acc = (st > c0 * S) ? t[c0] : h[c0];
+  for (uint32_t ch = c0 + 1; ch <= c1; ch++) xyzz_add(acc, h[ch]);
+  buckets[id] = acc;
 }
 #ifndef ZKFL_EMUL
 // one WARP per queue slot.  phase 0: lane l sums the partials of the slot's segment, chunks c0 + seg * SEG + l, + 32, ...; the 32 lane

@@ -51,12 +51,32 @@ int msm_accumulate(zkfl_ctx* c, const Affine<F>* bases, const MsmShape& s, int s
       CU(cudaMemsetAsync(heavy, 0, qbytes, c->stream));
     }
 #endif
-    if (env_u32("ZKFL_FIXUP_BOUND", 1))
+    // large batches: cut buckets are queued by how often they are cut and summed densely (k_msm_fixup_apply); at most one
+    // bucket is cut per chunk border, so rows * cpr ids per queue suffice
+    uint32_t* fq = nullptr;
+    const size_t q_cap = rows * cpr;
+    if (!heavy && rows >= env_u32("ZKFL_FIXUP_QUEUE_MIN_ROWS", 65) && rows * s.nb < 0xFFFFFFFFull && q_cap < 0xFFFFFFFFull && env_u32("ZKFL_FIXUP_QUEUE", 1)) {
+      TRY(c->fixq.reserve((4 + 2 * q_cap) * 4));
+      fq = c->fixq.as<uint32_t>();
+      CU(cudaMemsetAsync(fq, 0, 16, c->stream));
+    }
+    const bool bound = env_u32("ZKFL_FIXUP_BOUND", 1) != 0;
+    if (bound)
       ZK_LAUNCH((k_msm_fixup<F, 1>), rows * s.nb, 128, c->stream, offsets, counts, s, S, cpr, (const Xyzz<F>*)head, (const Xyzz<F>*)tail,
-                c->buckets[slot].as<Xyzz<F>>(), heavy_span, heavy_cap, heavy);
+                c->buckets[slot].as<Xyzz<F>>(), heavy_span, heavy_cap, heavy, fq, (uint32_t)q_cap);
     else
       ZK_LAUNCH((k_msm_fixup<F, 0>), rows * s.nb, 128, c->stream, offsets, counts, s, S, cpr, (const Xyzz<F>*)head, (const Xyzz<F>*)tail,
-                c->buckets[slot].as<Xyzz<F>>(), heavy_span, heavy_cap, heavy);
+                c->buckets[slot].as<Xyzz<F>>(), heavy_span, heavy_cap, heavy, fq, (uint32_t)q_cap);
+    if (fq)
+      for (uint32_t which = 0; which < 2; which++) {
+        // the queue lengths are only known on the device: a grid for the worst case, unused threads exit at once
+        if (bound)
+          ZK_LAUNCH((k_msm_fixup_apply<F, 1>), q_cap, 128, c->stream, offsets, counts, s, S, cpr, (const Xyzz<F>*)head, (const Xyzz<F>*)tail,
+                    c->buckets[slot].as<Xyzz<F>>(), (const uint32_t*)fq, (uint32_t)q_cap, which);
+        else
+          ZK_LAUNCH((k_msm_fixup_apply<F, 0>), q_cap, 128, c->stream, offsets, counts, s, S, cpr, (const Xyzz<F>*)head, (const Xyzz<F>*)tail,
+                    c->buckets[slot].as<Xyzz<F>>(), (const uint32_t*)fq, (uint32_t)q_cap, which);
+      }
 #ifndef ZKFL_EMUL
     // the number of queued segments is only known on the device: a fixed grid of warps (unused slots exit at once) keeps the stream
     // free of host round trips; large batches never queue (their rows are small circuits) and skip the launches
