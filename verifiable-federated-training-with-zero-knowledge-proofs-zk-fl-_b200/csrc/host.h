@@ -67,7 +67,7 @@ struct zkfl_ctx {
   DevBuf w, abc, hsc, stage_in, stage_rs, aos;
   // counts / offsets of a bucket sort are still read by side-stream work (fix-up, reductions) while the main stream may
   // already run the NEXT sort: one set per sort of a proving pass (0: witness, 1: witness restricted to the B query, 2: H)
-  DevBuf counts[3], offsets[3], cursors, chunk_sums, sorted, skey;
+  DevBuf counts[3], offsets[3], cursors, chunk_sums, sorted[3], skey;   // sorted lists per sort too: the next sort runs on its own stream while the previous lists are accumulated
   DevBuf head[5], tail[5];   // chunk partials per MSM slot (read by that slot's reduction on its side stream)
   DevBuf fixq;               // large batches: ids of the buckets cut once / more than once (k_msm_fixup -> k_msm_fixup_apply)
   DevBuf heavy;              // heavy buckets of the current fix-up: [slots used | records (bucket, segment, segments, first slot)] + segment sums
@@ -79,6 +79,8 @@ struct zkfl_ctx {
   DevBuf buckets[5], Rs[5], Ts[5], lvl2[5], win[5];
   DevBuf red_main[5][2], red_pool[5][2];   // ping-pong buffers of the latency variant of the bucket reduction
   cudaStream_t side[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // one per MSM slot: the reductions are latency-bound and run concurrently
+  cudaStream_t sort_stream = nullptr;      // the three sorts of a proving pass (L2-atomic bound) run beside the product-bound stages
+  cudaEvent_t ev_in = nullptr, ev_hsc = nullptr, ev_sort[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t ev_acc[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}, ev_red[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   DevBuf res_g1, res_g2, t_g1, t_g2, pis, var, proofs, pubs, bad;
   // deferred checks of a proving call (constraint check of the HBM-resident witness, witness well-formedness): the kernels
@@ -182,7 +184,8 @@ struct ReducePlan { uint32_t L1, L2, N1, N2; };
 uint32_t accumulate_chunk();
 MsmShape msm_shape(uint32_t m, uint32_t B, bool shared, uint32_t force_c = 0, uint32_t c_cap = 0);
 ReducePlan reduce_plan(const MsmShape& s);
-int msm_sort(zkfl_ctx* c, const Fr* scalars, const uint8_t* skip, const MsmShape& s, int gen = 0);   // gen: which counts/offsets set
+int msm_sort(zkfl_ctx* c, const Fr* scalars, const uint8_t* skip, const MsmShape& s, int gen = 0, cudaStream_t stream = nullptr);   // gen: which counts/offsets/list set; stream: default = the context's
+int msm_sort_reserve(zkfl_ctx* c, const MsmShape& s, int gen);   // the allocations of msm_sort (cudaMalloc would serialise concurrent streams)
 int msm_range_mask(zkfl_ctx* c, const uint8_t* base_skip, uint32_t m, uint32_t lo, uint32_t hi, uint8_t* out);
 bool reduce_deep(const MsmShape& s);
 int msm_reserve_reduce(zkfl_ctx* c, const MsmShape& s, int slot, size_t elem);

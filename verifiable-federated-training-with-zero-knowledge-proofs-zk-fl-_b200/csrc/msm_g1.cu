@@ -50,17 +50,23 @@ ReducePlan reduce_plan(const MsmShape& s) {
   return p;
 }
 
-int msm_sort(zkfl_ctx* c, const Fr* scalars, const uint8_t* skip, const MsmShape& s, int gen) {
+int msm_sort_reserve(zkfl_ctx* c, const MsmShape& s, int gen) {
   size_t rows = (size_t)s.B * s.R;
   uint32_t nchunk = (s.nb + ZK_SCAN_CHUNK - 1) / ZK_SCAN_CHUNK;
   TRY(c->counts[gen].reserve(rows * s.nb * 4));
   TRY(c->offsets[gen].reserve(rows * s.nb * 4));
   TRY(c->cursors.reserve(rows * s.nb * 4));
   TRY(c->chunk_sums.reserve(rows * nchunk * 4));
-  TRY(c->sorted.reserve(rows * s.cap * 4));
-  const bool want_keys = s.lsS != 0;             // only the batch-affine accumulation walks the list by keys
-  if (want_keys) TRY(c->skey.reserve(rows * s.cap * sizeof(zk_key_t)));
-  zk_key_t* keys = want_keys ? c->skey.as<zk_key_t>() : nullptr;
+  TRY(c->sorted[gen].reserve(rows * s.cap * 4));
+  if (s.lsS != 0) TRY(c->skey.reserve(rows * s.cap * sizeof(zk_key_t)));   // only the batch-affine accumulation walks the list by keys
+  return 0;
+}
+int msm_sort(zkfl_ctx* c, const Fr* scalars, const uint8_t* skip, const MsmShape& s, int gen, cudaStream_t stream) {
+  if (!stream) stream = c->stream;
+  size_t rows = (size_t)s.B * s.R;
+  uint32_t nchunk = (s.nb + ZK_SCAN_CHUNK - 1) / ZK_SCAN_CHUNK;
+  TRY(msm_sort_reserve(c, s, gen));
+  zk_key_t* keys = s.lsS != 0 ? c->skey.as<zk_key_t>() : nullptr;
 #ifndef ZKFL_EMUL
   // OPT-IN (ZKFL_MSM_SORT_CTA=1): one CTA per proof with the histogram in shared memory.  Measured on B200 at 1024 proofs: 8.6 ms per
   // sort against ~7 ms for the global-atomics passes below -- ~300 proofs are in flight at once, their 1.2 MB list regions no longer fit
@@ -69,20 +75,20 @@ int msm_sort(zkfl_ctx* c, const Fr* scalars, const uint8_t* skip, const MsmShape
   if (s.R == 1 && rows >= 32 && s.nb <= 32768 && env_u32("ZKFL_MSM_SORT_CTA", 0)) {
     const size_t smem = ((size_t)s.nb + 32) * 4;
     if (!c->sort_attr) { CU(cudaFuncSetAttribute(k_msm_sort_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (32768 + 32) * 4)); c->sort_attr = true; }
-    k_msm_sort_cta<<<(unsigned)rows, 1024, smem, c->stream>>>(scalars, skip, s, c->offsets[gen].as<uint32_t>(), c->counts[gen].as<uint32_t>(),
-                                                             c->sorted.as<uint32_t>(), keys);
+    k_msm_sort_cta<<<(unsigned)rows, 1024, smem, stream>>>(scalars, skip, s, c->offsets[gen].as<uint32_t>(), c->counts[gen].as<uint32_t>(),
+                                                             c->sorted[gen].as<uint32_t>(), keys);
     zkrt::note_launch("k_msm_sort_cta");
-    if (zkrt::debug_sync()) zkrt::debug_check("k_msm_sort_cta", c->stream);
+    if (zkrt::debug_sync()) zkrt::debug_check("k_msm_sort_cta", stream);
     CU(cudaGetLastError());
     return 0;
   }
 #endif
-  CU(cudaMemsetAsync(c->counts[gen].p, 0, rows * s.nb * 4, c->stream));
-  ZK_LAUNCH(k_msm_count, (size_t)s.m * s.B, 256, c->stream, scalars, skip, s, c->counts[gen].as<uint32_t>());
-  ZK_LAUNCH(k_msm_scan_chunks, rows * nchunk, 128, c->stream, c->counts[gen].as<uint32_t>(), s, c->chunk_sums.as<uint32_t>());
-  ZK_LAUNCH(k_msm_scan_write, rows * nchunk, 128, c->stream, c->counts[gen].as<uint32_t>(), c->chunk_sums.as<uint32_t>(), s,
+  CU(cudaMemsetAsync(c->counts[gen].p, 0, rows * s.nb * 4, stream));
+  ZK_LAUNCH(k_msm_count, (size_t)s.m * s.B, 256, stream, scalars, skip, s, c->counts[gen].as<uint32_t>());
+  ZK_LAUNCH(k_msm_scan_chunks, rows * nchunk, 128, stream, c->counts[gen].as<uint32_t>(), s, c->chunk_sums.as<uint32_t>());
+  ZK_LAUNCH(k_msm_scan_write, rows * nchunk, 128, stream, c->counts[gen].as<uint32_t>(), c->chunk_sums.as<uint32_t>(), s,
             c->offsets[gen].as<uint32_t>(), c->cursors.as<uint32_t>());
-  ZK_LAUNCH(k_msm_scatter, (size_t)s.m * s.B, 256, c->stream, scalars, skip, s, c->cursors.as<uint32_t>(), c->sorted.as<uint32_t>(),
+  ZK_LAUNCH(k_msm_scatter, (size_t)s.m * s.B, 256, stream, scalars, skip, s, c->cursors.as<uint32_t>(), c->sorted[gen].as<uint32_t>(),
             keys);
   CU(cudaGetLastError());
   return 0;

@@ -25,12 +25,12 @@ int msm_accumulate(zkfl_ctx* c, const Affine<F>* bases, const MsmShape& s, int s
     TRY(c->aff_acc.reserve(n_groups * 32 * sizeof(Affine<F>)));
     TRY(c->aff_pre.reserve(n_groups * 32 * sizeof(F)));
     Stage st(c, tag);
-    ZK_LAUNCH(k_msm_accumulate_affine<F>, n_groups / K * 32, 128, c->stream, bases, c->sorted.as<uint32_t>(),
+    ZK_LAUNCH(k_msm_accumulate_affine<F>, n_groups / K * 32, 128, c->stream, bases, c->sorted[gen].as<uint32_t>(),
               c->skey.as<zk_key_t>(), offsets, counts, s, K, (uint32_t)rows,
               c->aff_acc.as<Affine<F>>(), c->aff_pre.as<F>(), c->buckets[slot].as<Xyzz<F>>(), head, tail);
   } else {
     Stage st(c, tag);
-    ZK_LAUNCH(k_msm_accumulate_chunks<F>, rows * cpr, 128, c->stream, bases, c->sorted.as<uint32_t>(), (const zk_key_t*)nullptr,
+    ZK_LAUNCH(k_msm_accumulate_chunks<F>, rows * cpr, 128, c->stream, bases, c->sorted[gen].as<uint32_t>(), (const zk_key_t*)nullptr,
               offsets, counts, s, S, cpr, c->buckets[slot].as<Xyzz<F>>(), head, tail);
   }
   {
