@@ -64,6 +64,16 @@ def test_queued_fixup_of_large_batches(emul_prover, monkeypatch):
         pc.case_prove(emul_prover, cc, pc.tiny_inputs(), [(11, 22), (33, 44), (0, 0)])
 
 
+def test_g2_operand_file_accumulation(emul_prover, monkeypatch):
+    """The opt-in operand-file form of the G2 bucket accumulation (running sum and temporaries in a per-thread file, one generic
+    operation as the only call): G2 MSMs and a proof batch, bit-exact against the oracle, with short and default chunks."""
+    monkeypatch.setenv("ZKFL_G2_OPERAND_FILE", "1")
+    for chunk in ("4", "64"):
+        monkeypatch.setenv("ZKFL_MSM_CHUNK", chunk)
+        pc.case_g2_msm(emul_prover, 40)
+        pc.case_prove(emul_prover, pc.tiny_circuit(), pc.tiny_inputs(), [(11, 22), (33, 44), (0, 0)])
+
+
 def test_batch_affine_accumulation(emul_prover, monkeypatch):
     """The batch-affine bucket accumulation (large-batch path) forced on small cases: degenerate buckets (doubling,
     P + (-P), infinity bases, runs cut by chunk borders) and a whole proof batch, bit-exact against the oracle."""

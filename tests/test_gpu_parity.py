@@ -120,6 +120,13 @@ def test_prove_sgd_verified_batch(gpu_prover):
     pc.case_prove(gpu_prover, build_circuit("sgd_verified"), ins, rs, python_verify=2)
 
 
+def test_g2_operand_file_accumulation(gpu_prover, monkeypatch):
+    """opt-in operand-file form of the G2 accumulation (shared-memory file, generic operation): bit-exact on the GPU"""
+    monkeypatch.setenv("ZKFL_G2_OPERAND_FILE", "1")
+    pc.case_g2_msm(gpu_prover, 300)
+    pc.case_prove(gpu_prover, build_circuit("sgd_verified"), I.sgd_verified_batch(3, nonzero_weights=True), [(1, 2), (3, 4), (5, 6)])
+
+
 def test_batch_affine_accumulation_forced(gpu_prover, monkeypatch):
     """The large-batch bucket accumulation (batch-affine, warp-shared inversion) forced on at test sizes: degenerate buckets,
     G1/G2 MSMs against the oracle, and sgd_verified proofs bit-exact with fixed (r, s) for several chunk/slot shapes."""

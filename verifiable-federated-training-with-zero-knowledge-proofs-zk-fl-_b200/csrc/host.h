@@ -98,6 +98,7 @@ struct zkfl_ctx {
   VkCacheEntry vk_cache[4];
   uint64_t vk_stamp = 0;
   int v_last_rlc = 0;        // 1 when the last zkfl_groth16_verify_batch was settled by the combined (random-linear-combination) check
+  bool g2f_attr = false;     // k_msm_accumulate_chunks_g2f has been granted its dynamic shared memory on this device
   bool sort_attr = false;    // k_msm_sort_cta has been granted its dynamic shared memory on this device
   DevBuf msm_sc, msm_out, mask_w, mask_wb, mask_h, part_out, part_in;
   cudaEvent_t t0 = nullptr, t1 = nullptr, ev_join = nullptr;

@@ -231,6 +231,157 @@ ZK_GLOBAL ZK_ACC_BOUNDS(F) void k_msm_accumulate_chunks(const Affine<F>* __restr
   else if (first) head[tid] = acc;   // run covers the chunk's first entry (possibly the whole chunk)
   else tail[tid] = acc;              // run started here and continues in the next chunk
 }
+// pass 4 for G2, OPERAND-FILE form (OPT-IN, ZKFL_G2_OPERAND_FILE=1; bit-exact in the tests).  ncu of k_msm_accumulate_chunks<Fq2> (profiles/r02_sass_opcode_mix_accumulate.txt):
+// 7 % of its executed instructions are IMAD.MOV / IMAD.U32 marshalling the 48 words of every by-value Fq2 product call and 2 % are
+// spills -- all on the FMA pipe that bounds the kernel.  Here the running sum and every temporary of the mixed addition live in a
+// per-thread OPERAND FILE in shared memory (9 Fq2 slots, 128-bit accesses, [slot][quarter][thread]: conflict-free) and ONE generic
+// operation  dst = (a [- pre]) * b [- p1] [- 2 p2]  (or the square of the first factor) is a call that takes three integers: nothing
+// is marshalled, nothing is live across the call, the file traffic (~14 LDS/STS.128 per operation) runs on the load/store pipe.
+// The whole kernel is ~1.5 k instructions (one product body, one square body) instead of 4.5 k.
+// The host emulation keeps the file in a thread-private array and runs the same operation sequence.
+// MEASURED on B200 (1024 proofs, chunks of 64): 72.0 ms against 70.7 ms for the by-value-call kernel.  ncu of this form
+// (profiles/r02_sass_opcode_mix_g2_operand_file.txt): IMAD.MOV 6.5 -> 3.2 % and no spills, but the slot address arithmetic brings
+// IMAD 3.0 -> 5.0 % and the operand decoding LOP3 4.8 -> 6.5 %, the merges of the optional operands keep moves alive, and the IMAD.X
+// carries (6.3 %) are untouched: non-multiply work on the FMA pipe 19.9 -> 17.4 % of the instructions, not enough to pay for the
+// longer dependent chain through shared memory.  Kept as the starting point for a form with constant strides and branch-free operands.
+enum { G2F_X = 0, G2F_Y, G2F_ZZ, G2F_ZZZ, G2F_P, G2F_R, G2F_PP, G2F_PPP, G2F_Q, G2F_SLOTS, G2F_NONE = 15 };
+#ifndef ZKFL_EMUL
+typedef uint4* G2FilePtr;                      // shared memory + threadIdx.x; slot s, quarter q at [(s * 4 + q) * blockDim.x]
+__device__ __forceinline__ Fq2 g2f_ld(G2FilePtr f, uint32_t s) {
+  const uint4* p = f + (size_t)s * 4 * blockDim.x;
+  const uint4 v0 = p[0], v1 = p[blockDim.x], v2 = p[2 * blockDim.x], v3 = p[3 * blockDim.x];
+  Fq2 r;
+  r.a.v[0] = v0.x; r.a.v[1] = v0.y; r.a.v[2] = v0.z; r.a.v[3] = v0.w; r.a.v[4] = v1.x; r.a.v[5] = v1.y; r.a.v[6] = v1.z; r.a.v[7] = v1.w;
+  r.b.v[0] = v2.x; r.b.v[1] = v2.y; r.b.v[2] = v2.z; r.b.v[3] = v2.w; r.b.v[4] = v3.x; r.b.v[5] = v3.y; r.b.v[6] = v3.z; r.b.v[7] = v3.w;
+  return r;
+}
+__device__ __forceinline__ void g2f_st(G2FilePtr f, uint32_t s, const Fq2& x) {
+  uint4* p = f + (size_t)s * 4 * blockDim.x;
+  p[0] = make_uint4(x.a.v[0], x.a.v[1], x.a.v[2], x.a.v[3]); p[blockDim.x] = make_uint4(x.a.v[4], x.a.v[5], x.a.v[6], x.a.v[7]);
+  p[2 * blockDim.x] = make_uint4(x.b.v[0], x.b.v[1], x.b.v[2], x.b.v[3]); p[3 * blockDim.x] = make_uint4(x.b.v[4], x.b.v[5], x.b.v[6], x.b.v[7]);
+}
+#else
+typedef Fq2* G2FilePtr;
+static inline Fq2 g2f_ld(G2FilePtr f, uint32_t s) { return f[s]; }
+static inline void g2f_st(G2FilePtr f, uint32_t s, const Fq2& x) { f[s] = x; }
+#endif
+// code: dst | a << 4 | b << 8 | pre << 12 | p1 << 16 | p2 << 20 | sqr << 24 | neg_b << 25; b == G2F_NONE: second factor = *gb (global)
+#define G2F_OP(dst, a, b, pre, p1, p2, sqr, neg) \
+  ((uint32_t)(dst) | (uint32_t)(a) << 4 | (uint32_t)(b) << 8 | (uint32_t)(pre) << 12 | (uint32_t)(p1) << 16 | (uint32_t)(p2) << 20 | (uint32_t)(sqr) << 24 | (uint32_t)(neg) << 25)
+// returns 1 when the result is zero
+#ifndef ZKFL_EMUL
+static __device__ __noinline__
+#else
+static inline
+#endif
+uint32_t g2f_op(G2FilePtr f, uint32_t code, const Fq2* gb) {
+  const uint32_t dst = code & 15u, a = (code >> 4) & 15u, b = (code >> 8) & 15u, pre = (code >> 12) & 15u, p1 = (code >> 16) & 15u,
+                 p2 = (code >> 20) & 15u;
+  Fq2 x = g2f_ld(f, a);
+  if (pre != G2F_NONE) x = x - g2f_ld(f, pre);
+  Fq2 r;
+  if ((code >> 24) & 1u) {
+    const Fq t = Fq::mul_inline(x.a, x.b);
+    r.a = Fq::mul_inline(x.a + x.b, x.a - x.b); r.b = t.dbl();
+  } else {
+    Fq2 y = b == G2F_NONE ? *gb : g2f_ld(f, b);
+    if ((code >> 25) & 1u) y = y.neg();
+    const Fq aa = Fq::mul_inline(x.a, y.a), bb = Fq::mul_inline(x.b, y.b), ss = Fq::mul_inline(x.a + x.b, y.a + y.b);
+    r.a = aa - bb; r.b = ss - aa - bb;
+  }
+  if (p1 != G2F_NONE) r = r - g2f_ld(f, p1);
+  if (p2 != G2F_NONE) r = r - g2f_ld(f, p2).dbl();
+  g2f_st(f, dst, r);
+  return r.is_zero() ? 1u : 0u;
+}
+// acc (in the file) += q (affine, global), exactly xyzz_madd; `inf`: the running sum is the point at infinity (nothing valid in the file)
+ZK_D void g2f_madd(G2FilePtr f, bool& inf, const G2Affine* __restrict__ qp, bool negate) {
+  const G2Affine q = *qp;
+  if (q.is_inf()) return;
+  if (inf) {
+    g2f_st(f, G2F_X, q.x); g2f_st(f, G2F_Y, negate ? q.y.neg() : q.y); g2f_st(f, G2F_ZZ, Fq2::one()); g2f_st(f, G2F_ZZZ, Fq2::one());
+    inf = false;
+    return;
+  }
+  const uint32_t zp = g2f_op(f, G2F_OP(G2F_P, G2F_ZZ, G2F_NONE, G2F_NONE, G2F_X, G2F_NONE, 0, 0), &qp->x);        // P = x2 ZZ1 - X1
+  const uint32_t zr = g2f_op(f, G2F_OP(G2F_R, G2F_ZZZ, G2F_NONE, G2F_NONE, G2F_Y, G2F_NONE, 0, negate ? 1 : 0), &qp->y);   // R = y2 ZZZ1 - Y1
+  if (zp) {                                                   // same x: doubling or cancellation (never on the hot path)
+    if (zr) {
+      G2Affine qq = q; if (negate) qq.y = qq.y.neg();
+      const G2Xyzz d = xyzz_dbl_affine(qq);
+      g2f_st(f, G2F_X, d.X); g2f_st(f, G2F_Y, d.Y); g2f_st(f, G2F_ZZ, d.ZZ); g2f_st(f, G2F_ZZZ, d.ZZZ);
+    } else inf = true;
+    return;
+  }
+  g2f_op(f, G2F_OP(G2F_PP, G2F_P, G2F_NONE, G2F_NONE, G2F_NONE, G2F_NONE, 1, 0), nullptr);                          // PP = P^2
+  g2f_op(f, G2F_OP(G2F_PPP, G2F_P, G2F_PP, G2F_NONE, G2F_NONE, G2F_NONE, 0, 0), nullptr);                           // PPP = P PP
+  g2f_op(f, G2F_OP(G2F_Q, G2F_X, G2F_PP, G2F_NONE, G2F_NONE, G2F_NONE, 0, 0), nullptr);                             // Q = X1 PP
+  g2f_op(f, G2F_OP(G2F_X, G2F_R, G2F_NONE, G2F_NONE, G2F_PPP, G2F_Q, 1, 0), nullptr);                               // X3 = R^2 - PPP - 2 Q
+  g2f_op(f, G2F_OP(G2F_Y, G2F_Y, G2F_PPP, G2F_NONE, G2F_NONE, G2F_NONE, 0, 0), nullptr);                            // Y1 PPP
+  g2f_op(f, G2F_OP(G2F_Y, G2F_Q, G2F_R, G2F_X, G2F_Y, G2F_NONE, 0, 0), nullptr);                                    // Y3 = (Q - X3) R - Y1 PPP
+  g2f_op(f, G2F_OP(G2F_ZZ, G2F_ZZ, G2F_PP, G2F_NONE, G2F_NONE, G2F_NONE, 0, 0), nullptr);                           // ZZ3 = ZZ1 PP
+  g2f_op(f, G2F_OP(G2F_ZZZ, G2F_ZZZ, G2F_PPP, G2F_NONE, G2F_NONE, G2F_NONE, 0, 0), nullptr);                        // ZZZ3 = ZZZ1 PPP
+}
+ZK_D G2Xyzz g2f_read(G2FilePtr f, bool inf) {
+  if (inf) return G2Xyzz::infinity();
+  G2Xyzz r; r.X = g2f_ld(f, G2F_X); r.Y = g2f_ld(f, G2F_Y); r.ZZ = g2f_ld(f, G2F_ZZ); r.ZZZ = g2f_ld(f, G2F_ZZZ);
+  return r;
+}
+// same decomposition, outputs and run logic as k_msm_accumulate_chunks; dynamic shared memory = G2F_SLOTS * 64 * blockDim.x bytes
+#if defined(__CUDACC__) && !defined(ZKFL_EMUL)
+static __global__ void __launch_bounds__(128, 3)
+#else
+static void
+#endif
+k_msm_accumulate_chunks_g2f(const G2Affine* __restrict__ bases, const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ offsets,
+                            const uint32_t* __restrict__ counts, MsmShape s, uint32_t S, uint32_t chunks_per_row,
+                            G2Xyzz* __restrict__ buckets, G2Xyzz* __restrict__ head, G2Xyzz* __restrict__ tail) {
+#ifndef ZKFL_EMUL
+  extern __shared__ uint4 zk_g2f_sm[];
+  G2FilePtr f = zk_g2f_sm + threadIdx.x;
+#else
+  Fq2 file[G2F_SLOTS];
+  G2FilePtr f = file;
+#endif
+  size_t tid = ZK_TID;
+  if (tid >= (size_t)s.B * s.R * chunks_per_row) return;
+  size_t row = tid / chunks_per_row;
+  uint32_t ch = (uint32_t)(tid % chunks_per_row);
+  const uint32_t* off = offsets + row * s.nb;
+  const uint32_t* cnt = counts + row * s.nb;
+  uint32_t total = off[s.nb - 1] + cnt[s.nb - 1];
+  uint32_t pos0 = ch * S;
+  if (pos0 >= total) return;
+  uint32_t pos1 = pos0 + S < total ? pos0 + S : total;
+  const uint32_t* list = sorted + row * s.cap;
+  uint32_t lo = 0, hi = s.nb;
+  while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (off[mid] <= pos0) lo = mid; else hi = mid; }
+  uint32_t cur = lo, run_end = off[cur] + cnt[cur];
+  bool first = true, inf = true;
+  uint32_t e_next = list[pos0], e_next2 = 0;
+  if (pos0 + 1 < pos1) e_next2 = list[pos0 + 1];
+  for (uint32_t pos = pos0; pos < pos1; pos++) {
+    const uint32_t e = e_next;
+    e_next = e_next2;
+    if (pos + 1 < pos1) {
+      ZK_PREFETCH(bases + (e_next & 0x7FFFFFFFu));
+      if (pos + 2 < pos1) e_next2 = list[pos + 2];
+    }
+    if (pos == run_end) {
+      if (first && off[cur] < pos0) head[tid] = g2f_read(f, inf); else buckets[row * s.nb + cur] = g2f_read(f, inf);
+      inf = true;
+      do { cur++; } while (cnt[cur] == 0);
+      run_end = off[cur] + cnt[cur];
+      first = false;
+    }
+    g2f_madd(f, inf, bases + (e & 0x7FFFFFFFu), (e >> 31) != 0);
+  }
+  bool starts_here = !(first && off[cur] < pos0);
+  bool ends_here = run_end <= pos1;
+  if (starts_here && ends_here) buckets[row * s.nb + cur] = g2f_read(f, inf);
+  else if (first) head[tid] = g2f_read(f, inf);
+  else tail[tid] = g2f_read(f, inf);
+}
 // pass 4, BATCH-AFFINE variant (large batches).  Same decomposition into chunks of S sorted entries and the same outputs
 // (whole buckets written directly, head/tail partials for pass 4b), but the running sums stay AFFINE, and the S additions
 // of a chunk are interleaved with those of the K-1 other chunks of the same thread and of the 32*K chunks of the warp, so

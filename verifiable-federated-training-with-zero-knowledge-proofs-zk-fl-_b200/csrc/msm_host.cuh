@@ -5,6 +5,26 @@
 
 static inline uint32_t affine_slots() { uint32_t K = env_u32("ZKFL_MSM_AFFINE_K", 64); return K < 1 ? 1 : (K > 4096 ? 4096 : K); }   // chunks per thread
 
+// the operand-file form of the G2 accumulation (k_msm_accumulate_chunks_g2f): 9 Fq2 slots per thread in dynamic shared memory
+static inline int msm_launch_g2f(zkfl_ctx* c, const void* bases, const uint32_t* sorted, const uint32_t* offsets, const uint32_t* counts,
+                                 const MsmShape& s, uint32_t S, uint32_t cpr, void* buckets, void* head, void* tail) {
+  const size_t total = (size_t)s.B * s.R * cpr;
+  if (!total) return 0;
+#ifndef ZKFL_EMUL
+  const unsigned block = 128;
+  const size_t smem = (size_t)G2F_SLOTS * 64 * block;
+  if (!c->g2f_attr) { CU(cudaFuncSetAttribute(k_msm_accumulate_chunks_g2f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); c->g2f_attr = true; }
+  k_msm_accumulate_chunks_g2f<<<(unsigned)((total + block - 1) / block), block, smem, c->stream>>>(
+      (const G2Affine*)bases, sorted, offsets, counts, s, S, cpr, (G2Xyzz*)buckets, (G2Xyzz*)head, (G2Xyzz*)tail);
+  zkrt::note_launch("k_msm_accumulate_chunks_g2f");
+  if (zkrt::debug_sync()) zkrt::debug_check("k_msm_accumulate_chunks_g2f", c->stream);
+#else
+  ZK_LAUNCH(k_msm_accumulate_chunks_g2f, total, 128, c->stream, (const G2Affine*)bases, sorted, offsets, counts, s, S, cpr, (G2Xyzz*)buckets,
+            (G2Xyzz*)head, (G2Xyzz*)tail);
+#endif
+  CU(cudaGetLastError());
+  return 0;
+}
 // bucket accumulation of one MSM (slot = which of the five buffer sets) and the fix-up of the buckets cut by chunk borders, on the
 // main stream; uses the lists left by msm_sort(gen).
 template <class F>
@@ -28,6 +48,9 @@ int msm_accumulate(zkfl_ctx* c, const Affine<F>* bases, const MsmShape& s, int s
     ZK_LAUNCH(k_msm_accumulate_affine<F>, n_groups / K * 32, 128, c->stream, bases, c->sorted[gen].as<uint32_t>(),
               c->skey.as<zk_key_t>(), offsets, counts, s, K, (uint32_t)rows,
               c->aff_acc.as<Affine<F>>(), c->aff_pre.as<F>(), c->buckets[slot].as<Xyzz<F>>(), head, tail);
+  } else if (sizeof(F) > 32 && env_u32("ZKFL_G2_OPERAND_FILE", 0)) {   // opt-in: measured no faster, see k_msm.cuh
+    Stage st(c, tag);
+    TRY(msm_launch_g2f(c, (const void*)bases, c->sorted[gen].as<uint32_t>(), offsets, counts, s, S, cpr, c->buckets[slot].p, (void*)head, (void*)tail));
   } else {
     Stage st(c, tag);
     ZK_LAUNCH(k_msm_accumulate_chunks<F>, rows * cpr, 128, c->stream, bases, c->sorted[gen].as<uint32_t>(), (const zk_key_t*)nullptr,
