@@ -60,6 +60,7 @@ def parse_args():
                     help="contexts (streams) per GPU; the batch of a step is split evenly over them and proved concurrently")
     ap.add_argument("--no-msm", action="store_true", help="skip the standalone 2^20-point G1 MSM measurement")
     ap.add_argument("--no-split", action="store_true", help="skip the 2^20-domain split-proof measurement")
+    ap.add_argument("--no-round", action="store_true", help="skip the 1 023-client full-round measurement (BASELINE configs[3])")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline legs (dev runs under a profiler)")
     return ap.parse_args()
 
@@ -502,6 +503,27 @@ def main():
             p.close()
         split = bench_split(prover, torch, dist, rank, world, barrier, with_cpu=not args.no_cpu)
         log("split proof done" + (f": prove {split['prove_ms']:.1f} ms, full prove {split['full_prove_ms']:.1f} ms" if split else ""))
+    # ---- BASELINE configs[3]: the reference's whole round (tests/full_system_simulation.mjs:1244-1395) at 1 023 clients over the GPUs
+    # of this run: inputs from the GPU commitment pipeline, 3 x 1 023 proofs sharded b -> rank, batch verification and the masked
+    # aggregation on rank 0's GPU.  Second of two rounds (the first makes the three keys and allocates the workspaces).
+    full_round = None
+    if not args.no_round and args.workload == "proofs":
+        try:
+            from zkfl_b200 import simulation
+            cache = {}
+            for p in provers[1:]:
+                p.close()
+            simulation.run_round(prover, 1023, cache=cache, setup_seed=b"zkfl-bench-round")
+            barrier()
+            rep = simulation.run_round(prover, 1023, cache=cache, setup_seed=b"zkfl-bench-round")
+            barrier()
+            if rep is not None:
+                full_round = {"clients": rep["clients"], "n_gpus": rep.get("n_gpus", world), "proofs": rep.get("proofs"),
+                              "verified": rep["verified"], "timing_s": {k: round(v, 4) for k, v in rep["timing"].items()},
+                              "note": "one round through the Python host API (simulation.run_round), wall clock on rank 0, inputs included"}
+        except Exception as e:            # a side measurement must never cost the headline line
+            full_round = {"error": f"{type(e).__name__}: {e}"}
+        log("full round done" + (f": {full_round['timing_s'].get('round_s')} s" if full_round and "timing_s" in full_round else ""))
     line = None
     if rank == 0:
         m, n, l = zkey.n_vars, zkey.domain, zkey.n_public
@@ -584,6 +606,7 @@ def main():
             "msm_g1_2pow20": msm,
             "split_proof": split,
             "verify_batch": verify,
+            "full_round_1023": full_round,
             "cpu_baseline": cpu,
         }
         if args.workload == "split" and split is not None:

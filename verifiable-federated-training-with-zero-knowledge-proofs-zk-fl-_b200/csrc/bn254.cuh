@@ -546,6 +546,38 @@ template <class F> ZK_HD void xyzz_add(Xyzz<F>& acc, const Xyzz<F>& q) {  // add
   acc.ZZ = acc.ZZ * q.ZZ * PP;
   acc.ZZZ = acc.ZZZ * q.ZZZ * PPP;
 }
+// the same addition / doubling with the products of the hot path (Fq: inlined, Fq2: one call per Fq2 product with its three Fq
+// products interleaved): for the FEW-ROW kernels (single proofs, split proofs, one MSM), which are chains of dependent additions on
+// a nearly idle GPU -- with by-value leaf calls the 14 products of an addition run back to back (~1 500 cycles each), inlined the
+// independent ones (U1, U2, S1, S2; PPP, Q; the two halves of Y3; ZZ, ZZZ) overlap.  One call site per kernel (2.6 k instructions).
+template <class F> ZK_HD void xyzz_add_hot(Xyzz<F>& acc, const Xyzz<F>& q) {  // add-2008-s
+  if (q.is_inf()) return;
+  if (acc.is_inf()) { acc = q; return; }
+  F U1 = F::mul_hot(acc.X, q.ZZ), U2 = F::mul_hot(q.X, acc.ZZ), S1 = F::mul_hot(acc.Y, q.ZZZ), S2 = F::mul_hot(q.Y, acc.ZZZ);
+  F ZZq = F::mul_hot(acc.ZZ, q.ZZ), ZZZq = F::mul_hot(acc.ZZZ, q.ZZZ);
+  F Pp = U2 - U1, Rr = S2 - S1;
+  if (Pp.is_zero()) {
+    if (Rr.is_zero()) acc = xyzz_dbl(acc); else acc = Xyzz<F>::infinity();
+    return;
+  }
+  F PP = F::sqr_hot(Pp), PPP = F::mul_hot(Pp, PP), Qq = F::mul_hot(U1, PP);
+  F X3 = F::sqr_hot(Rr) - PPP - Qq.dbl();
+  acc.Y = F::mul_hot(Rr, Qq - X3) - F::mul_hot(S1, PPP);
+  acc.X = X3;
+  acc.ZZ = F::mul_hot(ZZq, PP);
+  acc.ZZZ = F::mul_hot(ZZZq, PPP);
+}
+template <class F> ZK_HD Xyzz<F> xyzz_dbl_hot(const Xyzz<F>& p) {  // dbl-2008-s-1, a = 0
+  if (p.is_inf()) return p;
+  F U = p.Y.dbl(), V = F::sqr_hot(U), W = F::mul_hot(U, V), S = F::mul_hot(p.X, V);
+  F M = F::sqr_hot(p.X); M = M.dbl() + M;
+  Xyzz<F> r;
+  r.X = F::sqr_hot(M) - S.dbl();
+  r.Y = F::mul_hot(M, S - r.X) - F::mul_hot(W, p.Y);
+  r.ZZ = F::mul_hot(V, p.ZZ);
+  r.ZZZ = F::mul_hot(W, p.ZZZ);
+  return r;
+}
 template <class F> ZK_HD Xyzz<F> xyzz_neg(const Xyzz<F>& p) { Xyzz<F> r = p; r.Y = p.Y.neg(); return r; }
 
 // Montgomery-form affine; infinity -> (0,0)

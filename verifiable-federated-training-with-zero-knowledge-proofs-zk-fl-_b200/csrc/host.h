@@ -182,7 +182,7 @@ static inline uint32_t env_u32(const char* name, uint32_t dflt) {
 
 // ---- msm_g1.cu (group-independent parts) and msm_g1.cu / msm_g2.cu (explicit instantiations for Fq / Fq2)
 struct ReducePlan { uint32_t L1, L2, N1, N2; };
-uint32_t accumulate_chunk();
+uint32_t accumulate_chunk(size_t entries);   // sorted entries per accumulation thread (by the size of the sort; ZKFL_MSM_CHUNK overrides)
 MsmShape msm_shape(uint32_t m, uint32_t B, bool shared, uint32_t force_c = 0, uint32_t c_cap = 0);
 ReducePlan reduce_plan(const MsmShape& s);
 int msm_sort(zkfl_ctx* c, const Fr* scalars, const uint8_t* skip, const MsmShape& s, int gen = 0, cudaStream_t stream = nullptr);   // gen: which counts/offsets/list set; stream: default = the context's

@@ -622,7 +622,10 @@ ZK_GLOBAL ZK_FIX_BOUNDS(F, BOUND) void k_msm_fixup(const uint32_t* __restrict__ 
   const Xyzz<F>* h = head + row * chunks_per_row;
   const Xyzz<F>* t = tail + row * chunks_per_row;
   Xyzz<F> acc = (st > c0 * S) ? t[c0] : h[c0];
-  for (uint32_t ch = c0 + 1; ch <= c1; ch++) xyzz_add(acc, h[ch]);
+  ZK_NOUNROLL for (uint32_t ch = c0 + 1; ch <= c1; ch++) {
+    if (BOUND == 2) xyzz_add_hot(acc, h[ch]);      // few rows: a chain of dependent additions, products overlapped
+    else xyzz_add(acc, h[ch]);
+  }
   buckets[tid] = acc;
 }
 // thread i of queue `which`: the bucket's partial sums, tail (or head) of its first chunk plus the heads of the following ones
@@ -658,25 +661,33 @@ static __global__ void k_msm_fixup_heavy(const uint32_t* __restrict__ offsets, c
   const uint32_t id = q[0], seg = q[1], nseg = q[2], slot0 = q[3];
   if (nseg == 0) return;                                    // unused slot
   if (phase == 1 && seg != 0) return;
-  Xyzz<F> acc = Xyzz<F>::infinity();
+  // ONE addition site (inlined products, see xyzz_add_hot): first the lane's strided partials -- every lane makes the same number of
+  // trips, the ones past the end add infinity -- then the five rounds of the shuffle tree
+  const Xyzz<F>* src = hsum + slot0;       // phase 1: the bucket's segment sums
+  const Xyzz<F>* first_src = nullptr;      // phase 0, segment 0 of a run that starts inside its first chunk: that chunk's TAIL partial
+  uint32_t n_items = nseg;
   if (phase == 0) {
     const size_t row = id / s.nb;
     const uint32_t st = offsets[id], cnt = counts[id], c0 = st / S, c1 = (st + cnt - 1) / S;
-    const Xyzz<F>* h = head + row * chunks_per_row;
-    const Xyzz<F>* t = tail + row * chunks_per_row;
     const uint32_t lo = c0 + seg * ZK_HEAVY_SEG, hi = lo + ZK_HEAVY_SEG - 1 < c1 ? lo + ZK_HEAVY_SEG - 1 : c1;
-    for (uint32_t ch = lo + lane; ch <= hi; ch += 32) {
-      const Xyzz<F>* p = (ch == c0 && st > c0 * S) ? t + c0 : h + ch;
-      xyzz_add(acc, *p);
-    }
-  } else {
-    for (uint32_t g = lane; g < nseg; g += 32) xyzz_add(acc, hsum[slot0 + g]);
+    src = head + row * chunks_per_row + lo;
+    n_items = hi - lo + 1;
+    if (seg == 0 && st > c0 * S) first_src = tail + row * chunks_per_row + c0;
   }
-  ZK_NOUNROLL for (uint32_t off = 16; off >= 1; off >>= 1) {
+  Xyzz<F> acc = Xyzz<F>::infinity();
+  const uint32_t trips = (n_items + 31) / 32;                 // the same for every lane of the warp
+  ZK_NOUNROLL for (uint32_t i = 0; i < trips + 5; i++) {
     Xyzz<F> o;
-    o.X = warp_shfl<ZK_SHFL_DOWN>(acc.X, off); o.Y = warp_shfl<ZK_SHFL_DOWN>(acc.Y, off);
-    o.ZZ = warp_shfl<ZK_SHFL_DOWN>(acc.ZZ, off); o.ZZZ = warp_shfl<ZK_SHFL_DOWN>(acc.ZZZ, off);
-    xyzz_add(acc, o);
+    if (i < trips) {
+      const uint32_t g = i * 32 + lane;
+      if (g < n_items) o = (g == 0 && first_src) ? *first_src : src[g];
+      else o = Xyzz<F>::infinity();
+    } else {
+      const uint32_t off = 16u >> (i - trips);
+      o.X = warp_shfl<ZK_SHFL_DOWN>(acc.X, off); o.Y = warp_shfl<ZK_SHFL_DOWN>(acc.Y, off);
+      o.ZZ = warp_shfl<ZK_SHFL_DOWN>(acc.ZZ, off); o.ZZZ = warp_shfl<ZK_SHFL_DOWN>(acc.ZZZ, off);
+    }
+    xyzz_add_hot(acc, o);
   }
   if (lane == 0) { if (phase == 0) hsum[warp] = acc; else buckets[id] = acc; }
 }
@@ -767,7 +778,7 @@ ZK_GLOBAL void k_reduce_bits_level(const Xyzz<F>* __restrict__ main_in, const Xy
   }
   Xyzz<F> acc = Xyzz<F>::infinity();
   for (uint32_t j = 0; j < L; j++)
-    if (bit == 0xFFFFFFFFu || ((j >> bit) & 1u)) xyzz_add(acc, src[j]);
+    if (bit == 0xFFFFFFFFu || ((j >> bit) & 1u)) xyzz_add_hot(acc, src[j]);   // latency-bound: overlapping products
   *dst = acc;
 }
 // main: [rows] (Y_all), pool: [n_bits][rows] (Y_b): out[row] = Y_all + sum_b 2^b Y_b by Horner from the top bit
@@ -777,11 +788,10 @@ ZK_GLOBAL void k_reduce_bits_final(const Xyzz<F>* __restrict__ main_in, const Xy
   size_t row = ZK_TID;
   if (row >= rows) return;
   Xyzz<F> z = Xyzz<F>::infinity();
-  for (int b = (int)n_bits - 1; b >= 0; b--) {
-    z = xyzz_dbl(z);
-    xyzz_add(z, pool[(size_t)b * rows + row]);
+  ZK_NOUNROLL for (int b = (int)n_bits - 1; b >= -1; b--) {      // b = -1: the unweighted term (one addition site for all of them)
+    if (b >= 0) z = xyzz_dbl_hot(z);
+    xyzz_add_hot(z, b >= 0 ? pool[(size_t)b * rows + row] : main_in[row]);
   }
-  xyzz_add(z, main_in[row]);
   out[row] = z;
 }
 // pass 6: Horner over the windows, one thread per proof: out[b] = sum_j 2^(c*j) * win[b][j]

@@ -7,7 +7,10 @@
 // ms): S = 24: 3 676 (192.0 / 29.2), 32: 3 700 (194.8 / 24.1), 40: 3 714, 48: 3 729, 64: 3 737 (200.8 / 15.0), 96: 3 698, 128: 3 668
 // (208.4 / 12.3).  Short chunks make more of the additions free (the first entry of every run is a copy) but leave more partial sums
 // to the fix-up, whose full additions cost 1.4 mixed ones at half the lane efficiency.
-uint32_t accumulate_chunk() { uint32_t S = env_u32("ZKFL_MSM_CHUNK", 64); return S < 4 ? 4 : S; }
+// By the size of the whole sort (`entries` = rows x list capacity): small jobs need the threads more than the cheaper fix-up -- a
+// single sgd_verified proof (202 k entries) makes 6 k threads at 32 and runs 5.9 ms against 6.7 ms at 64 -- while from a 2^20-domain
+// proof or a 2^20-point MSM on (15 M entries) 64 is at least as good (22.0 against 22.4 ms; 3.71 ms both ways).
+uint32_t accumulate_chunk(size_t entries) { uint32_t S = env_u32("ZKFL_MSM_CHUNK", entries >= ((size_t)8 << 20) ? 64 : 32); return S < 4 ? 4 : S; }
 // shared = all windows of a proof accumulate into ONE bucket set (bases table precomputed with the window shifts)
 MsmShape msm_shape(uint32_t m, uint32_t B, bool shared, uint32_t force_c, uint32_t c_cap) {
   uint32_t best_c = 4; double best = 1e300;
@@ -32,7 +35,7 @@ MsmShape msm_shape(uint32_t m, uint32_t B, bool shared, uint32_t force_c, uint32
   // warps per scheduler on average (profiles/r01_ncu_full_k_msm_accumulate_affine.csv), so the XYZZ kernel stays the default.
   // ZKFL_MSM_AFFINE = 0 / unset: never, 1: always, 2: by size (needs K*S sorted entries per thread to fill the GPU).
   const uint32_t mode = env_u32("ZKFL_MSM_AFFINE", 0);
-  uint32_t S = accumulate_chunk(), ls = 0;
+  uint32_t S = accumulate_chunk((size_t)B * s.R * s.cap), ls = 0;
   while ((1u << ls) < S) ls++;
   const double threads = (double)B * s.R * s.cap / ((double)(1u << ls) * affine_slots());
   if (mode == 1 || (mode != 0 && shared && threads >= 148.0 * 512.0)) {

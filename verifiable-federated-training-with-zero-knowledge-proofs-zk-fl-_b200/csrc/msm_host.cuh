@@ -31,7 +31,7 @@ template <class F>
 int msm_accumulate(zkfl_ctx* c, const Affine<F>* bases, const MsmShape& s, int slot, const char* tag, int gen) {
   size_t rows = (size_t)s.B * s.R;
   TRY(c->buckets[slot].reserve(rows * s.nb * sizeof(Xyzz<F>)));
-  const uint32_t S = s.lsS ? (1u << s.lsS) : accumulate_chunk(), cpr = (s.cap + S - 1) / S;
+  const uint32_t S = s.lsS ? (1u << s.lsS) : accumulate_chunk(rows * s.cap), cpr = (s.cap + S - 1) / S;
   TRY(c->head[slot].reserve(rows * cpr * sizeof(Xyzz<F>)));
   TRY(c->tail[slot].reserve(rows * cpr * sizeof(Xyzz<F>)));
   const uint32_t* offsets = c->offsets[gen].as<uint32_t>();
@@ -84,7 +84,10 @@ int msm_accumulate(zkfl_ctx* c, const Affine<F>* bases, const MsmShape& s, int s
       CU(cudaMemsetAsync(fq, 0, 16, c->stream));
     }
     const bool bound = env_u32("ZKFL_FIXUP_BOUND", 1) != 0;
-    if (bound)
+    if (heavy)      // few rows: the latency form (inlined, overlapping products)
+      ZK_LAUNCH((k_msm_fixup<F, 2>), rows * s.nb, 128, c->stream, offsets, counts, s, S, cpr, (const Xyzz<F>*)head, (const Xyzz<F>*)tail,
+                c->buckets[slot].as<Xyzz<F>>(), heavy_span, heavy_cap, heavy, fq, (uint32_t)q_cap);
+    else if (bound)
       ZK_LAUNCH((k_msm_fixup<F, 1>), rows * s.nb, 128, c->stream, offsets, counts, s, S, cpr, (const Xyzz<F>*)head, (const Xyzz<F>*)tail,
                 c->buckets[slot].as<Xyzz<F>>(), heavy_span, heavy_cap, heavy, fq, (uint32_t)q_cap);
     else

@@ -29,7 +29,7 @@ static inline void zk_atomic_min_u32(uint32_t* p, uint32_t v) {
 #endif
 #if defined(__CUDACC__) && !defined(ZKFL_EMUL)
 #define ZK_ACC_BOUNDS(F) __launch_bounds__(128, sizeof(F) > 32 ? ZKFL_G2_MIN_CTAS : 4)
-#define ZK_FIX_BOUNDS(F, BOUND) __launch_bounds__(128, (BOUND) ? (sizeof(F) > 32 ? 3 : 4) : 1)
+#define ZK_FIX_BOUNDS(F, BOUND) __launch_bounds__(128, (BOUND) == 1 ? (sizeof(F) > 32 ? 3 : 4) : 1)   // BOUND 2: few rows, inlined products, no cap
 #define ZK_LVL_BOUNDS(F, BOUND) __launch_bounds__(64, (BOUND) ? (sizeof(F) > 32 ? 6 : 8) : 1)
 #else
 #define ZK_ACC_BOUNDS(F)
