@@ -70,7 +70,7 @@ struct zkfl_ctx {
   DevBuf counts[3], offsets[3], cursors, chunk_sums, sorted[3], skey;   // sorted lists per sort too: the next sort runs on its own stream while the previous lists are accumulated
   DevBuf head[5], tail[5];   // chunk partials per MSM slot (read by that slot's reduction on its side stream)
   DevBuf fixq;               // large batches: ids of the buckets cut once / more than once (k_msm_fixup -> k_msm_fixup_apply)
-  DevBuf heavy;              // heavy buckets of the current fix-up: [slots used | records (bucket, segment, segments, first slot)] + segment sums
+  DevBuf heavy[5];            // heavy buckets of the current fix-up: [slots used | records (bucket, segment, segments, first slot)] + segment sums
   DevBuf v_ic, v_pub, v_proofs, v_t, v_g1, v_g2, v_flags, v_f, v_halves, v_ok;   // batch verifier
   DevBuf v_lines, v_rho, v_cps, v_sum[2], v_s, v_spart, v_tmul, v_sub, v_tree[2], v_misc;   // lane-cooperative / batched (RLC) verifier
   DevBuf aff_acc, aff_pre;   // batch-affine accumulation: running affine sums and prefix products, [slot group][lane]
@@ -190,7 +190,7 @@ int msm_sort_reserve(zkfl_ctx* c, const MsmShape& s, int gen);   // the allocati
 int msm_range_mask(zkfl_ctx* c, const uint8_t* base_skip, uint32_t m, uint32_t lo, uint32_t hi, uint8_t* out);
 bool reduce_deep(const MsmShape& s);
 int msm_reserve_reduce(zkfl_ctx* c, const MsmShape& s, int slot, size_t elem);
-template <class F> int msm_accumulate(zkfl_ctx* c, const Affine<F>* bases, const MsmShape& s, int slot, const char* tag, int gen = 0);
+template <class F> int msm_accumulate(zkfl_ctx* c, const Affine<F>* bases, const MsmShape& s, int slot, const char* tag, int gen = 0, cudaStream_t stream = nullptr);
 template <class F> int msm_reduce(zkfl_ctx* c, const MsmShape& s, int slot, Xyzz<F>* out, cudaStream_t stream, const char* tag, int gen = 0);
 template <class F> int msm_run(zkfl_ctx* c, const Affine<F>* bases, const MsmShape& s, Xyzz<F>* out, const char* acc_tag, const char* red_tag);
 template <class F> int msm_precompute_windows(zkfl_ctx* c, const Affine<F>* raw, uint32_t cnt, uint32_t cw, uint32_t W, Affine<F>* table);

@@ -6,20 +6,20 @@
 static inline uint32_t affine_slots() { uint32_t K = env_u32("ZKFL_MSM_AFFINE_K", 64); return K < 1 ? 1 : (K > 4096 ? 4096 : K); }   // chunks per thread
 
 // the operand-file form of the G2 accumulation (k_msm_accumulate_chunks_g2f): 9 Fq2 slots per thread in dynamic shared memory
-static inline int msm_launch_g2f(zkfl_ctx* c, const void* bases, const uint32_t* sorted, const uint32_t* offsets, const uint32_t* counts,
-                                 const MsmShape& s, uint32_t S, uint32_t cpr, void* buckets, void* head, void* tail) {
+static inline int msm_launch_g2f(zkfl_ctx* c, cudaStream_t stream, const void* bases, const uint32_t* sorted, const uint32_t* offsets,
+                                 const uint32_t* counts, const MsmShape& s, uint32_t S, uint32_t cpr, void* buckets, void* head, void* tail) {
   const size_t total = (size_t)s.B * s.R * cpr;
   if (!total) return 0;
 #ifndef ZKFL_EMUL
   const unsigned block = 128;
   const size_t smem = (size_t)G2F_SLOTS * 64 * block;
   if (!c->g2f_attr) { CU(cudaFuncSetAttribute(k_msm_accumulate_chunks_g2f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); c->g2f_attr = true; }
-  k_msm_accumulate_chunks_g2f<<<(unsigned)((total + block - 1) / block), block, smem, c->stream>>>(
+  k_msm_accumulate_chunks_g2f<<<(unsigned)((total + block - 1) / block), block, smem, stream>>>(
       (const G2Affine*)bases, sorted, offsets, counts, s, S, cpr, (G2Xyzz*)buckets, (G2Xyzz*)head, (G2Xyzz*)tail);
   zkrt::note_launch("k_msm_accumulate_chunks_g2f");
-  if (zkrt::debug_sync()) zkrt::debug_check("k_msm_accumulate_chunks_g2f", c->stream);
+  if (zkrt::debug_sync()) zkrt::debug_check("k_msm_accumulate_chunks_g2f", stream);
 #else
-  ZK_LAUNCH(k_msm_accumulate_chunks_g2f, total, 128, c->stream, (const G2Affine*)bases, sorted, offsets, counts, s, S, cpr, (G2Xyzz*)buckets,
+  ZK_LAUNCH(k_msm_accumulate_chunks_g2f, total, 128, stream, (const G2Affine*)bases, sorted, offsets, counts, s, S, cpr, (G2Xyzz*)buckets,
             (G2Xyzz*)head, (G2Xyzz*)tail);
 #endif
   CU(cudaGetLastError());
@@ -28,7 +28,8 @@ static inline int msm_launch_g2f(zkfl_ctx* c, const void* bases, const uint32_t*
 // bucket accumulation of one MSM (slot = which of the five buffer sets) and the fix-up of the buckets cut by chunk borders, on the
 // main stream; uses the lists left by msm_sort(gen).
 template <class F>
-int msm_accumulate(zkfl_ctx* c, const Affine<F>* bases, const MsmShape& s, int slot, const char* tag, int gen) {
+int msm_accumulate(zkfl_ctx* c, const Affine<F>* bases, const MsmShape& s, int slot, const char* tag, int gen, cudaStream_t stream) {
+  if (!stream) stream = c->stream;
   size_t rows = (size_t)s.B * s.R;
   TRY(c->buckets[slot].reserve(rows * s.nb * sizeof(Xyzz<F>)));
   const uint32_t S = s.lsS ? (1u << s.lsS) : accumulate_chunk(rows * s.cap), cpr = (s.cap + S - 1) / S;
@@ -44,20 +45,20 @@ int msm_accumulate(zkfl_ctx* c, const Affine<F>* bases, const MsmShape& s, int s
     if ((cpr >> 5) % K != 0 || rows >= 0xFFFFFFFFull) return fail(ZKFL_ERR_ARG, "batch-affine accumulation: bad list geometry");
     TRY(c->aff_acc.reserve(n_groups * 32 * sizeof(Affine<F>)));
     TRY(c->aff_pre.reserve(n_groups * 32 * sizeof(F)));
-    Stage st(c, tag);
-    ZK_LAUNCH(k_msm_accumulate_affine<F>, n_groups / K * 32, 128, c->stream, bases, c->sorted[gen].as<uint32_t>(),
+    Stage st(c, tag, stream);
+    ZK_LAUNCH(k_msm_accumulate_affine<F>, n_groups / K * 32, 128, stream, bases, c->sorted[gen].as<uint32_t>(),
               c->skey.as<zk_key_t>(), offsets, counts, s, K, (uint32_t)rows,
               c->aff_acc.as<Affine<F>>(), c->aff_pre.as<F>(), c->buckets[slot].as<Xyzz<F>>(), head, tail);
   } else if (sizeof(F) > 32 && env_u32("ZKFL_G2_OPERAND_FILE", 0)) {   // opt-in: measured no faster, see k_msm.cuh
-    Stage st(c, tag);
-    TRY(msm_launch_g2f(c, (const void*)bases, c->sorted[gen].as<uint32_t>(), offsets, counts, s, S, cpr, c->buckets[slot].p, (void*)head, (void*)tail));
+    Stage st(c, tag, stream);
+    TRY(msm_launch_g2f(c, stream, (const void*)bases, c->sorted[gen].as<uint32_t>(), offsets, counts, s, S, cpr, c->buckets[slot].p, (void*)head, (void*)tail));
   } else {
-    Stage st(c, tag);
-    ZK_LAUNCH(k_msm_accumulate_chunks<F>, rows * cpr, 128, c->stream, bases, c->sorted[gen].as<uint32_t>(), (const zk_key_t*)nullptr,
+    Stage st(c, tag, stream);
+    ZK_LAUNCH(k_msm_accumulate_chunks<F>, rows * cpr, 128, stream, bases, c->sorted[gen].as<uint32_t>(), (const zk_key_t*)nullptr,
               offsets, counts, s, S, cpr, c->buckets[slot].as<Xyzz<F>>(), head, tail);
   }
   {
-    Stage st(c, "msm_fixup");
+    Stage st(c, "msm_fixup", stream);
     // heavy buckets (runs over more than 16 chunks) go to warps, one per segment of 256 chunks; the queue lives in the context:
     // [slots used | heavy_cap records of four words], then heavy_cap segment sums.  Measured on B200 (2^20-domain proof / 2^20-point
     // MSM): span 16, segments of 256 -> fix-up 2.9 / 0.19 ms; span 4, segments of 64 (every bucket of such a proof spans ~7 chunks
@@ -68,10 +69,10 @@ int msm_accumulate(zkfl_ctx* c, const Affine<F>* bases, const MsmShape& s, int s
 #ifndef ZKFL_EMUL
     if (env_u32("ZKFL_FIXUP_HEAVY", 1) && rows <= 64 && rows * s.nb < 0xFFFFFFFFull) {   // few rows: single proofs, split proofs
       const size_t qbytes = ((size_t)heavy_cap + 1) * 16;
-      TRY(c->heavy.reserve(qbytes + (size_t)heavy_cap * sizeof(Xyzz<Fq2>)));
-      heavy = c->heavy.as<uint32_t>();
-      hsum = (Xyzz<F>*)((uint8_t*)c->heavy.p + qbytes);
-      CU(cudaMemsetAsync(heavy, 0, qbytes, c->stream));
+      TRY(c->heavy[slot].reserve(qbytes + (size_t)heavy_cap * sizeof(Xyzz<Fq2>)));
+      heavy = c->heavy[slot].as<uint32_t>();
+      hsum = (Xyzz<F>*)((uint8_t*)c->heavy[slot].p + qbytes);
+      CU(cudaMemsetAsync(heavy, 0, qbytes, stream));
     }
 #endif
     // large batches: cut buckets are queued by how often they are cut and summed densely (k_msm_fixup_apply); at most one
@@ -81,35 +82,35 @@ int msm_accumulate(zkfl_ctx* c, const Affine<F>* bases, const MsmShape& s, int s
     if (!heavy && rows >= env_u32("ZKFL_FIXUP_QUEUE_MIN_ROWS", 65) && rows * s.nb < 0xFFFFFFFFull && q_cap < 0xFFFFFFFFull && env_u32("ZKFL_FIXUP_QUEUE", 1)) {
       TRY(c->fixq.reserve((4 + 2 * q_cap) * 4));
       fq = c->fixq.as<uint32_t>();
-      CU(cudaMemsetAsync(fq, 0, 16, c->stream));
+      CU(cudaMemsetAsync(fq, 0, 16, stream));
     }
     const bool bound = env_u32("ZKFL_FIXUP_BOUND", 1) != 0;
     if (heavy)      // few rows: the latency form (inlined, overlapping products)
-      ZK_LAUNCH((k_msm_fixup<F, 2>), rows * s.nb, 128, c->stream, offsets, counts, s, S, cpr, (const Xyzz<F>*)head, (const Xyzz<F>*)tail,
+      ZK_LAUNCH((k_msm_fixup<F, 2>), rows * s.nb, 128, stream, offsets, counts, s, S, cpr, (const Xyzz<F>*)head, (const Xyzz<F>*)tail,
                 c->buckets[slot].as<Xyzz<F>>(), heavy_span, heavy_cap, heavy, fq, (uint32_t)q_cap);
     else if (bound)
-      ZK_LAUNCH((k_msm_fixup<F, 1>), rows * s.nb, 128, c->stream, offsets, counts, s, S, cpr, (const Xyzz<F>*)head, (const Xyzz<F>*)tail,
+      ZK_LAUNCH((k_msm_fixup<F, 1>), rows * s.nb, 128, stream, offsets, counts, s, S, cpr, (const Xyzz<F>*)head, (const Xyzz<F>*)tail,
                 c->buckets[slot].as<Xyzz<F>>(), heavy_span, heavy_cap, heavy, fq, (uint32_t)q_cap);
     else
-      ZK_LAUNCH((k_msm_fixup<F, 0>), rows * s.nb, 128, c->stream, offsets, counts, s, S, cpr, (const Xyzz<F>*)head, (const Xyzz<F>*)tail,
+      ZK_LAUNCH((k_msm_fixup<F, 0>), rows * s.nb, 128, stream, offsets, counts, s, S, cpr, (const Xyzz<F>*)head, (const Xyzz<F>*)tail,
                 c->buckets[slot].as<Xyzz<F>>(), heavy_span, heavy_cap, heavy, fq, (uint32_t)q_cap);
     if (fq)
       for (uint32_t which = 0; which < 2; which++) {
         // the queue lengths are only known on the device: a grid for the worst case, unused threads exit at once
         if (bound)
-          ZK_LAUNCH((k_msm_fixup_apply<F, 1>), q_cap, 128, c->stream, offsets, counts, s, S, cpr, (const Xyzz<F>*)head, (const Xyzz<F>*)tail,
+          ZK_LAUNCH((k_msm_fixup_apply<F, 1>), q_cap, 128, stream, offsets, counts, s, S, cpr, (const Xyzz<F>*)head, (const Xyzz<F>*)tail,
                     c->buckets[slot].as<Xyzz<F>>(), (const uint32_t*)fq, (uint32_t)q_cap, which);
         else
-          ZK_LAUNCH((k_msm_fixup_apply<F, 0>), q_cap, 128, c->stream, offsets, counts, s, S, cpr, (const Xyzz<F>*)head, (const Xyzz<F>*)tail,
+          ZK_LAUNCH((k_msm_fixup_apply<F, 0>), q_cap, 128, stream, offsets, counts, s, S, cpr, (const Xyzz<F>*)head, (const Xyzz<F>*)tail,
                     c->buckets[slot].as<Xyzz<F>>(), (const uint32_t*)fq, (uint32_t)q_cap, which);
       }
 #ifndef ZKFL_EMUL
     // the number of queued segments is only known on the device: a fixed grid of warps (unused slots exit at once) keeps the stream
     // free of host round trips; large batches never queue (their rows are small circuits) and skip the launches
     if (heavy) {
-      ZK_LAUNCH(k_msm_fixup_heavy<F>, (size_t)heavy_cap * 32, 128, c->stream, offsets, counts, s, S, cpr, (const Xyzz<F>*)head, (const Xyzz<F>*)tail,
+      ZK_LAUNCH(k_msm_fixup_heavy<F>, (size_t)heavy_cap * 32, 128, stream, offsets, counts, s, S, cpr, (const Xyzz<F>*)head, (const Xyzz<F>*)tail,
                 c->buckets[slot].as<Xyzz<F>>(), heavy_cap, (const uint32_t*)heavy, hsum, 0);
-      ZK_LAUNCH(k_msm_fixup_heavy<F>, (size_t)heavy_cap * 32, 128, c->stream, offsets, counts, s, S, cpr, (const Xyzz<F>*)head, (const Xyzz<F>*)tail,
+      ZK_LAUNCH(k_msm_fixup_heavy<F>, (size_t)heavy_cap * 32, 128, stream, offsets, counts, s, S, cpr, (const Xyzz<F>*)head, (const Xyzz<F>*)tail,
                 c->buckets[slot].as<Xyzz<F>>(), heavy_cap, (const uint32_t*)heavy, hsum, 1);
     }
 #endif
@@ -226,7 +227,7 @@ int msm_point_scale(zkfl_ctx* c, const uint8_t* pts, const uint8_t* scalar, size
 }
 
 #define ZK_INSTANTIATE_MSM(F)                                                                                              \
-  template int msm_accumulate<F>(zkfl_ctx*, const Affine<F>*, const MsmShape&, int, const char*, int);                       \
+  template int msm_accumulate<F>(zkfl_ctx*, const Affine<F>*, const MsmShape&, int, const char*, int, cudaStream_t);                       \
   template int msm_reduce<F>(zkfl_ctx*, const MsmShape&, int, Xyzz<F>*, cudaStream_t, const char*, int);                     \
   template int msm_run<F>(zkfl_ctx*, const Affine<F>*, const MsmShape&, Xyzz<F>*, const char*, const char*);               \
   template int msm_precompute_windows<F>(zkfl_ctx*, const Affine<F>*, uint32_t, uint32_t, uint32_t, Affine<F>*);           \

@@ -126,63 +126,80 @@ static int prove_from_device_witness(zkfl_ctx* c, const zkfl_zkey* z, const Fr* 
     TRY(msm_range_mask(c, nullptr, n, hlo, hhi, c->mask_h.as<uint8_t>()));
     skip_w = c->mask_w.as<uint8_t>(); skip_wb = c->mask_wb.as<uint8_t>(); skip_h = c->mask_h.as<uint8_t>();
   }
-  // OPT-IN (ZKFL_SORT_OVERLAP=1): the sorts (bound by L2 atomics and scattered stores) on their own stream beside the product-bound
-  // stages -- the two witness sorts beside A.w / B.w and the NTTs, the H sort beside the accumulation of the witness MSMs; each sort
-  // has its own list / counts / offsets set for that.  MEASURED AND REJECTED as the default on B200 (1024 sgd_verified proofs per
-  // step): 3 796 proofs/s against 3 822 in the serial order -- the accumulation already fills every SM (4 CTAs x 128 registers), so
-  // the sort CTAs only take residency from it and every co-running stage stretches (NTT 15.1 -> 20.5 ms, fix-up 9.3 -> 18.6 ms,
-  // accumulation 130 -> 133 ms, sorts 19 -> 58 ms of stream time).
-  const bool overlap = sw.lsS == 0 && sh.lsS == 0 && env_u32("ZKFL_SORT_OVERLAP", 0) != 0;
+  // FEW ROWS (single proofs, the per-rank share of a split proof; ZKFL_MSM_CONCURRENT=0 turns it off): no kernel fills the GPU and
+  // everything is latency -- the five MSMs run side by side, each whole (accumulate, fix-up, reduce) on its own stream: the witness
+  // sorts come first (they need only the witness), A, C, B1, B2 start behind them, and A.w / B.w, the NTTs and the H sort run on the
+  // main stream meanwhile; H follows on its stream.  The heavy-bucket queues are per MSM for that (zkfl_ctx::heavy[slot]).
+  const bool concurrent = B <= 64 && sw.lsS == 0 && sh.lsS == 0 && env_u32("ZKFL_MSM_CONCURRENT", 1) != 0;
+  // OPT-IN (ZKFL_SORT_OVERLAP=1, large batches): the sorts (bound by L2 atomics and scattered stores) on their own stream beside the
+  // product-bound stages -- the two witness sorts beside A.w / B.w and the NTTs, the H sort beside the accumulation of the witness
+  // MSMs; each sort has its own list / counts / offsets set for that.  MEASURED AND REJECTED as the default on B200 (1024
+  // sgd_verified proofs per step): 3 796 proofs/s against 3 822 in the serial order -- the accumulation already fills every SM
+  // (4 CTAs x 128 registers), so the sort CTAs only take residency from it and every co-running stage stretches (NTT 15.1 -> 20.5 ms,
+  // fix-up 9.3 -> 18.6 ms, accumulation 130 -> 133 ms, sorts 19 -> 58 ms of stream time).
+  const bool overlap = !concurrent && sw.lsS == 0 && sh.lsS == 0 && env_u32("ZKFL_SORT_OVERLAP", 0) != 0;
   cudaStream_t ss = overlap ? c->sort_stream : c->stream;
   auto sort = [&](const char* tag, const Fr* sc, const uint8_t* skip, const MsmShape& shp, int gen) -> int {
     { Stage st(c, tag, ss); TRY(msm_sort(c, sc, skip, shp, gen, ss)); }
-    if (overlap) CU(cudaEventRecord(c->ev_sort[gen], ss));
+    if (overlap || concurrent) CU(cudaEventRecord(c->ev_sort[gen], ss));
     return 0;
   };
   auto sorted_ready = [&](int gen) -> int { if (overlap) CU(cudaStreamWaitEvent(c->stream, c->ev_sort[gen], 0)); return 0; };
-  if (overlap) {
-    CU(cudaEventRecord(c->ev_in, c->stream));            // witness (and range masks) complete; earlier passes' accumulations too
-    CU(cudaStreamWaitEvent(ss, c->ev_in, 0));
+  // one MSM: serial order -- accumulate + fix-up on the main stream, the latency-bound reduction on the slot's side stream;
+  // concurrent -- all three on the side stream, behind the sort of its lists
+  auto msm_g1 = [&](int slot, int gen, const G1Affine* bases, const MsmShape& shp, G1Xyzz* out) -> int {
+    cudaStream_t as = concurrent ? c->side[slot] : c->stream;
+    if (concurrent) CU(cudaStreamWaitEvent(as, c->ev_sort[gen], 0));
+    TRY(msm_accumulate<Fq>(c, bases, shp, slot, "msm_acc_g1", gen, as));
+    if (!concurrent) { CU(cudaEventRecord(c->ev_acc[slot], c->stream)); CU(cudaStreamWaitEvent(c->side[slot], c->ev_acc[slot], 0)); }
+    TRY(msm_reduce<Fq>(c, shp, slot, out, c->side[slot], "msm_reduce_g1", gen));
+    CU(cudaEventRecord(c->ev_red[slot], c->side[slot]));
+    return 0;
+  };
+  auto msm_g2 = [&](int slot, int gen, const G2Affine* bases, const MsmShape& shp, G2Xyzz* out) -> int {
+    cudaStream_t as = concurrent ? c->side[slot] : c->stream;
+    if (concurrent) CU(cudaStreamWaitEvent(as, c->ev_sort[gen], 0));
+    TRY(msm_accumulate<Fq2>(c, bases, shp, slot, "msm_acc_g2", gen, as));
+    if (!concurrent) { CU(cudaEventRecord(c->ev_acc[slot], c->stream)); CU(cudaStreamWaitEvent(c->side[slot], c->ev_acc[slot], 0)); }
+    TRY(msm_reduce<Fq2>(c, shp, slot, out, c->side[slot], "msm_reduce_g2", gen));
+    CU(cudaEventRecord(c->ev_red[slot], c->side[slot]));
+    return 0;
+  };
+  if (concurrent) {
     TRY(sort("msm_sort_w", w, skip_w, sw, 0));
     TRY(sort("msm_sort_w", w, skip_wb, sw, 1));
-  }
-  TRY(run_h_poly(c, z, B, check));
-  if (overlap) {
-    CU(cudaEventRecord(c->ev_hsc, c->stream));
-    CU(cudaStreamWaitEvent(ss, c->ev_hsc, 0));
+    TRY(msm_g1(0, 0, z->pA.as<G1Affine>(), sw, r1));
+    TRY(msm_g1(1, 0, z->pC.as<G1Affine>(), sw, r1 + 2 * (size_t)B));
+    TRY(msm_g2(4, 1, z->pB2.as<G2Affine>(), sw, r2));          // the longest of the four first
+    TRY(msm_g1(2, 1, z->pB1.as<G1Affine>(), sw, r1 + B));
+    TRY(run_h_poly(c, z, B, check));
     TRY(sort("msm_sort_h", c->hsc.as<Fr>(), skip_h, sh, 2));
+    TRY(msm_g1(3, 2, z->pH.as<G1Affine>(), sh, r1 + 3 * (size_t)B));
+  } else {
+    if (overlap) {
+      CU(cudaEventRecord(c->ev_in, c->stream));            // witness (and range masks) complete; earlier passes' accumulations too
+      CU(cudaStreamWaitEvent(ss, c->ev_in, 0));
+      TRY(sort("msm_sort_w", w, skip_w, sw, 0));
+      TRY(sort("msm_sort_w", w, skip_wb, sw, 1));
+    }
+    TRY(run_h_poly(c, z, B, check));
+    if (overlap) {
+      CU(cudaEventRecord(c->ev_hsc, c->stream));
+      CU(cudaStreamWaitEvent(ss, c->ev_hsc, 0));
+      TRY(sort("msm_sort_h", c->hsc.as<Fr>(), skip_h, sh, 2));
+    }
+    if (!overlap) TRY(sort("msm_sort_w", w, skip_w, sw, 0));
+    TRY(sorted_ready(0));
+    TRY(msm_g1(0, 0, z->pA.as<G1Affine>(), sw, r1));
+    TRY(msm_g1(1, 0, z->pC.as<G1Affine>(), sw, r1 + 2 * (size_t)B));
+    if (!overlap) TRY(sort("msm_sort_w", w, skip_wb, sw, 1));
+    TRY(sorted_ready(1));
+    TRY(msm_g1(2, 1, z->pB1.as<G1Affine>(), sw, r1 + B));
+    TRY(msm_g2(4, 1, z->pB2.as<G2Affine>(), sw, r2));
+    if (!overlap) TRY(sort("msm_sort_h", c->hsc.as<Fr>(), skip_h, sh, 2));
+    TRY(sorted_ready(2));
+    TRY(msm_g1(3, 2, z->pH.as<G1Affine>(), sh, r1 + 3 * (size_t)B));
   }
-  if (!overlap) TRY(sort("msm_sort_w", w, skip_w, sw, 0));
-  TRY(sorted_ready(0));
-  TRY(msm_accumulate<Fq>(c, z->pA.as<G1Affine>(), sw, 0, "msm_acc_g1", 0));
-  CU(cudaEventRecord(c->ev_acc[0], c->stream));
-  CU(cudaStreamWaitEvent(c->side[0], c->ev_acc[0], 0));
-  TRY(msm_reduce<Fq>(c, sw, 0, r1, c->side[0], "msm_reduce_g1", 0));
-  CU(cudaEventRecord(c->ev_red[0], c->side[0]));
-  TRY(msm_accumulate<Fq>(c, z->pC.as<G1Affine>(), sw, 1, "msm_acc_g1", 0));
-  CU(cudaEventRecord(c->ev_acc[1], c->stream));
-  CU(cudaStreamWaitEvent(c->side[1], c->ev_acc[1], 0));
-  TRY(msm_reduce<Fq>(c, sw, 1, r1 + 2 * (size_t)B, c->side[1], "msm_reduce_g1", 0));
-  CU(cudaEventRecord(c->ev_red[1], c->side[1]));
-  if (!overlap) TRY(sort("msm_sort_w", w, skip_wb, sw, 1));
-  TRY(sorted_ready(1));
-  TRY(msm_accumulate<Fq>(c, z->pB1.as<G1Affine>(), sw, 2, "msm_acc_g1", 1));
-  CU(cudaEventRecord(c->ev_acc[2], c->stream));
-  CU(cudaStreamWaitEvent(c->side[2], c->ev_acc[2], 0));
-  TRY(msm_reduce<Fq>(c, sw, 2, r1 + B, c->side[2], "msm_reduce_g1", 1));
-  CU(cudaEventRecord(c->ev_red[2], c->side[2]));
-  TRY(msm_accumulate<Fq2>(c, z->pB2.as<G2Affine>(), sw, 4, "msm_acc_g2", 1));
-  CU(cudaEventRecord(c->ev_acc[4], c->stream));
-  CU(cudaStreamWaitEvent(c->side[4], c->ev_acc[4], 0));
-  TRY(msm_reduce<Fq2>(c, sw, 4, r2, c->side[4], "msm_reduce_g2", 1));
-  CU(cudaEventRecord(c->ev_red[4], c->side[4]));
-  if (!overlap) TRY(sort("msm_sort_h", c->hsc.as<Fr>(), skip_h, sh, 2));
-  TRY(sorted_ready(2));
-  TRY(msm_accumulate<Fq>(c, z->pH.as<G1Affine>(), sh, 3, "msm_acc_g1", 2));
-  CU(cudaEventRecord(c->ev_acc[3], c->stream));
-  CU(cudaStreamWaitEvent(c->side[3], c->ev_acc[3], 0));
-  TRY(msm_reduce<Fq>(c, sh, 3, r1 + 3 * (size_t)B, c->side[3], "msm_reduce_g1", 2));
-  CU(cudaEventRecord(c->ev_red[3], c->side[3]));
   for (int i = 0; i < 5; i++) CU(cudaStreamWaitEvent(c->stream, c->ev_red[i], 0));
   if (!finalize) return 0;
   return finalize_from_sums(c, z, rs_dev, B);
