@@ -503,27 +503,6 @@ def main():
             p.close()
         split = bench_split(prover, torch, dist, rank, world, barrier, with_cpu=not args.no_cpu)
         log("split proof done" + (f": prove {split['prove_ms']:.1f} ms, full prove {split['full_prove_ms']:.1f} ms" if split else ""))
-    # ---- BASELINE configs[3]: the reference's whole round (tests/full_system_simulation.mjs:1244-1395) at 1 023 clients over the GPUs
-    # of this run: inputs from the GPU commitment pipeline, 3 x 1 023 proofs sharded b -> rank, batch verification and the masked
-    # aggregation on rank 0's GPU.  Second of two rounds (the first makes the three keys and allocates the workspaces).
-    full_round = None
-    if not args.no_round and args.workload == "proofs":
-        try:
-            from zkfl_b200 import simulation
-            cache = {}
-            for p in provers[1:]:
-                p.close()
-            simulation.run_round(prover, 1023, cache=cache, setup_seed=b"zkfl-bench-round")
-            barrier()
-            rep = simulation.run_round(prover, 1023, cache=cache, setup_seed=b"zkfl-bench-round")
-            barrier()
-            if rep is not None:
-                full_round = {"clients": rep["clients"], "n_gpus": rep.get("n_gpus", world), "proofs": rep.get("proofs"),
-                              "verified": rep["verified"], "timing_s": {k: round(v, 4) for k, v in rep["timing"].items()},
-                              "note": "one round through the Python host API (simulation.run_round), wall clock on rank 0, inputs included"}
-        except Exception as e:            # a side measurement must never cost the headline line
-            full_round = {"error": f"{type(e).__name__}: {e}"}
-        log("full round done" + (f": {full_round['timing_s'].get('round_s')} s" if full_round and "timing_s" in full_round else ""))
     line = None
     if rank == 0:
         m, n, l = zkey.n_vars, zkey.domain, zkey.n_public
@@ -606,7 +585,7 @@ def main():
             "msm_g1_2pow20": msm,
             "split_proof": split,
             "verify_batch": verify,
-            "full_round_1023": full_round,
+            "full_round_1023": None,
             "cpu_baseline": cpu,
         }
         if args.workload == "split" and split is not None:
@@ -617,9 +596,52 @@ def main():
                     "e2e": {"value": split["full_prove_ms"], "unit": "ms", "h2d_bytes_per_step": 32 * circuit.n_inputs, "d2h_bytes_per_step": 256 + 32 * 6},
                     "gpu_launches": int(launches), "clocks": clk, "split_proof": split, "cpu_baseline": split.get("cpu_baseline"),
                     "roofline": line["roofline"], "proofs_per_s_line": {"value": value, "unit": UNIT}}
+    # ---- BASELINE configs[3]: the reference's whole round (tests/full_system_simulation.mjs:1244-1395) at 1 023 clients over the GPUs
+    # of this run: inputs from the GPU commitment pipeline, 3 x 1 023 proofs sharded b -> rank, batch verification and the masked
+    # aggregation on rank 0's GPU.  Second of two rounds (the first makes the three keys and allocates the workspaces).
+    # A SIDE measurement, made after the headline line is complete: it must never cost that line.  If a rank fails inside one of
+    # its collectives the others would wait for it forever, so every rank arms a watchdog that prints the line (rank 0) and leaves.
+    round_failed = False
+    if not args.no_round and args.workload == "proofs":
+        import threading
+
+        def _bail():
+            try:
+                if line is not None:
+                    line["full_round_1023"] = {"error": "timeout: the round did not finish in 300 s"}
+                    print(json.dumps(line), flush=True)
+            finally:
+                os._exit(0)
+        wd = threading.Timer(300.0, _bail)
+        wd.daemon = True
+        wd.start()
+        full_round = None
+        try:
+            from zkfl_b200 import simulation
+            cache = {}
+            for p in provers[1:]:
+                p.close()
+            simulation.run_round(prover, 1023, cache=cache, setup_seed=b"zkfl-bench-round")
+            barrier()
+            rep = simulation.run_round(prover, 1023, cache=cache, setup_seed=b"zkfl-bench-round")
+            barrier()
+            if rep is not None:
+                full_round = {"clients": rep["clients"], "n_gpus": rep.get("n_gpus", world), "proofs": rep.get("proofs"),
+                              "verified": rep["verified"], "timing_s": {k: round(v, 4) for k, v in rep["timing"].items()},
+                              "note": "one round through the Python host API (simulation.run_round), wall clock on rank 0, inputs included"}
+        except Exception as e:
+            full_round = {"error": f"{type(e).__name__}: {e}"}
+            round_failed = True
+        wd.cancel()
+        log("full round done" + (f": {full_round['timing_s'].get('round_s')} s" if full_round and "timing_s" in full_round else ""))
+        if line is not None:
+            line["full_round_1023"] = full_round
     if line is not None:
         print(json.dumps(line), flush=True)
         log("line printed")
+    if round_failed:          # the other ranks may be stuck in a collective of the failed side measurement: no barrier, just leave
+        sys.stdout.flush()
+        os._exit(0)
     barrier()
     if dist is not None:
         dist.destroy_process_group()

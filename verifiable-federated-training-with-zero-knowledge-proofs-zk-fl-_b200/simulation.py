@@ -46,22 +46,6 @@ def _setup(prover, name, cache, setup_seed: bytes | None = None):
     return cache[name]
 
 
-class _Lazy:
-    """a list of per-client circuit inputs built on demand: a rank of a multi-GPU round only builds its own shard"""
-
-    def __init__(self, n, make):
-        self.n, self.make = n, make
-
-    def __len__(self):
-        return self.n
-
-    def __getitem__(self, i):
-        return self.make(i)
-
-    def __iter__(self):
-        return (self.make(i) for i in range(self.n))
-
-
 def run_round(prover, n_clients: int = 3, seed: int = 12345, weights=None, verify: bool = True, cache: dict | None = None,
               setup_seed: bytes | None = None, gpu_inputs: bool = True) -> dict | None:
     """One round.  With a torch.distributed process group of G > 1 ranks (one per GPU) the proofs of every phase are sharded
@@ -87,14 +71,11 @@ def run_round(prover, n_clients: int = 3, seed: int = 12345, weights=None, verif
         if dist is not None:
             proofs, pubs = sharding.prove_independent(prover, circ, zkey, ins)  # constraint check inside every rank's pass
         else:
-            proofs, pubs = prover.full_prove(circ, zkey, list(ins))            # constraint check inside the pass; r, s from the OS like snarkjs
-        timing[name + "_s"] = time.perf_counter() - t                          # includes building this rank's circuit inputs
+            proofs, pubs = prover.full_prove(circ, zkey, ins)                  # constraint check inside the pass; r, s from the OS like snarkjs
+        timing[name + "_s"] = time.perf_counter() - t
         if rank != 0:
             return vk, None, None
-        t = time.perf_counter()
-        out = vk, [formats.proof_bytes_to_json(p) for p in proofs], [formats.publics_bytes_to_json(q) for q in pubs]
-        timing["json_s"] = timing.get("json_s", 0.0) + time.perf_counter() - t  # proof.json / public.json objects for the server's checks
-        return out
+        return vk, [formats.proof_bytes_to_json(p) for p in proofs], [formats.publics_bytes_to_json(q) for q in pubs]
 
     def verify_all(vk, sigs, proofs):
         if not verify:
@@ -105,7 +86,7 @@ def run_round(prover, n_clients: int = 3, seed: int = 12345, weights=None, verif
         return ok
 
     # phase 3: balance proofs; Server.verifyBalanceProof (:848-880)
-    vk, proofs, sigs = prove_phase("balance_unified", _Lazy(len(clients), lambda i: clients[i].balance_input()))
+    vk, proofs, sigs = prove_phase("balance_unified", [c.balance_input() for c in clients])
     balance_root = {}
     if rank == 0:
         valid = verify_all(vk, sigs, proofs)
@@ -116,7 +97,7 @@ def run_round(prover, n_clients: int = 3, seed: int = 12345, weights=None, verif
                 report["verified"]["balance"] += 1
 
     # phase 4: verified-gradient proofs; Server.verifyTrainingProof (:886-990)
-    vk, proofs, sigs = prove_phase("sgd_verified", _Lazy(len(clients), lambda i: clients[i].training_input(model)))
+    vk, proofs, sigs = prove_phase("sgd_verified", [c.training_input(model) for c in clients])
     trained = set()
     if rank == 0:
         valid = verify_all(vk, sigs, proofs)
@@ -135,7 +116,7 @@ def run_round(prover, n_clients: int = 3, seed: int = 12345, weights=None, verif
         base = 3 * ((c.id - 1) // 3)
         return [base + k for k in (1, 2, 3) if base + k != c.id]
 
-    vk, proofs, sigs = prove_phase("secure_masked_update", _Lazy(len(clients), lambda i: clients[i].secagg_input(peers_of(clients[i]))))
+    vk, proofs, sigs = prove_phase("secure_masked_update", [c.secagg_input(peers_of(c)) for c in clients])
     if rank != 0:
         return None
     accepted = []
