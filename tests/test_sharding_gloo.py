@@ -59,6 +59,50 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
+def _round_worker(rank, world, port, q):
+    for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+        sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import __graft_entry__ as ge
+        import zkfl_b200  # noqa: F401
+        from zkfl_b200 import simulation
+        from zkfl_b200.api import Prover
+        P = Prover(0, lib_path=ge.EMUL)
+        rep = simulation.run_round(P, 3, setup_seed=b"gloo-round")       # the reference's 3-client round, proofs sharded b -> rank
+        if rank == 0:
+            assert rep["verified"] == {"balance": 3, "training": 3, "secagg": 3} and rep["proofs"] == 9 and rep["n_gpus"] == world, rep
+            assert rep["aggregated_gradient"] == rep["expected_gradient"], rep       # masks cancel: the server recovers the mean gradient
+        else:
+            assert rep is None
+        q.put((rank, "ok"))
+    except Exception as e:  # surface the failure in the parent
+        import traceback
+        q.put((rank, traceback.format_exc() + repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_full_round():
+    """simulation.run_round over two ranks (what `bench.py`'s full_round_1023 section and `torchrun -m zkfl_b200.simulation` do on
+    GPUs): every phase's proofs sharded over the ranks, rank 0 verifies and aggregates, the other rank returns None, nobody waits."""
+    import __graft_entry__ as ge
+    ge.build_emul()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_round_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=900) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, "ok"), (1, "ok")], res
+
+
 def test_two_rank_sharding_and_split_msm():
     import __graft_entry__ as ge
     ge.build_emul()
