@@ -501,7 +501,7 @@ def main():
     if not args.no_split or args.workload == "split":
         for p in provers[1:]:
             p.close()
-        split = bench_split(prover, torch, dist, rank, world, barrier, with_cpu=not args.no_cpu)
+        split = bench_split(prover, torch, dist, rank, world, barrier, with_cpu=not args.no_cpu and world == 1)
         log("split proof done" + (f": prove {split['prove_ms']:.1f} ms, full prove {split['full_prove_ms']:.1f} ms" if split else ""))
     line = None
     if rank == 0:
@@ -525,8 +525,8 @@ def main():
         # reductions (side streams) and sorts (sort stream) overlap the product-bound stages of the main stream
         main_stream = sum(v["ms"] for k, v in prof.items() if not k.startswith(("msm_reduce", "msm_sort")))
         cpu = None
-        if not args.no_cpu:
-            # ---- CPU baseline (bounded sample, all host cores)
+        if not args.no_cpu and world == 1:
+            # ---- CPU baseline (bounded sample, all host cores; at N = 1 only: with more ranks the other processes hold the cores)
             ncores = len(os.sched_getaffinity(0))
             packs = [ins[i * 32 * circuit.n_inputs:(i + 1) * 32 * circuit.n_inputs] for i in range(min(B, 4))]
             sample = max(ncores, 4)
